@@ -1,0 +1,167 @@
+"""ctypes binding of the CPU oracle (oracle/libsgoracle.so) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` / ``--impl reference`` legs may
+import this module; the product package never does (see oracle/sg_oracle.c header).  PARITY UNPINNED:
+the reference ships no golden vectors for this path and MuJoCo is not installable here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ST_DIVERGED, ST_CON_FULL, ST_EFC_FULL, ST_UNSUPPORTED = 1, 2, 4, 8
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libsgoracle.so")
+    src = os.path.join(_HERE, "sg_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libsgoracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        P, D, I = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.sgo_model_load.restype = P
+        L.sgo_model_load.argtypes = [C.c_char_p, C.c_size_t]
+        L.sgo_model_free.argtypes = [P]
+        L.sgo_model_int.argtypes = [P, C.c_char_p]
+        L.sgo_world_create.restype = P
+        L.sgo_world_create.argtypes = [P]
+        L.sgo_world_free.argtypes = [P]
+        for f in ("sgo_set_jnt_stiffness", "sgo_set_tendon_stiffness", "sgo_set_dof_damping", "sgo_set_tendon_damping"):
+            getattr(L, f).argtypes = [P, C.c_int, C.c_double]
+        L.sgo_set_body_pos.argtypes = [P, C.c_int, D]
+        L.sgo_set_ctrl.argtypes = [P, D]
+        L.sgo_set_dense_solver.argtypes = [P, C.c_int]
+        L.sgo_set_geom_mask.argtypes = [P, I]
+        L.sgo_reset.argtypes = [P]
+        L.sgo_forward.argtypes = [P]
+        L.sgo_step.argtypes = [P]
+        L.sgo_status.argtypes = [P]
+        L.sgo_get_state.argtypes = [P, D, D, D, D]
+        L.sgo_set_state.argtypes = [P, D, D, D, D]
+        L.sgo_get_sensordata.argtypes = [P, D]
+        L.sgo_get_touch_mask.argtypes = [P]
+        L.sgo_get_int.argtypes = [P, C.c_char_p]
+        L.sgo_get_array.argtypes = [P, C.c_char_p, D, C.c_int]
+        L.sgo_episode.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, D, I]
+        L.sgo_last_step_flops.restype = C.c_double
+        L.sgo_last_step_flops.argtypes = [P]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+class OracleModel:
+    def __init__(self, blob: bytes):
+        self._L = lib()
+        self._blob = bytes(blob)
+        self.h = self._L.sgo_model_load(self._blob, len(self._blob))
+        if not self.h:
+            raise ValueError("oracle could not parse the model blob")
+        for k in ("nv", "nbody", "ngeom", "neq", "nu", "nsensordata", "ntendon", "njnt", "npair", "nsite", "nM"):
+            setattr(self, k, self._L.sgo_model_int(self.h, k.encode()))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self._L.sgo_model_free(self.h)
+            self.h = None
+
+
+class OracleWorld:
+    """One fp64 world (the mjData of a single ManEnv)."""
+
+    def __init__(self, model: OracleModel):
+        self.m = model
+        self._L = lib()
+        self.h = self._L.sgo_world_create(model.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self._L.sgo_world_free(self.h)
+            self.h = None
+
+    # parameters ------------------------------------------------------------------------
+    def set_stiffness(self, k, joint_ids=range(11, 64), tendon_ids=(0,)):
+        """ManEnv.set_new_stiffness (ref: environment/manenv.py:103-109)."""
+        for j in joint_ids:
+            self._L.sgo_set_jnt_stiffness(self.h, int(j), float(k))
+        for t in tendon_ids:
+            self._L.sgo_set_tendon_stiffness(self.h, int(t), float(k))
+
+    def set_jnt_stiffness(self, j, k): self._L.sgo_set_jnt_stiffness(self.h, int(j), float(k))
+    def set_tendon_stiffness(self, t, k): self._L.sgo_set_tendon_stiffness(self.h, int(t), float(k))
+    def set_dof_damping(self, i, v): self._L.sgo_set_dof_damping(self.h, int(i), float(v))
+    def set_tendon_damping(self, t, v): self._L.sgo_set_tendon_damping(self.h, int(t), float(v))
+
+    def set_body_pos(self, b, xyz):
+        a = np.ascontiguousarray(xyz, dtype=np.float64)
+        self._L.sgo_set_body_pos(self.h, int(b), _dp(a))
+
+    def set_ctrl(self, ctrl):
+        a = np.ascontiguousarray(ctrl, dtype=np.float64)
+        assert a.shape[0] == self.m.nu
+        self._L.sgo_set_ctrl(self.h, _dp(a))
+
+    def set_dense_solver(self, on): self._L.sgo_set_dense_solver(self.h, int(on))
+
+    def set_geom_mask(self, mask):
+        a = np.ascontiguousarray(mask, dtype=np.int32)
+        assert a.shape[0] == self.m.ngeom
+        self._L.sgo_set_geom_mask(self.h, a.ctypes.data_as(C.POINTER(C.c_int)))
+
+    # stepping ---------------------------------------------------------------------------
+    def reset(self): self._L.sgo_reset(self.h)
+    def forward(self): self._L.sgo_forward(self.h)
+    def step(self): return self._L.sgo_step(self.h)
+    def status(self): return self._L.sgo_status(self.h)
+
+    def get_state(self):
+        nv, nu = self.m.nv, self.m.nu
+        q, v, a, w = np.zeros(nv), np.zeros(nv), np.zeros(nu), np.zeros(nv)
+        self._L.sgo_get_state(self.h, _dp(q), _dp(v), _dp(a), _dp(w))
+        return q, v, a, w
+
+    def set_state(self, qpos=None, qvel=None, act=None, warm=None):
+        arrs = [None if x is None else np.ascontiguousarray(x, dtype=np.float64) for x in (qpos, qvel, act, warm)]
+        self._L.sgo_set_state(self.h, *[_dp(x) for x in arrs])
+
+    def sensordata(self):
+        out = np.zeros(self.m.nsensordata)
+        self._L.sgo_get_sensordata(self.h, _dp(out))
+        return out
+
+    def touch_mask(self): return self._L.sgo_get_touch_mask(self.h)
+    def get_int(self, key): return self._L.sgo_get_int(self.h, key.encode())
+
+    def get(self, key):
+        n = self._L.sgo_get_array(self.h, key.encode(), None, 0)
+        if n < 0:
+            raise KeyError(key)
+        out = np.zeros(max(n, 1))
+        self._L.sgo_get_array(self.h, key.encode(), _dp(out), n)
+        return out[:n]
+
+    def last_step_flops(self): return self._L.sgo_last_step_flops(self.h)
+
+    def episode(self, sim_start=1, sim_step=7, n_settle=40, n_iter=160, open_close_div=80, ctrl_mag=0.2):
+        """create_dataset.log_into_file's episode (ref: create_dataset.py:33-60) -> (rows[T,12], touch[T], status)."""
+        T = n_settle + n_iter
+        out = np.zeros((T, self.m.nsensordata))
+        touch = np.zeros(T, dtype=np.int32)
+        st = self._L.sgo_episode(self.h, sim_start, sim_step, n_settle, n_iter, open_close_div, float(ctrl_mag),
+                                 _dp(out), touch.ctypes.data_as(C.POINTER(C.c_int)))
+        return out, touch, st

@@ -786,6 +786,7 @@ static void collision(sgo_world* d) {
       d->con_exclude[c] = (rc[i].dist >= margin - gap);
       d->con_efc[c] = -1;
       int mk = d->geom_mask[g1] | d->geom_mask[g2];
+      d->touch_mask |= (1 << 30);
       if (mk & 1) d->touch_mask |= (mk >> 1);
     }
   }

@@ -1,0 +1,465 @@
+// sg_api.cu -- C-ABI of libsoftgrip.so (include/softgrip.h): model/plan upload, batch state in HBM,
+// kernel launches.  Host logic only; all physics is in sg_kernels.cuh.  There is no CPU fallback: every
+// entry point that would compute needs a CUDA device and fails with an error otherwise.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/softgrip.h"
+#include "sg_plan.hpp"
+#define SG_ST_CON_FULL_BIT 2
+#define SG_ST_UNSUPPORTED_BIT 8
+#include "sg_kernels.cuh"
+
+using namespace sg;
+
+static thread_local std::string g_err;
+static int fail(const std::string& msg) { g_err = msg; return -1; }
+#define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct sg_model {
+  Plan plan;
+  int maxcon_default, maxcand_default;
+};
+
+struct sg_batch {
+  const sg_model* model;
+  PlanDims D;                 // with per-batch capacities and masks folded in
+  int W, device, precision;
+  size_t esize;
+  SmemLayout L;
+  void* tab = nullptr;        // device table in batch precision
+  int* itab = nullptr;
+  void *qpos = nullptr, *qvel = nullptr, *warm = nullptr, *act = nullptr, *ctrl = nullptr;
+  double *p_stiff = nullptr, *p_damp = nullptr, *p_tdamp = nullptr, *p_objoff = nullptr;   // owned copies
+  bool has_stiff = false, has_damp = false, has_tdamp = false, has_objoff = false;
+  int* status = nullptr;
+  int* d_ctrl_event = nullptr; double* d_ctrl_value = nullptr; int sched_cap = 0;
+  double* debug_out = nullptr; int debug_cap = 0, debug_world = -1;
+  void* stage_traj = nullptr; size_t stage_traj_bytes = 0;   // device staging for rollout_host
+  int* stage_touch = nullptr; size_t stage_touch_bytes = 0;
+  long long launches = 0;
+  int max_ctas = 0;
+};
+
+extern "C" const char* sg_last_error(void) { return g_err.c_str(); }
+extern "C" int sg_version(void) { return 1; }
+
+extern "C" int sg_model_load(const void* blob, size_t nbytes, sg_model** out) {
+  if (!blob || !out) return fail("sg_model_load: null argument");
+  try {
+    sg_model* m = new sg_model();
+    m->plan = build_plan(blob, nbytes);
+    const int ns = m->plan.d.ns;
+    int mc = ((ns * 3 / 4 + 15) / 16) * 16;
+    if (mc < 32) mc = 32;
+    if (mc > 128) mc = 128;
+    if (const char* e = std::getenv("SOFTGRIP_MAXCON")) mc = std::atoi(e);
+    m->maxcon_default = mc;
+    m->maxcand_default = 256;
+    *out = m;
+    return 0;
+  } catch (const std::exception& e) { return fail(e.what()); }
+}
+
+extern "C" void sg_model_destroy(sg_model* m) { delete m; }
+
+extern "C" int sg_model_info(const sg_model* m, sg_info* out) {
+  if (!m || !out) return fail("sg_model_info: null argument");
+  std::memset(out, 0, sizeof(*out));
+  PlanDims D = m->plan.d;
+  D.maxcon = m->maxcon_default; D.maxcand = m->maxcand_default;
+  out->nv = D.nv; out->nfinger = D.nfd; out->nshell = D.ns; out->neq = m->plan.neq; out->nu = D.nu; out->nsensordata = D.nsd;
+  out->nlevels = D.nlev; out->maxcon = D.maxcon; out->ngeom = m->plan.ngeom;
+  out->smem_bytes32 = make_layout<float>(D).bytes; out->smem_bytes64 = make_layout<double>(D).bytes;
+  return 0;
+}
+
+extern "C" int sg_model_set_stiffness_targets(sg_model* m, const int* joint_mask, int tendon0) {
+  if (!m || !joint_mask) return fail("sg_model_set_stiffness_targets: null argument");
+  PlanDims& D = m->plan.d;
+  for (int i = 0; i < D.nfd; i++) if (joint_mask[i]) return fail("stiffness targets must be shell joints");
+  for (int e = 0; e < D.ns; e++) m->plan.itab[D.io_kmask + e] = joint_mask[D.nfd + e] ? 1 : 0;
+  D.stiff_tendon0 = tendon0 ? 1 : 0;
+  return 0;
+}
+
+extern "C" int sg_model_set_geom_mask(sg_model* m, const int* mask) {
+  if (!m || !mask) return fail("sg_model_set_geom_mask: null argument");
+  Plan& P = m->plan;
+  P.geom_mask.assign(mask, mask + P.ngeom);
+  for (size_t c = 0; c < P.coll_geom.size(); c++) P.tab[P.d.o_coll + c * CO_STRIDE + CO_MASK] = mask[P.coll_geom[c]];
+  P.d.cap_mask = 0;
+  for (int e = 0; e < P.d.ns; e++) P.d.cap_mask = (double)((int)P.d.cap_mask | mask[P.first_capsule_geom + e]);
+  for (int e = 0; e < P.d.ns; e++) if (mask[P.first_capsule_geom + e] != (int)P.d.cap_mask) return fail("shell geoms must share one name mask");
+  P.d.sph_mask = P.center_geom >= 0 ? mask[P.center_geom] : 0;
+  return 0;
+}
+
+template <typename T>
+static int upload_tables(sg_batch* b) {
+  const Plan& P = b->model->plan;
+  std::vector<T> t(P.tab.size());
+  for (size_t i = 0; i < t.size(); i++) t[i] = (T)P.tab[i];
+  CUDA_OK(cudaMalloc(&b->tab, sizeof(T) * (t.size() ? t.size() : 1)));
+  CUDA_OK(cudaMemcpy(b->tab, t.data(), sizeof(T) * t.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc((void**)&b->itab, sizeof(int) * (P.itab.size() ? P.itab.size() : 1)));
+  CUDA_OK(cudaMemcpy(b->itab, P.itab.data(), sizeof(int) * P.itab.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int precision, sg_batch** out) {
+  if (!m || !out) return fail("sg_batch_create: null argument");
+  if (nworlds < 1) return fail("sg_batch_create: nworlds must be >= 1");
+  if (precision != 32 && precision != 64) return fail("sg_batch_create: precision must be 32 or 64");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail("sg_batch_create: no CUDA device available (libsoftgrip has no CPU path)");
+  if (device < 0 || device >= ndev) return fail("sg_batch_create: bad device index");
+  CUDA_OK(cudaSetDevice(device));
+  sg_batch* b = new sg_batch();
+  b->model = m; b->W = nworlds; b->device = device; b->precision = precision;
+  b->esize = precision == 32 ? 4 : 8;
+  b->D = m->plan.d;
+  b->D.maxcon = m->maxcon_default; b->D.maxcand = m->maxcand_default;
+  b->L = precision == 32 ? make_layout<float>(b->D) : make_layout<double>(b->D);
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if ((size_t)b->L.bytes > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: world does not fit in shared memory"); }
+  int rc = precision == 32 ? upload_tables<float>(b) : upload_tables<double>(b);
+  if (rc) { delete b; return rc; }
+  const size_t nv = b->D.nv, nu = b->D.nu > 0 ? b->D.nu : 1;
+  CUDA_OK(cudaMalloc(&b->qpos, b->esize * nv * nworlds));
+  CUDA_OK(cudaMalloc(&b->qvel, b->esize * nv * nworlds));
+  CUDA_OK(cudaMalloc(&b->warm, b->esize * nv * nworlds));
+  CUDA_OK(cudaMalloc(&b->act, b->esize * nu * nworlds));
+  CUDA_OK(cudaMalloc(&b->ctrl, b->esize * nu * nworlds));
+  CUDA_OK(cudaMalloc((void**)&b->status, sizeof(int) * nworlds));
+  CUDA_OK(cudaMalloc((void**)&b->p_stiff, sizeof(double) * nworlds));
+  CUDA_OK(cudaMalloc((void**)&b->p_damp, sizeof(double) * nworlds));
+  CUDA_OK(cudaMalloc((void**)&b->p_tdamp, sizeof(double) * nworlds));
+  CUDA_OK(cudaMalloc((void**)&b->p_objoff, sizeof(double) * 3 * nworlds));
+  b->debug_cap = 64 + 16 * 2 * b->D.maxcon + b->D.nv + 3 * (b->D.nrow + 1 + MAXFD + 3 * b->D.maxcon) + 64;
+  CUDA_OK(cudaMalloc((void**)&b->debug_out, sizeof(double) * b->debug_cap));
+  CUDA_OK(cudaMemset(b->debug_out, 0, sizeof(double) * b->debug_cap));
+  // resident CTAs: one warp per world, limited by shared memory
+  if (precision == 32) {
+    CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.bytes));
+    CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  } else {
+    CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.bytes));
+    CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  }
+  int per_sm = 0;
+  if (precision == 32) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_step_kernel<float>, 32, b->L.bytes)); }
+  else { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_step_kernel<double>, 32, b->L.bytes)); }
+  if (per_sm < 1) per_sm = 1;
+  b->max_ctas = per_sm * prop.multiProcessorCount;
+  *out = b;
+  return sg_batch_reset(b, nullptr);
+}
+
+extern "C" void sg_batch_destroy(sg_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  void* ptrs[] = {b->tab, b->itab, b->qpos, b->qvel, b->warm, b->act, b->ctrl, b->status, b->p_stiff, b->p_damp, b->p_tdamp,
+                  b->p_objoff, b->d_ctrl_event, b->d_ctrl_value, b->debug_out, b->stage_traj, b->stage_touch};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete b;
+}
+
+extern "C" int sg_batch_nworlds(const sg_batch* b) { return b ? b->W : -1; }
+extern "C" int sg_batch_precision(const sg_batch* b) { return b ? b->precision : -1; }
+extern "C" long long sg_batch_launch_count(const sg_batch* b) { return b ? b->launches : -1; }
+
+extern "C" int sg_batch_set_params(sg_batch* b, const double* stiffness, const double* damping, const double* tdamping,
+                                   const double* objoff, void* stream) {
+  if (!b) return fail("sg_batch_set_params: null batch");
+  CUDA_OK(cudaSetDevice(b->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  b->has_stiff = stiffness != nullptr; b->has_damp = damping != nullptr; b->has_tdamp = tdamping != nullptr; b->has_objoff = objoff != nullptr;
+  if (stiffness) CUDA_OK(cudaMemcpyAsync(b->p_stiff, stiffness, sizeof(double) * b->W, cudaMemcpyDefault, s));
+  if (damping) CUDA_OK(cudaMemcpyAsync(b->p_damp, damping, sizeof(double) * b->W, cudaMemcpyDefault, s));
+  if (tdamping) CUDA_OK(cudaMemcpyAsync(b->p_tdamp, tdamping, sizeof(double) * b->W, cudaMemcpyDefault, s));
+  if (objoff) CUDA_OK(cudaMemcpyAsync(b->p_objoff, objoff, sizeof(double) * 3 * b->W, cudaMemcpyDefault, s));
+  return 0;
+}
+
+extern "C" int sg_batch_reset(sg_batch* b, void* stream) {
+  if (!b) return fail("sg_batch_reset: null batch");
+  CUDA_OK(cudaSetDevice(b->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t nv = b->D.nv, nu = b->D.nu > 0 ? b->D.nu : 1;
+  CUDA_OK(cudaMemsetAsync(b->qpos, 0, b->esize * nv * b->W, s));   // qpos0 == 0 is validated by the plan
+  CUDA_OK(cudaMemsetAsync(b->qvel, 0, b->esize * nv * b->W, s));
+  CUDA_OK(cudaMemsetAsync(b->warm, 0, b->esize * nv * b->W, s));
+  CUDA_OK(cudaMemsetAsync(b->act, 0, b->esize * nu * b->W, s));
+  CUDA_OK(cudaMemsetAsync(b->ctrl, 0, b->esize * nu * b->W, s));
+  CUDA_OK(cudaMemsetAsync(b->status, 0, sizeof(int) * b->W, s));
+  return 0;
+}
+
+template <typename T> __global__ void cvt_kernel(const double* in, T* out, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (T)in[i];
+}
+template <typename T> __global__ void bcast_kernel(const double* in, T* out, int nu, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (T)in[i % nu];
+}
+
+extern "C" int sg_batch_set_ctrl(sg_batch* b, const double* ctrl, void* stream) {
+  if (!b || !ctrl) return fail("sg_batch_set_ctrl: null argument");
+  CUDA_OK(cudaSetDevice(b->device));
+  const size_t n = (size_t)b->D.nu * b->W;
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (b->precision == 32) cvt_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctrl, (float*)b->ctrl, n);
+  else cvt_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctrl, (double*)b->ctrl, n);
+  b->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sg_batch_set_ctrl_all(sg_batch* b, const double* ctrl_host, void* stream) {
+  if (!b || !ctrl_host) return fail("sg_batch_set_ctrl_all: null argument");
+  CUDA_OK(cudaSetDevice(b->device));
+  const int nu = b->D.nu;
+  if (nu == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (b->sched_cap < 1) {
+    if (b->d_ctrl_event) cudaFree(b->d_ctrl_event);
+    if (b->d_ctrl_value) cudaFree(b->d_ctrl_value);
+    b->sched_cap = 256;
+    CUDA_OK(cudaMalloc((void**)&b->d_ctrl_event, sizeof(int) * b->sched_cap));
+    CUDA_OK(cudaMalloc((void**)&b->d_ctrl_value, sizeof(double) * b->sched_cap * nu));
+  }
+  CUDA_OK(cudaMemcpyAsync(b->d_ctrl_value, ctrl_host, sizeof(double) * nu, cudaMemcpyHostToDevice, s));
+  const size_t n = (size_t)nu * b->W;
+  if (b->precision == 32) bcast_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b->d_ctrl_value, (float*)b->ctrl, nu, n);
+  else bcast_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b->d_ctrl_value, (double*)b->ctrl, nu, n);
+  b->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static KArgs<T> make_args(sg_batch* b) {
+  KArgs<T> K{};
+  K.D = b->D; K.L = b->L;
+  // fold the (possibly updated) model-level masks / stiffness targets into this launch
+  K.D.stiff_tendon0 = b->model->plan.d.stiff_tendon0;
+  K.D.cap_mask = b->model->plan.d.cap_mask; K.D.sph_mask = b->model->plan.d.sph_mask;
+  K.tab = (const T*)b->tab; K.itab = b->itab; K.nworlds = b->W;
+  K.qpos = (T*)b->qpos; K.qvel = (T*)b->qvel; K.warm = (T*)b->warm; K.act = (T*)b->act; K.ctrl = (T*)b->ctrl;
+  K.p_stiff = b->has_stiff ? b->p_stiff : nullptr; K.p_damp = b->has_damp ? b->p_damp : nullptr;
+  K.p_tdamp = b->has_tdamp ? b->p_tdamp : nullptr; K.p_objoff = b->has_objoff ? b->p_objoff : nullptr;
+  K.status = b->status;
+  K.debug_world = b->debug_world; K.debug_out = b->debug_out; K.debug_cap = b->debug_cap;
+  return K;
+}
+
+// tables are uploaded at batch creation; model-level edits made later (masks, stiffness targets) are
+// re-synchronised lazily here
+static int sync_tables(sg_batch* b) {
+  const Plan& P = b->model->plan;
+  if (b->precision == 32) {
+    std::vector<float> t(P.tab.size());
+    for (size_t i = 0; i < t.size(); i++) t[i] = (float)P.tab[i];
+    CUDA_OK(cudaMemcpy(b->tab, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
+  } else CUDA_OK(cudaMemcpy(b->tab, P.tab.data(), sizeof(double) * P.tab.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(b->itab, P.itab.data(), sizeof(int) * P.itab.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+template <typename T>
+static int launch(sg_batch* b, KArgs<T>& K, cudaStream_t s) {
+  int grid = b->W;
+  if (K.rollout && grid > b->max_ctas) grid = b->max_ctas;   // persistent: each CTA walks worlds w, w+grid, ...
+  sg_step_kernel<T><<<grid, 32, b->L.bytes, s>>>(K);
+  b->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int do_step(sg_batch* b, int nsub, int integrate, void* sens_out, int* touch_out, void* stream) {
+  CUDA_OK(cudaSetDevice(b->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (b->precision == 32) {
+    KArgs<float> K = make_args<float>(b);
+    K.nsub = nsub; K.integrate = integrate; K.sens_out = (float*)sens_out; K.touch_out = touch_out;
+    return launch<float>(b, K, s);
+  }
+  KArgs<double> K = make_args<double>(b);
+  K.nsub = nsub; K.integrate = integrate; K.sens_out = (double*)sens_out; K.touch_out = touch_out;
+  return launch<double>(b, K, s);
+}
+
+extern "C" int sg_batch_step(sg_batch* b, int nsub, void* sens_out, int* touch_out, void* stream) {
+  if (!b) return fail("sg_batch_step: null batch");
+  if (nsub < 1) return fail("sg_batch_step: nsub must be >= 1");
+  return do_step(b, nsub, 1, sens_out, touch_out, stream);
+}
+
+extern "C" int sg_batch_forward(sg_batch* b, void* sens_out, int* touch_out, void* stream) {
+  if (!b) return fail("sg_batch_forward: null batch");
+  return do_step(b, 1, 0, sens_out, touch_out, stream);
+}
+
+static int upload_schedule(sg_batch* b, const sg_schedule* sc, cudaStream_t s) {
+  const int nu = b->D.nu > 0 ? b->D.nu : 1;
+  if (sc->nrows > b->sched_cap) {
+    if (b->d_ctrl_event) cudaFree(b->d_ctrl_event);
+    if (b->d_ctrl_value) cudaFree(b->d_ctrl_value);
+    b->sched_cap = sc->nrows > 256 ? sc->nrows : 256;
+    CUDA_OK(cudaMalloc((void**)&b->d_ctrl_event, sizeof(int) * b->sched_cap));
+    CUDA_OK(cudaMalloc((void**)&b->d_ctrl_value, sizeof(double) * b->sched_cap * nu));
+  }
+  CUDA_OK(cudaMemcpyAsync(b->d_ctrl_event, sc->ctrl_event, sizeof(int) * sc->nrows, cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemcpyAsync(b->d_ctrl_value, sc->ctrl_value, sizeof(double) * sc->nrows * b->D.nu, cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+extern "C" int sg_batch_rollout(sg_batch* b, const sg_schedule* sc, void* traj_out, int* touch_out, void* stream) {
+  if (!b || !sc || !traj_out) return fail("sg_batch_rollout: null argument");
+  if (sc->nrows < 1 || sc->sim_step < 1 || sc->sim_start < 0 || !sc->ctrl_event || !sc->ctrl_value) return fail("sg_batch_rollout: bad schedule");
+  CUDA_OK(cudaSetDevice(b->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = upload_schedule(b, sc, s);
+  if (rc) return rc;
+  const size_t nu = b->D.nu > 0 ? b->D.nu : 1;
+  CUDA_OK(cudaMemsetAsync(b->act, 0, b->esize * nu * b->W, s));
+  CUDA_OK(cudaMemsetAsync(b->ctrl, 0, b->esize * nu * b->W, s));
+  if (b->precision == 32) {
+    KArgs<float> K = make_args<float>(b);
+    K.rollout = 1; K.sim_start = sc->sim_start; K.sim_step = sc->sim_step; K.nrows = sc->nrows;
+    K.ctrl_event = b->d_ctrl_event; K.ctrl_value = b->d_ctrl_value; K.sens_out = (float*)traj_out; K.touch_out = touch_out;
+    return launch<float>(b, K, s);
+  }
+  KArgs<double> K = make_args<double>(b);
+  K.rollout = 1; K.sim_start = sc->sim_start; K.sim_step = sc->sim_step; K.nrows = sc->nrows;
+  K.ctrl_event = b->d_ctrl_event; K.ctrl_value = b->d_ctrl_value; K.sens_out = (double*)traj_out; K.touch_out = touch_out;
+  return launch<double>(b, K, s);
+}
+
+extern "C" int sg_batch_rollout_host(sg_batch* b, const sg_schedule* sc, const double* stiffness_host, void* traj_host,
+                                     int* touch_host, int* status_host) {
+  if (!b || !sc || !traj_host) return fail("sg_batch_rollout_host: null argument");
+  CUDA_OK(cudaSetDevice(b->device));
+  const size_t tb = b->esize * (size_t)b->W * sc->nrows * b->D.nsd, ub = sizeof(int) * (size_t)b->W * sc->nrows;
+  if (tb > b->stage_traj_bytes) { if (b->stage_traj) cudaFree(b->stage_traj); CUDA_OK(cudaMalloc(&b->stage_traj, tb)); b->stage_traj_bytes = tb; }
+  if (touch_host && ub > b->stage_touch_bytes) { if (b->stage_touch) cudaFree(b->stage_touch); CUDA_OK(cudaMalloc((void**)&b->stage_touch, ub)); b->stage_touch_bytes = ub; }
+  if (stiffness_host) { int rc = sg_batch_set_params(b, stiffness_host, nullptr, nullptr, nullptr, nullptr); if (rc) return rc; }
+  CUDA_OK(cudaMemsetAsync(b->status, 0, sizeof(int) * b->W, 0));
+  int rc = sg_batch_rollout(b, sc, b->stage_traj, touch_host ? b->stage_touch : nullptr, nullptr);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(traj_host, b->stage_traj, tb, cudaMemcpyDeviceToHost, 0));
+  if (touch_host) CUDA_OK(cudaMemcpyAsync(touch_host, b->stage_touch, ub, cudaMemcpyDeviceToHost, 0));
+  if (status_host) CUDA_OK(cudaMemcpyAsync(status_host, b->status, sizeof(int) * b->W, cudaMemcpyDeviceToHost, 0));
+  CUDA_OK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+template <typename T>
+static int get_arr(const void* dev, double* host, size_t n) {
+  if (!host) return 0;
+  std::vector<T> tmp(n);
+  CUDA_OK(cudaMemcpy(tmp.data(), dev, sizeof(T) * n, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; i++) host[i] = (double)tmp[i];
+  return 0;
+}
+template <typename T>
+static int set_arr(void* dev, const double* host, size_t n) {
+  if (!host) return 0;
+  std::vector<T> tmp(n);
+  for (size_t i = 0; i < n; i++) tmp[i] = (T)host[i];
+  CUDA_OK(cudaMemcpy(dev, tmp.data(), sizeof(T) * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int sg_batch_get_state(sg_batch* b, double* qpos, double* qvel, double* act, double* warm) {
+  if (!b) return fail("sg_batch_get_state: null batch");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  const size_t n = (size_t)b->D.nv * b->W, na = (size_t)b->D.nu * b->W;
+  int rc = 0;
+  if (b->precision == 32) { rc |= get_arr<float>(b->qpos, qpos, n); rc |= get_arr<float>(b->qvel, qvel, n); rc |= get_arr<float>(b->act, act, na); rc |= get_arr<float>(b->warm, warm, n); }
+  else { rc |= get_arr<double>(b->qpos, qpos, n); rc |= get_arr<double>(b->qvel, qvel, n); rc |= get_arr<double>(b->act, act, na); rc |= get_arr<double>(b->warm, warm, n); }
+  return rc;
+}
+
+extern "C" int sg_batch_set_state(sg_batch* b, const double* qpos, const double* qvel, const double* act, const double* warm) {
+  if (!b) return fail("sg_batch_set_state: null batch");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  const size_t n = (size_t)b->D.nv * b->W, na = (size_t)b->D.nu * b->W;
+  int rc = 0;
+  if (b->precision == 32) { rc |= set_arr<float>(b->qpos, qpos, n); rc |= set_arr<float>(b->qvel, qvel, n); rc |= set_arr<float>(b->act, act, na); rc |= set_arr<float>(b->warm, warm, n); }
+  else { rc |= set_arr<double>(b->qpos, qpos, n); rc |= set_arr<double>(b->qvel, qvel, n); rc |= set_arr<double>(b->act, act, na); rc |= set_arr<double>(b->warm, warm, n); }
+  return rc;
+}
+
+extern "C" int sg_batch_status(sg_batch* b, int* status_host, int clear) {
+  if (!b || !status_host) return fail("sg_batch_status: null argument");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(status_host, b->status, sizeof(int) * b->W, cudaMemcpyDeviceToHost));
+  if (clear) CUDA_OK(cudaMemset(b->status, 0, sizeof(int) * b->W));
+  return 0;
+}
+
+extern "C" int sg_batch_sync(sg_batch* b, void* stream) {
+  if (!b) return fail("sg_batch_sync: null batch");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int sg_batch_set_debug_world(sg_batch* b, int world) {
+  if (!b) return fail("sg_batch_set_debug_world: null batch");
+  if (world >= b->W) return fail("sg_batch_set_debug_world: world out of range");
+  b->debug_world = world;
+  // model-level edits (geom masks, stiffness targets) may have happened since creation
+  return sync_tables(b);
+}
+
+extern "C" int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int cap) {
+  if (!b || !key) return fail("sg_batch_debug_get: null argument");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  std::vector<double> h(b->debug_cap);
+  CUDA_OK(cudaMemcpy(h.data(), b->debug_out, sizeof(double) * b->debug_cap, cudaMemcpyDeviceToHost));
+  const int ncontot = (int)h[0], nefc = (int)h[1], ncon = (int)h[3], nlim = (int)h[4];
+  const std::string k(key);
+  auto put = [&](const double* src, int n) { if (out) for (int i = 0; i < n && i < cap; i++) out[i] = src[i]; return n; };
+  auto scalar = [&](double v) { if (out && cap > 0) out[0] = v; return 1; };
+  if (k == "ncon") return scalar(ncontot);
+  if (k == "nefc") return scalar(nefc);
+  if (k == "solver_iter") return scalar(h[2]);
+  if (k == "ncon_rows") return scalar(ncon);
+  if (k == "nlim") return scalar(nlim);
+  if (k == "maxlev") return scalar(h[5]);
+  if (k == "ncand") return scalar(h[6]);
+  const int base = 64 + 16 * 2 * b->D.maxcon, eb = base + b->D.nv;
+  if (k == "qacc") return put(&h[base], b->D.nv);
+  if (k == "con_dist" || k == "con_pos" || k == "con_frame") {
+    const int per = k == "con_dist" ? 1 : (k == "con_pos" ? 3 : 9), offs = k == "con_dist" ? 0 : (k == "con_pos" ? 1 : 4);
+    std::vector<double> t((size_t)per * ncontot);
+    for (int i = 0; i < ncontot && i < 2 * b->D.maxcon; i++) for (int j = 0; j < per; j++) t[(size_t)i * per + j] = h[64 + 16 * i + offs + j];
+    return put(t.data(), per * ncontot);
+  }
+  if (k == "efc_force" || k == "efc_aref" || k == "efc_R") {
+    // device rows are in schedule order; map the equality block back to MuJoCo row ids
+    const int which = k == "efc_force" ? 0 : (k == "efc_aref" ? 1 : 2);
+    std::vector<double> t(nefc);
+    const std::vector<int>& sched = b->model->plan.sched_eq;
+    for (int p = 0; p < b->D.nrow; p++) t[sched[p]] = h[eb + which * nefc + p];
+    for (int r = b->D.nrow; r < nefc; r++) t[r] = h[eb + which * nefc + r];
+    return put(t.data(), nefc);
+  }
+  return fail("sg_batch_debug_get: unknown key " + k);
+}

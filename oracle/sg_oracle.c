@@ -20,9 +20,10 @@
  * answer tests, the independently derived compile-time constants of SURVEY App. D, physical
  * invariants, and a dense "literal efc_AR" PGS mode that cross-checks the matrix-free solver.
  * Two pieces are *defined here* rather than recalled: (i) the capsule-box narrowphase (MuJoCo's
- * mjc_CapsuleBox case analysis is replaced by: closest point of the segment to the box via the
- * convex signed-distance minimum, sphere-box there, plus a second sphere-box at the far end of the
- * segment when that end is also within margin), and (ii) the PGS keeps qacc = qacc_smooth +
+ * mjc_CapsuleBox case analysis is replaced by: closest point of the segment to the box (root of the
+ * monotone derivative of the squared distance; if the segment enters the box, its inside end),
+ * sphere-box there, plus a second sphere-box at the far end of the segment when that end is also
+ * within margin), and (ii) the PGS keeps qacc = qacc_smooth +
  * M^-1 J^T f incrementally ("matrix-free"), algebraically identical to res = b + AR f.
  *
  * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off).
@@ -667,7 +668,8 @@ static int capsule_box(rawcon* con, double margin, const double* cpos, const dou
   }
   seg_box_grad(c, h, bsize, tstar, &d2);
   if (d2 <= MINVAL * MINVAL) {
-    /* the segment enters the box: take the deepest point, depth(t) = min_k (s_k - |p_k(t)|) (concave, piecewise linear) */
+    /* the segment enters the box: use the end that is inside (the deeper one if both are), or the middle of
+     * the inside interval when the segment passes through */
     double t0 = -1, t1 = 1;
     for (int k = 0; k < 3; k++) {
       if (fabs(h[k]) < MINVAL) continue;
@@ -676,18 +678,17 @@ static int capsule_box(rawcon* con, double margin, const double* cpos, const dou
       if (ta > t0) t0 = ta;
       if (tb < t1) t1 = tb;
     }
-    double cand[32]; int nc = 0;
-    cand[nc++] = t0; cand[nc++] = t1;
-    /* the six planes: f_i(t) = a_i + b_i t */
+    /* the six planes: depth_i(t) = a_i + b_i t ; depth(t) = min_i depth_i(t) */
     double a[6], b[6];
     for (int k = 0; k < 3; k++) { a[2 * k] = bsize[k] - c[k]; b[2 * k] = -h[k]; a[2 * k + 1] = bsize[k] + c[k]; b[2 * k + 1] = h[k]; }
-    for (int i = 0; i < 6; i++) for (int j = i + 1; j < 6; j++) { double db = b[i] - b[j]; if (fabs(db) > MINVAL) { double t = (a[j] - a[i]) / db; if (t > t0 && t < t1) cand[nc++] = t; } }
-    double best = -1e300; tstar = t0;
-    for (int i = 0; i < nc; i++) {
-      double dep = 1e300;
-      for (int q = 0; q < 6; q++) dep = fmin(dep, a[q] + b[q] * cand[i]);
-      if (dep > best) { best = dep; tstar = cand[i]; }
-    }
+    int in0 = (t0 <= -1), in1 = (t1 >= 1);
+    if (in0 && in1) {
+      double dm = 1e300, dp = 1e300;
+      for (int q = 0; q < 6; q++) { dm = fmin(dm, a[q] - b[q]); dp = fmin(dp, a[q] + b[q]); }
+      tstar = (dp > dm) ? 1 : -1;
+    } else if (in0) tstar = -1;
+    else if (in1) tstar = 1;
+    else tstar = 0.5 * (t0 + t1);
   }
   int n = 0; double sp[3];
   for (int k = 0; k < 3; k++) sp[k] = cpos[k] + axis_w[k] * (tstar * hl);

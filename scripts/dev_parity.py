@@ -45,7 +45,7 @@ for t in range(nsteps):
     bad = (ncon_o != ncon_g) or (nefc_o != nefc_g) or (it_o != it_g) or max(e.values()) > (1e-6 if prec == "64" else 1e-2)
     for kk, vv in e.items(): worst[kk] = max(worst.get(kk, 0), vv)
     if bad or t % 50 == 0:
-        print(t, "ncon", ncon_o, ncon_g, "nefc", nefc_o, nefc_g, "iter", it_o, it_g, {kk: "%.2e" % vv for kk, vv in e.items()}, "touch", ow.touch_mask(), int(touch[0]) if False else "", "st", st, env.status()[0])
+        print(t, "ncon", ncon_o, ncon_g, "nefc", nefc_o, nefc_g, "iter", it_o, it_g, {kk: "%.2e" % vv for kk, vv in e.items()}, "touch", ow.touch_mask(), int(touch[0]) if False else "", "st", st, env.status()[0], "ncand", int(env.debug(0, "ncand")[0]))
     if bad and "-k" not in sys.argv:
         fo, fg = ow.get("efc_force"), env.debug(0, "efc_force")
         ao, ag = ow.get("efc_aref"), env.debug(0, "efc_aref")
@@ -57,6 +57,12 @@ for t in range(nsteps):
         po, pg = ow.get("con_pos"), env.debug(0, "con_pos")
         m = min(len(po), len(pg))
         if m: print(" con_pos err", np.abs(po[:m] - pg[:m]).max(), "frame err", np.abs(ow.get("con_frame")[:3*m] - env.debug(0, "con_frame")[:3*m]).max())
+        fo_, fg_ = ow.get("con_frame").reshape(-1, 9), env.debug(0, "con_frame").reshape(-1, 9)
+        po_, pg_ = po.reshape(-1, 3), pg.reshape(-1, 3)
+        g1, g2 = ow.get("con_geom1"), ow.get("con_geom2")
+        for ci in range(min(len(po_), len(pg_))):
+            if np.abs(po_[ci] - pg_[ci]).max() > 1e-9 or np.abs(fo_[ci] - fg_[ci]).max() > 1e-9:
+                print("  contact", ci, "geoms", g1[ci], g2[ci], "dist", do[ci], dg[ci], "\n    pos o", po_[ci], "g", pg_[ci], "\n    n o", fo_[ci][:3], "g", fg_[ci][:3], "\n    t1 o", fo_[ci][3:6], "g", fg_[ci][3:6])
         print(" qacc o", w2[:8], "\n qacc g", gw[0][:8])
         break
 print("worst", {kk: "%.3e" % vv for kk, vv in worst.items()})

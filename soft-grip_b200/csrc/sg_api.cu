@@ -61,6 +61,7 @@ extern "C" int sg_model_load(const void* blob, size_t nbytes, sg_model** out) {
     if (const char* e = std::getenv("SOFTGRIP_MAXCON")) mc = std::atoi(e);
     m->maxcon_default = mc;
     m->maxcand_default = 256;
+    if (const char* e = std::getenv("SOFTGRIP_MAXCAND")) m->maxcand_default = std::atoi(e);
     *out = m;
     return 0;
   } catch (const std::exception& e) { return fail(e.what()); }

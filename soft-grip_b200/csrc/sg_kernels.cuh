@@ -277,22 +277,19 @@ __device__ int capsule_box(RawCon<T>* con, const T* cpos, const T* axis_w, T rad
       if (ta > t0) t0 = ta;
       if (tb < t1) t1 = tb;
     }
-    T a[6], b[6];
+    const bool in0 = (t0 <= T(-1)), in1 = (t1 >= T(1));
+    if (in0 && in1) {
+      T dm = T(1e30), dp = T(1e30);
 #pragma unroll
-    for (int k = 0; k < 3; k++) { a[2 * k] = bsize[k] - c[k]; b[2 * k] = -h[k]; a[2 * k + 1] = bsize[k] + c[k]; b[2 * k + 1] = h[k]; }
-    T best = T(-1e30); tstar = t0;
-    auto eval = [&](T t) {
-      T dep = T(1e30);
-#pragma unroll
-      for (int q = 0; q < 6; q++) dep = tmin(dep, a[q] + b[q] * t);
-      if (dep > best) { best = dep; tstar = t; }
-    };
-    eval(t0); eval(t1);
-    for (int i = 0; i < 6; i++)
-      for (int j = i + 1; j < 6; j++) {
-        T db = b[i] - b[j];
-        if (tabs(db) > T(SG_MINVAL)) { T t = (a[j] - a[i]) / db; if (t > t0 && t < t1) eval(t); }
+      for (int k = 0; k < 3; k++) {
+        const T a0 = bsize[k] - c[k], a1 = bsize[k] + c[k];
+        dm = tmin(dm, tmin(a0 + h[k], a1 - h[k]));     // depth at t = -1
+        dp = tmin(dp, tmin(a0 - h[k], a1 + h[k]));     // depth at t = +1
       }
+      tstar = (dp > dm) ? T(1) : T(-1);
+    } else if (in0) tstar = T(-1);
+    else if (in1) tstar = T(1);
+    else tstar = T(0.5) * (t0 + t1);
   }
   int n = 0; T sp[3];
 #pragma unroll
@@ -800,6 +797,14 @@ struct World {
         T dif[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
         if ((int)co[CO_TYPE] == GEOM_PLANE) { T nrm[3] = {rot1[2], rot1[5], rot1[8]}; pass = !(dot3(dif, nrm) > rb2); }
         else { T bound = co[CO_RBOUND] + rb2; pass = !(dot3(dif, dif) > bound * bound); }
+        if (pass && pt == PAIR_BOX_CAPSULE) {
+          // mid-phase (prunes only): the capsule's bounding box in the frame of the box must overlap the box
+          T dl[3], al[3];
+          matTvec3(dl, rot1, dif);
+          matTvec3(al, rot1, tab(D.o_sl_axis) + 3 * pb);
+#pragma unroll
+          for (int k = 0; k < 3; k++) if (tabs(dl[k]) > co[CO_SIZE + k] + T(D.cap_r) + T(D.cap_hl) * tabs(al[k])) pass = false;
+        }
       }
       const unsigned m = __ballot_sync(FULLMASK, pass);
       if (pass) {

@@ -1419,3 +1419,25 @@ int sgo_episode(sgo_world* d, int sim_start, int sim_step, int n_settle, int n_i
   }
   return st;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* test hooks (known-answer tests of the static helpers)                                       */
+/* ------------------------------------------------------------------------------------------ */
+/* out: n, then per contact dist, pos[3], normal[3] */
+int sgo_test_capsule_box(const double* cpos, const double* cmat, const double* csize, const double* bpos,
+                         const double* bmat, const double* bsize, double* out) {
+  rawcon rc[2];
+  int n = capsule_box(rc, 0.0, cpos, cmat, csize, bpos, bmat, bsize);
+  for (int i = 0; i < n; i++) { out[7 * i] = rc[i].dist; memcpy(out + 7 * i + 1, rc[i].pos, 3 * sizeof(double)); memcpy(out + 7 * i + 4, rc[i].frame, 3 * sizeof(double)); }
+  return n;
+}
+int sgo_test_sphere_box(const double* spos, double radius, const double* bpos, const double* bmat, const double* bsize, double* out) {
+  rawcon rc;
+  int n = sphere_box(&rc, 0.0, spos, radius, bpos, bmat, bsize);
+  if (n) { out[0] = rc.dist; memcpy(out + 1, rc.pos, 3 * sizeof(double)); memcpy(out + 4, rc.frame, 3 * sizeof(double)); }
+  return n;
+}
+int sgo_test_qcqp2(const double* A, const double* b, const double* d, double r, double* res) { return qcqp2(res, A, b, d, r); }
+double sgo_test_impedance(const double* solimp, double pos, double margin) { return impedance(solimp, pos, margin); }
+int sgo_test_box_box(const double* p1, const double* R1, const double* s1, const double* p2, const double* R2, const double* s2) { return box_box_overlap(p1, R1, s1, p2, R2, s2); }
+void sgo_test_make_frame(double* frame) { make_frame(frame); }

@@ -57,6 +57,13 @@ def lib():
         L.sgo_episode.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, D, I]
         L.sgo_last_step_flops.restype = C.c_double
         L.sgo_last_step_flops.argtypes = [P]
+        L.sgo_test_capsule_box.argtypes = [D, D, D, D, D, D, D]
+        L.sgo_test_sphere_box.argtypes = [D, C.c_double, D, D, D, D]
+        L.sgo_test_qcqp2.argtypes = [D, D, D, C.c_double, D]
+        L.sgo_test_impedance.restype = C.c_double
+        L.sgo_test_impedance.argtypes = [D, C.c_double, C.c_double]
+        L.sgo_test_box_box.argtypes = [D, D, D, D, D, D]
+        L.sgo_test_make_frame.argtypes = [D]
         _LIB = L
     return _LIB
 
@@ -165,3 +172,46 @@ class OracleWorld:
         st = self._L.sgo_episode(self.h, sim_start, sim_step, n_settle, n_iter, open_close_div, float(ctrl_mag),
                                  _dp(out), touch.ctypes.data_as(C.POINTER(C.c_int)))
         return out, touch, st
+
+
+# ---- hooks for known-answer tests of the oracle's static helpers -----------------------------------
+def _arr(x):
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def capsule_box(cpos, cmat, csize, bpos, bmat, bsize):
+    """-> list of (dist, pos[3], normal[3]) from the oracle's capsule-box narrowphase."""
+    out = np.zeros(14)
+    a = [_arr(v) for v in (cpos, np.asarray(cmat).reshape(9), csize, bpos, np.asarray(bmat).reshape(9), bsize)]
+    n = lib().sgo_test_capsule_box(*[_dp(v) for v in a], _dp(out))
+    return [(out[7 * i], out[7 * i + 1:7 * i + 4].copy(), out[7 * i + 4:7 * i + 7].copy()) for i in range(n)]
+
+
+def sphere_box(spos, radius, bpos, bmat, bsize):
+    out = np.zeros(7)
+    a = [_arr(v) for v in (spos, bpos, np.asarray(bmat).reshape(9), bsize)]
+    n = lib().sgo_test_sphere_box(_dp(a[0]), float(radius), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(out))
+    return (out[0], out[1:4].copy(), out[4:7].copy()) if n else None
+
+
+def qcqp2(A, b, d, r):
+    res = np.zeros(2)
+    a = [_arr(np.asarray(A).reshape(4)), _arr(b), _arr(d)]
+    active = lib().sgo_test_qcqp2(_dp(a[0]), _dp(a[1]), _dp(a[2]), float(r), _dp(res))
+    return res, bool(active)
+
+
+def impedance(solimp, pos, margin=0.0):
+    a = _arr(solimp)
+    return lib().sgo_test_impedance(_dp(a), float(pos), float(margin))
+
+
+def box_box_overlap(p1, R1, s1, p2, R2, s2):
+    a = [_arr(np.asarray(v).reshape(-1)) for v in (p1, R1, s1, p2, R2, s2)]
+    return bool(lib().sgo_test_box_box(*[_dp(v) for v in a]))
+
+
+def make_frame(frame):
+    a = _arr(np.asarray(frame).reshape(9)).copy()
+    lib().sgo_test_make_frame(_dp(a))
+    return a.reshape(3, 3)

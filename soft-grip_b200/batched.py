@@ -28,14 +28,15 @@ NUM_EPISODES, MAX_ITER_PER_EP, OPEN_CLOSE_DIV, START_STEP = 1, 160, 80, 40
 def world_uniform(seed, world_ids, lo, hi, stream=0):
     """Counter-based U(lo,hi) per *global* world id (splitmix64 of (seed, stream, id)): the draw of world w
     does not depend on how worlds are sharded over GPUs."""
-    x = (np.asarray(world_ids, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
-    x ^= np.uint64(seed & 0xFFFFFFFFFFFFFFFF) * np.uint64(0xBF58476D1CE4E5B9) + np.uint64(stream) * np.uint64(0x94D049BB133111EB)
-    for _ in range(2):
-        x ^= x >> np.uint64(30)
-        x *= np.uint64(0xBF58476D1CE4E5B9)
-        x ^= x >> np.uint64(27)
-        x *= np.uint64(0x94D049BB133111EB)
-        x ^= x >> np.uint64(31)
+    with np.errstate(over="ignore"):
+        x = (np.asarray(world_ids, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        x = x ^ (np.uint64(seed & 0xFFFFFFFFFFFFFFFF) * np.uint64(0xBF58476D1CE4E5B9) + np.uint64(stream) * np.uint64(0x94D049BB133111EB))
+        for _ in range(2):
+            x = x ^ (x >> np.uint64(30))
+            x = x * np.uint64(0xBF58476D1CE4E5B9)
+            x = x ^ (x >> np.uint64(27))
+            x = x * np.uint64(0x94D049BB133111EB)
+            x = x ^ (x >> np.uint64(31))
     u = (x >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
     return lo + (hi - lo) * u
 

@@ -1,0 +1,145 @@
+"""Host-side logic: episode schedule, per-world RNG, dataset format, driver CLI, sharding (gloo, world_size 2)."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, pkg
+
+
+def test_default_schedule_is_the_reference_protocol(batched):
+    """ctrl = 0 for 40 rows, close_hand at row 40, toggle (-> +0.2) at row 120 only (ref: create_dataset.py:41-60)."""
+    ev, val = batched.default_schedule(2)
+    assert ev.shape == (200,) and val.shape == (200, 2)
+    assert list(np.nonzero(ev)[0]) == [40, 120]
+    np.testing.assert_array_equal(val[40], [-0.2, -0.2]); np.testing.assert_array_equal(val[120], [0.2, 0.2])
+    ev2, val2 = batched.default_schedule(2, n_settle=5, n_iter=50, open_close_div=20)
+    assert list(np.nonzero(ev2)[0]) == [5, 25, 45] and val2[25, 0] == 0.2 and val2[45, 0] == -0.2
+
+
+def test_world_uniform_is_sharding_invariant(batched):
+    full = batched.world_uniform(7, np.arange(1000), 300, 1400, stream=3)
+    parts = np.concatenate([batched.world_uniform(7, np.arange(a, b), 300, 1400, stream=3) for a, b in ((0, 250), (250, 600), (600, 1000))])
+    np.testing.assert_array_equal(full, parts)
+    assert full.min() >= 300 and full.max() <= 1400 and abs(full.mean() - 850) < 30
+    assert not np.array_equal(full, batched.world_uniform(8, np.arange(1000), 300, 1400, stream=3))
+    assert not np.array_equal(full, batched.world_uniform(7, np.arange(1000), 300, 1400, stream=4))
+
+
+def test_geom_name_mask(batched):
+    names = ["ground", None, "g121", "g122", "g21", "g23", "OBJGcenter", "OBJG2_1_0"]
+    m = batched.geom_name_mask(names, "OBJ", ("g12", "g2"))
+    assert list(m) == [0, 0, 2, 2, 4, 4, 1, 1]          # 'g2' must not match g122, 'G2' (upper case) must not match
+
+
+def test_dataset_pickle_layout(tmp_path):
+    ds = pkg("dataset")
+    traj = np.random.default_rng(0).normal(size=(5, 200, 12)).astype(np.float32)
+    k = np.linspace(300, 1400, 5)
+    p = tmp_path / "d" / "x.pickle"
+    ds.write_pickle(str(p), traj, k)
+    raw = pickle.load(open(p, "rb"))
+    assert sorted(raw) == ["data", "stiffness"] and len(raw["data"]) == 5
+    assert raw["data"][0].shape == (200, 12) and raw["data"][0].dtype == np.float64 and isinstance(raw["stiffness"][0], float)
+    x, y = ds.read_pickle(str(p))                      # what functions/utils.create_tf_generators does
+    assert x.shape == (5, 200, 12) and y.shape == (5,)
+    np.testing.assert_allclose(x, traj.astype(np.float64))
+    masked = ds.mask_contact(traj, np.zeros((5, 200), dtype=bool))
+    assert not masked.any()
+    edges, stats = ds.feature_stats(x, y, nbins=2)
+    assert stats[0]["n"] + stats[1]["n"] == 5 and stats[0]["mean"].shape == (4,)
+
+
+def test_create_dataset_cli_flags():
+    sys.path.insert(0, os.path.join(ROOT, "soft-grip_b200"))
+    cd = pkg("create_dataset")
+    args, _ = cd.build_parser().parse_known_args(["--mujoco-model-paths", "a.xml", "b.xml", "--vis", "False"])
+    assert args.sim_step == 7 and args.sim_start == 1 and args.mujoco_model_paths == ["a.xml", "b.xml"]
+    assert args.vis is True                  # type=bool quirk kept
+    assert args.data_name == "dataset_all_shapes" and args.mask_contact is False
+    assert (cd.NUM_EPISODES, cd.MAX_ITER_PER_EP, cd.OPEN_CLOSE_DIV, cd.START_STEP) == (1, 160, 80, 40)
+
+
+def test_episode_rows_protocol():
+    """episode_rows drives the ManEnv verbs in the reference order (fake env, no GPU)."""
+    cd = pkg("create_dataset")
+
+    class Fake:
+        def __init__(self): self.log = []; self.n = 0
+        def step(self): self.n += 1; self.log.append("s"); return np.full(12, float(self.n)), self.n % 2 == 0
+        def close_hand(self): self.log.append("close")
+        def toggle_grip(self): self.log.append("toggle")
+        def render(self): pass
+
+    env = Fake()
+    rows = list(cd.episode_rows(env, mask_contact=True))
+    assert len(rows) == 200
+    assert env.log.index("close") == 40 and env.log.count("toggle") == 1
+    assert env.log.index("toggle") == 40 + 1 + 80          # before the 81st squeeze step
+    assert rows[0].sum() == 0 and rows[1].sum() == 24       # odd steps masked (no contact), even kept
+
+
+def test_manenv_surface_matches_reference():
+    sys.path.insert(0, os.path.join(ROOT, "soft-grip_b200"))
+    from environment import ManEnv
+    from environment.interface import Env
+    assert issubclass(ManEnv, Env)
+    assert ManEnv.joint_ids == list(range(11, 64)) and ManEnv.tendon_ids == [0]
+    assert ManEnv.obj_name == "OBJ" and list(ManEnv._finger_names0) == ["g12", "g2"]
+    for name in ("step", "reset", "get_sensor_sensordata", "toggle_grip", "close_hand", "loose_hand", "set_new_stiffness",
+                 "get_env", "render", "load_env", "get_std_spec"):
+        assert callable(getattr(ManEnv, name))
+
+    class A: sim_start = 1; sim_step = 7; mujoco_model_paths = ["x.xml"]; vis = False
+    assert ManEnv.get_std_spec(A) == {"sim_start": 1, "sim_step": 7, "env_paths": ["x.xml"], "is_vis": False}
+    with pytest.raises(NotImplementedError):
+        Env(1, 7).step()
+
+
+def test_bench_shard_plan():
+    sys.path.insert(0, ROOT)
+    import bench
+    for n in (1, 2, 4, 8):
+        shards = [bench.shard_range(1000, r, n) for r in range(n)]
+        assert shards[0][0] == 0 and shards[-1][1] == 1000
+        assert all(shards[i][1] == shards[i + 1][0] for i in range(n - 1))
+    assert bench.shard_range(10, 3, 4) == (9, 10)
+
+
+WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import bench
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+lo, hi = bench.shard_range(64, rank, world)
+import importlib
+batched = importlib.import_module("soft-grip_b200.batched")
+k = batched.world_uniform(0, np.arange(lo, hi), 300, 1400)
+ms = 10.0 + rank
+tmax = bench.max_over_ranks(ms, torch.device("cpu"))
+total = bench.sum_over_ranks(float(hi - lo), torch.device("cpu"))
+gathered = [None] * world
+dist.all_gather_object(gathered, k)
+if rank == 0:
+    full = batched.world_uniform(0, np.arange(64), 300, 1400)
+    assert np.array_equal(np.concatenate(gathered), full)
+    assert tmax == 10.0 + world - 1 and total == 64.0
+    print("OK")
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_sharding_with_gloo(tmp_path):
+    """N>1 host path on CPU: contiguous world shards, max-over-ranks timing, shard gather == unsharded draw."""
+    pytest.importorskip("torch")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29617", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "OK" in out.stdout

@@ -228,7 +228,7 @@ def main():
     ap.add_argument("--model", default="softbox")
     ap.add_argument("--worlds-per-gpu", type=int, default=8192)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-episodes-per-core", type=int, default=2)
+    ap.add_argument("--cpu-episodes-per-core", type=int, default=24)
     ap.add_argument("--ref-episodes-per-core", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -1,7 +1,7 @@
 // sg_api.cu -- C-ABI of libsoftgrip.so (include/softgrip.h): model/plan upload, batch state in HBM,
 // kernel launches.  Host logic only; all physics is in sg_kernels.cuh.  There is no CPU fallback: every
 // entry point that would compute needs a CUDA device and fails with an error otherwise.
-#include <cuda_runtime.h>
+#include "sg_rt.hpp"
 
 #include <cstdio>
 #include <cstdlib>
@@ -13,7 +13,10 @@
 #include "sg_plan.hpp"
 #define SG_ST_CON_FULL_BIT 2
 #define SG_ST_UNSUPPORTED_BIT 8
-#include "sg_kernels.cuh"
+#ifndef SG_SIMT_EMU
+#include "sg_kernels.cuh"      // first-generation kernel (one warp per world), kept for A/B runs: SOFTGRIP_KERNEL=1
+#endif
+#include "sg_launch.hpp"
 
 using namespace sg;
 
@@ -31,7 +34,13 @@ struct sg_batch {
   PlanDims D;                 // with per-batch capacities and masks folded in
   int W, device, precision;
   size_t esize;
+#ifndef SG_SIMT_EMU
   SmemLayout L;
+#endif
+  int kernel = 2;             // 2: sub-warp worlds (sg_kernels2.cuh); 1: one warp per world (sg_kernels.cuh)
+  int lpw = 8;                // lanes per world of kernel 2
+  Layout2 L2;
+  unsigned char* scratch = nullptr;   // global aux slots of kernel 2 (when aux is not in shared memory)
   void* tab = nullptr;        // device table in batch precision
   int* itab = nullptr;
   void *qpos = nullptr, *qvel = nullptr, *warm = nullptr, *act = nullptr, *ctrl = nullptr;
@@ -76,7 +85,7 @@ extern "C" int sg_model_info(const sg_model* m, sg_info* out) {
   D.maxcon = m->maxcon_default; D.maxcand = m->maxcand_default;
   out->nv = D.nv; out->nfinger = D.nfd; out->nshell = D.ns; out->neq = m->plan.neq; out->nu = D.nu; out->nsensordata = D.nsd;
   out->nlevels = D.nlev; out->maxcon = D.maxcon; out->ngeom = m->plan.ngeom;
-  out->smem_bytes32 = make_layout<float>(D).bytes; out->smem_bytes64 = make_layout<double>(D).bytes;
+  out->smem_bytes32 = make_layout2<float>(D, 1, 1).smem_stride; out->smem_bytes64 = make_layout2<double>(D, 1, 1).smem_stride;
   return 0;
 }
 
@@ -113,6 +122,22 @@ static int upload_tables(sg_batch* b) {
   return 0;
 }
 
+// (precision, lanes-per-world) -> instantiation; the list must match the Makefile's SG_INSTANCES
+#define SG_K2_CASES(X) X(float, 4) X(float, 8) X(float, 16) X(float, 32) X(double, 4) X(double, 8) X(double, 16) X(double, 32)
+static int k2_dispatch_configure(int precision, int lpw, size_t smem, int* per_sm) {
+#define X(T, N) if ((precision == 32) == (sizeof(T) == 4) && lpw == N) return k2_configure<T, N>(smem, per_sm);
+  SG_K2_CASES(X)
+#undef X
+  return -12345;
+}
+template <typename T>
+static int k2_dispatch_launch(int lpw, const KArgs2<T>& K, int grid, size_t smem, void* stream) {
+#define X(TT, N) if (sizeof(TT) == sizeof(T) && lpw == N) return k2_launch<T, N>(K, grid, smem, stream);
+  SG_K2_CASES(X)
+#undef X
+  return -12345;
+}
+
 extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int precision, sg_batch** out) {
   if (!m || !out) return fail("sg_batch_create: null argument");
   if (nworlds < 1) return fail("sg_batch_create: nworlds must be >= 1");
@@ -127,10 +152,18 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   b->esize = precision == 32 ? 4 : 8;
   b->D = m->plan.d;
   b->D.maxcon = m->maxcon_default; b->D.maxcand = m->maxcand_default;
-  b->L = precision == 32 ? make_layout<float>(b->D) : make_layout<double>(b->D);
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  if ((size_t)b->L.bytes > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: world does not fit in shared memory"); }
+  // kernel selection (environment overrides are development knobs; the defaults are the measured best)
+  b->kernel = 2; b->lpw = 8;
+  int aux_in_smem = 0;
+  if (const char* e = std::getenv("SOFTGRIP_KERNEL")) b->kernel = std::atoi(e);
+  if (const char* e = std::getenv("SOFTGRIP_LPW")) b->lpw = std::atoi(e);
+  if (const char* e = std::getenv("SOFTGRIP_AUX_SMEM")) aux_in_smem = std::atoi(e);
+#ifdef SG_SIMT_EMU
+  b->kernel = 2;
+#endif
+  if (b->kernel != 1 && b->kernel != 2) { delete b; return fail("SOFTGRIP_KERNEL must be 1 or 2"); }
   int rc = precision == 32 ? upload_tables<float>(b) : upload_tables<double>(b);
   if (rc) { delete b; return rc; }
   const size_t nv = b->D.nv, nu = b->D.nu > 0 ? b->D.nu : 1;
@@ -144,22 +177,45 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   CUDA_OK(cudaMalloc((void**)&b->p_damp, sizeof(double) * nworlds));
   CUDA_OK(cudaMalloc((void**)&b->p_tdamp, sizeof(double) * nworlds));
   CUDA_OK(cudaMalloc((void**)&b->p_objoff, sizeof(double) * 3 * nworlds));
-  b->debug_cap = 64 + 16 * 2 * b->D.maxcon + b->D.nv + 3 * (b->D.nrow + 1 + MAXFD + 3 * b->D.maxcon) + 64;
+  b->debug_cap = 64 + 16 * 2 * b->D.maxcon + b->D.nv + 3 * (b->D.nrow + 1 + MAXFD + 3 * b->D.maxcon) + 64 + (b->D.nrow + 1);
   CUDA_OK(cudaMalloc((void**)&b->debug_out, sizeof(double) * b->debug_cap));
   CUDA_OK(cudaMemset(b->debug_out, 0, sizeof(double) * b->debug_cap));
-  // resident CTAs: one warp per world, limited by shared memory
-  if (precision == 32) {
-    CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.bytes));
-    CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  } else {
-    CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.bytes));
-    CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  }
   int per_sm = 0;
-  if (precision == 32) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_step_kernel<float>, 32, b->L.bytes)); }
-  else { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_step_kernel<double>, 32, b->L.bytes)); }
-  if (per_sm < 1) per_sm = 1;
-  b->max_ctas = per_sm * prop.multiProcessorCount;
+  if (b->kernel == 2) {
+    const int wpw = 32 / b->lpw;
+    b->L2 = precision == 32 ? make_layout2<float>(b->D, aux_in_smem, wpw) : make_layout2<double>(b->D, aux_in_smem, wpw);
+    const size_t smem = (size_t)b->L2.smem_stride * wpw;
+    if (smem > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: worlds of one warp do not fit in shared memory (lower SOFTGRIP_LPW packing or use SOFTGRIP_AUX_SMEM=0)"); }
+    int e = k2_dispatch_configure(precision, b->lpw, smem, &per_sm);
+    if (e == -12345) { delete b; return fail("SOFTGRIP_LPW: this lanes-per-world value is not compiled in"); }
+    if (e) { delete b; return fail(std::string("kernel configuration failed: ") + cudaGetErrorString((cudaError_t)e)); }
+    if (per_sm < 1) per_sm = 1;
+    b->max_ctas = per_sm * prop.multiProcessorCount;
+    int need = (nworlds + wpw - 1) / wpw;
+    int slots = need < b->max_ctas ? need : b->max_ctas;
+    if (!aux_in_smem) {
+      CUDA_OK(cudaMalloc((void**)&b->scratch, (size_t)slots * wpw * (size_t)b->L2.gs_stride));
+      CUDA_OK(cudaMemset(b->scratch, 0, (size_t)slots * wpw * (size_t)b->L2.gs_stride));
+    }
+  }
+#ifndef SG_SIMT_EMU
+  else {
+    b->L = precision == 32 ? make_layout<float>(b->D) : make_layout<double>(b->D);
+    if ((size_t)b->L.bytes > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: world does not fit in shared memory"); }
+    // resident CTAs: one warp per world, limited by shared memory
+    if (precision == 32) {
+      CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.bytes));
+      CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_step_kernel<float>, 32, b->L.bytes));
+    } else {
+      CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.bytes));
+      CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_step_kernel<double>, 32, b->L.bytes));
+    }
+    if (per_sm < 1) per_sm = 1;
+    b->max_ctas = per_sm * prop.multiProcessorCount;
+  }
+#endif
   *out = b;
   return sg_batch_reset(b, nullptr);
 }
@@ -168,7 +224,7 @@ extern "C" void sg_batch_destroy(sg_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   void* ptrs[] = {b->tab, b->itab, b->qpos, b->qvel, b->warm, b->act, b->ctrl, b->status, b->p_stiff, b->p_damp, b->p_tdamp,
-                  b->p_objoff, b->d_ctrl_event, b->d_ctrl_value, b->debug_out, b->stage_traj, b->stage_touch};
+                  b->p_objoff, b->d_ctrl_event, b->d_ctrl_value, b->debug_out, b->stage_traj, b->stage_touch, b->scratch};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete b;
 }
@@ -204,6 +260,10 @@ extern "C" int sg_batch_reset(sg_batch* b, void* stream) {
   return 0;
 }
 
+#ifdef SG_SIMT_EMU
+template <typename T> static void run_cvt(const double* in, T* out, size_t n, cudaStream_t) { for (size_t i = 0; i < n; i++) out[i] = (T)in[i]; }
+template <typename T> static void run_bcast(const double* in, T* out, int nu, size_t n, cudaStream_t) { for (size_t i = 0; i < n; i++) out[i] = (T)in[i % nu]; }
+#else
 template <typename T> __global__ void cvt_kernel(const double* in, T* out, size_t n) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = (T)in[i];
@@ -212,6 +272,9 @@ template <typename T> __global__ void bcast_kernel(const double* in, T* out, int
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) out[i] = (T)in[i % nu];
 }
+template <typename T> static void run_cvt(const double* in, T* out, size_t n, cudaStream_t s) { cvt_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n); }
+template <typename T> static void run_bcast(const double* in, T* out, int nu, size_t n, cudaStream_t s) { bcast_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, nu, n); }
+#endif
 
 extern "C" int sg_batch_set_ctrl(sg_batch* b, const double* ctrl, void* stream) {
   if (!b || !ctrl) return fail("sg_batch_set_ctrl: null argument");
@@ -219,8 +282,8 @@ extern "C" int sg_batch_set_ctrl(sg_batch* b, const double* ctrl, void* stream) 
   const size_t n = (size_t)b->D.nu * b->W;
   if (n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (b->precision == 32) cvt_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctrl, (float*)b->ctrl, n);
-  else cvt_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctrl, (double*)b->ctrl, n);
+  if (b->precision == 32) run_cvt<float>(ctrl, (float*)b->ctrl, n, s);
+  else run_cvt<double>(ctrl, (double*)b->ctrl, n, s);
   b->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -241,15 +304,23 @@ extern "C" int sg_batch_set_ctrl_all(sg_batch* b, const double* ctrl_host, void*
   }
   CUDA_OK(cudaMemcpyAsync(b->d_ctrl_value, ctrl_host, sizeof(double) * nu, cudaMemcpyHostToDevice, s));
   const size_t n = (size_t)nu * b->W;
-  if (b->precision == 32) bcast_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b->d_ctrl_value, (float*)b->ctrl, nu, n);
-  else bcast_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b->d_ctrl_value, (double*)b->ctrl, nu, n);
+  if (b->precision == 32) run_bcast<float>(b->d_ctrl_value, (float*)b->ctrl, nu, n, s);
+  else run_bcast<double>(b->d_ctrl_value, (double*)b->ctrl, nu, n, s);
   b->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
+struct LaunchSpec {
+  int nsub = 1, integrate = 1;
+  int rollout = 0, sim_start = 0, sim_step = 0, nrows = 0;
+  void* sens_out = nullptr;
+  int* touch_out = nullptr;
+};
+
+#ifndef SG_SIMT_EMU
 template <typename T>
-static KArgs<T> make_args(sg_batch* b) {
+static int launch_v1(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
   KArgs<T> K{};
   K.D = b->D; K.L = b->L;
   // fold the (possibly updated) model-level masks / stiffness targets into this launch
@@ -261,7 +332,51 @@ static KArgs<T> make_args(sg_batch* b) {
   K.p_tdamp = b->has_tdamp ? b->p_tdamp : nullptr; K.p_objoff = b->has_objoff ? b->p_objoff : nullptr;
   K.status = b->status;
   K.debug_world = b->debug_world; K.debug_out = b->debug_out; K.debug_cap = b->debug_cap;
-  return K;
+  K.nsub = sp.nsub; K.integrate = sp.integrate; K.sens_out = (T*)sp.sens_out; K.touch_out = sp.touch_out;
+  K.rollout = sp.rollout; K.sim_start = sp.sim_start; K.sim_step = sp.sim_step; K.nrows = sp.nrows;
+  K.ctrl_event = b->d_ctrl_event; K.ctrl_value = b->d_ctrl_value;
+  int grid = b->W;
+  if (grid > b->max_ctas) grid = b->max_ctas;   // persistent: each CTA walks worlds w, w+grid, ...
+  sg_step_kernel<T><<<grid, 32, b->L.bytes, s>>>(K);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+#endif
+
+template <typename T>
+static int launch_v2(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
+  KArgs2<T> K{};
+  K.D = b->D; K.L = b->L2;
+  // fold the (possibly updated) model-level masks / stiffness targets into this launch
+  K.D.stiff_tendon0 = b->model->plan.d.stiff_tendon0;
+  K.D.cap_mask = b->model->plan.d.cap_mask; K.D.sph_mask = b->model->plan.d.sph_mask;
+  K.C = make_cst<T>(K.D);
+  K.tab = (const T*)b->tab; K.itab = b->itab; K.nworlds = b->W;
+  K.scratch = b->scratch;
+  K.qpos = (T*)b->qpos; K.qvel = (T*)b->qvel; K.warm = (T*)b->warm; K.act = (T*)b->act; K.ctrl = (T*)b->ctrl;
+  K.p_stiff = b->has_stiff ? b->p_stiff : nullptr; K.p_damp = b->has_damp ? b->p_damp : nullptr;
+  K.p_tdamp = b->has_tdamp ? b->p_tdamp : nullptr; K.p_objoff = b->has_objoff ? b->p_objoff : nullptr;
+  K.status = b->status;
+  K.debug_world = b->debug_world; K.debug_out = b->debug_out; K.debug_cap = b->debug_cap;
+  K.nsub = sp.nsub; K.integrate = sp.integrate; K.sens_out = (T*)sp.sens_out; K.touch_out = sp.touch_out;
+  K.rollout = sp.rollout; K.sim_start = sp.sim_start; K.sim_step = sp.sim_step; K.nrows = sp.nrows;
+  K.ctrl_event = b->d_ctrl_event; K.ctrl_value = b->d_ctrl_value;
+  const int wpw = 32 / b->lpw;
+  int grid = (b->W + wpw - 1) / wpw;
+  if (grid > b->max_ctas) grid = b->max_ctas;   // persistent: each CTA walks its groups of worlds
+  int e = k2_dispatch_launch<T>(b->lpw, K, grid, (size_t)b->L2.smem_stride * wpw, (void*)s);
+  if (e) return fail(std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)e));
+  return 0;
+}
+
+static int launch_any(sg_batch* b, const LaunchSpec& sp, void* stream) {
+  CUDA_OK(cudaSetDevice(b->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  b->launches++;
+#ifndef SG_SIMT_EMU
+  if (b->kernel == 1) return b->precision == 32 ? launch_v1<float>(b, sp, s) : launch_v1<double>(b, sp, s);
+#endif
+  return b->precision == 32 ? launch_v2<float>(b, sp, s) : launch_v2<double>(b, sp, s);
 }
 
 // tables are uploaded at batch creation; model-level edits made later (masks, stiffness targets) are
@@ -277,38 +392,17 @@ static int sync_tables(sg_batch* b) {
   return 0;
 }
 
-template <typename T>
-static int launch(sg_batch* b, KArgs<T>& K, cudaStream_t s) {
-  int grid = b->W;
-  if (K.rollout && grid > b->max_ctas) grid = b->max_ctas;   // persistent: each CTA walks worlds w, w+grid, ...
-  sg_step_kernel<T><<<grid, 32, b->L.bytes, s>>>(K);
-  b->launches++;
-  CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-static int do_step(sg_batch* b, int nsub, int integrate, void* sens_out, int* touch_out, void* stream) {
-  CUDA_OK(cudaSetDevice(b->device));
-  cudaStream_t s = (cudaStream_t)stream;
-  if (b->precision == 32) {
-    KArgs<float> K = make_args<float>(b);
-    K.nsub = nsub; K.integrate = integrate; K.sens_out = (float*)sens_out; K.touch_out = touch_out;
-    return launch<float>(b, K, s);
-  }
-  KArgs<double> K = make_args<double>(b);
-  K.nsub = nsub; K.integrate = integrate; K.sens_out = (double*)sens_out; K.touch_out = touch_out;
-  return launch<double>(b, K, s);
-}
-
 extern "C" int sg_batch_step(sg_batch* b, int nsub, void* sens_out, int* touch_out, void* stream) {
   if (!b) return fail("sg_batch_step: null batch");
   if (nsub < 1) return fail("sg_batch_step: nsub must be >= 1");
-  return do_step(b, nsub, 1, sens_out, touch_out, stream);
+  LaunchSpec sp; sp.nsub = nsub; sp.integrate = 1; sp.sens_out = sens_out; sp.touch_out = touch_out;
+  return launch_any(b, sp, stream);
 }
 
 extern "C" int sg_batch_forward(sg_batch* b, void* sens_out, int* touch_out, void* stream) {
   if (!b) return fail("sg_batch_forward: null batch");
-  return do_step(b, 1, 0, sens_out, touch_out, stream);
+  LaunchSpec sp; sp.nsub = 1; sp.integrate = 0; sp.sens_out = sens_out; sp.touch_out = touch_out;
+  return launch_any(b, sp, stream);
 }
 
 static int upload_schedule(sg_batch* b, const sg_schedule* sc, cudaStream_t s) {
@@ -335,16 +429,9 @@ extern "C" int sg_batch_rollout(sg_batch* b, const sg_schedule* sc, void* traj_o
   const size_t nu = b->D.nu > 0 ? b->D.nu : 1;
   CUDA_OK(cudaMemsetAsync(b->act, 0, b->esize * nu * b->W, s));
   CUDA_OK(cudaMemsetAsync(b->ctrl, 0, b->esize * nu * b->W, s));
-  if (b->precision == 32) {
-    KArgs<float> K = make_args<float>(b);
-    K.rollout = 1; K.sim_start = sc->sim_start; K.sim_step = sc->sim_step; K.nrows = sc->nrows;
-    K.ctrl_event = b->d_ctrl_event; K.ctrl_value = b->d_ctrl_value; K.sens_out = (float*)traj_out; K.touch_out = touch_out;
-    return launch<float>(b, K, s);
-  }
-  KArgs<double> K = make_args<double>(b);
-  K.rollout = 1; K.sim_start = sc->sim_start; K.sim_step = sc->sim_step; K.nrows = sc->nrows;
-  K.ctrl_event = b->d_ctrl_event; K.ctrl_value = b->d_ctrl_value; K.sens_out = (double*)traj_out; K.touch_out = touch_out;
-  return launch<double>(b, K, s);
+  LaunchSpec sp; sp.rollout = 1; sp.sim_start = sc->sim_start; sp.sim_step = sc->sim_step; sp.nrows = sc->nrows;
+  sp.sens_out = traj_out; sp.touch_out = touch_out;
+  return launch_any(b, sp, stream);
 }
 
 extern "C" int sg_batch_rollout_host(sg_batch* b, const sg_schedule* sc, const double* stiffness_host, void* traj_host,

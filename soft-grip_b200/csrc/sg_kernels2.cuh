@@ -1,0 +1,1411 @@
+// sg_kernels2.cuh -- sm_100a device code of the batched soft-gripper simulator (sub-warp worlds).
+//
+// A warp is split into 32/LPW groups of LPW lanes; each group owns one world (LPW = 8: four worlds per
+// warp).  The whole mj_step of a world (ref call site:
+// environment/manenv.py:49 `self.env.step()`) runs without leaving the SM:
+//
+//   gripper()         finger-chain kinematics, inertia, bias, actuation, sensor pre-data   (1 lane / chain)
+//   collide()         broadphase (lane / pair) -> candidates -> narrowphase (lane / candidate); contacts are
+//                     emitted in MuJoCo's canonical order by ballot compaction, then scheduled per lane
+//   rows_and_smooth() equality / tendon / limit rows (impedance, R, aref) and the smooth forces
+//   warmstart()       forces from qacc_warmstart, dual cost test, qacc = qacc_smooth + M^-1 J^T f
+//   pgs()             projected Gauss-Seidel in exact MuJoCo row order.  Equality rows are swept by
+//                     *dependency levels* (rows of a level touch disjoint dofs, so lanes update them at once
+//                     with the result of the sequential sweep); the dense volume-tendon row is a sub-warp
+//                     shuffle reduction; limits and elliptic contact blocks run one lane per finger chain with
+//                     the chain's accelerations and inverse inertia held in registers
+//   finish()/euler()  accelerometers, implicit-damping Euler, NaN checks
+//
+// What the sweeps touch stays in shared memory ("hot": the running qacc, two words per equality row, finger
+// inverse inertia).  The matrix AR = J M^-1 J^T + R is never formed.  Per equality row only u = R f - aref and R
+// are kept: the residual is J.qacc + u, and f itself is not needed (no clamp on equality rows).  Everything
+// that is touched once per step ("aux": qpos, qvel, smooth forces, contact records, candidate lists) lives
+// either in shared memory too or in an L2-resident global scratch slot of the group (Layout2::aux_in_smem).
+//
+// No tensor cores: nothing here is a dense contraction (largest dense objects: 4x4 finger inertia blocks,
+// 3x3 contact blocks).  The kernel is bound by issue slots / dependent-issue latency of the Gauss-Seidel
+// sweep; sub-warp worlds raise the useful lanes per issued instruction, small hot state raises resident warps.
+#pragma once
+#include <stdint.h>
+
+#include "sg_plan.hpp"
+#include "sg_math.cuh"
+
+namespace sg {
+
+#ifndef SG_ST_CON_FULL_BIT
+#define SG_ST_CON_FULL_BIT 2
+#define SG_ST_UNSUPPORTED_BIT 8
+#endif
+
+// contact record: 32 words of T, 16-byte aligned groups
+enum { CR_JG = 0 /*12*/, CR_NS = 12 /*3*/, CR_IWE = 15, CR_AREF = 16 /*3*/, CR_R0 = 19, CR_A = 20 /*6: 00 01 02 11 12 22*/,
+       CR_R1 = 26, CR_F = 28 /*3*/, CR_STRIDE = 32 };
+
+// per-world memory plan.  Offsets are in elements (T for the real arrays, int for the int arrays).
+struct Layout2 {
+  // hot, always shared memory
+  int a;                 // nv (+ pad)
+  int row2;              // 2*nrow : (u, R) per equality row, schedule order
+  int minv;              // 16*MAXCHAIN
+  int hotT;
+  int h_misc;            // 8 ints
+  int hotI;
+  // aux: shared memory or global scratch
+  int q, v, qs, jtf, a0; // nv each (a0: qacc_warmstart at step entry, for the re-run after a divergence reset)
+  int act, ctrl, actdot; // nu each
+  int g_axis, g_anchor;  // 3*MAXFD each
+  int g_box;             // 12 per moving box
+  int s_jv, s_ab, s_rot; // per sensor: 12, 3, 9
+  int sens;              // nsd
+  int lim;               // 3*MAXFD : f, aref, R per finger dof (valid where the limit is active)
+  int crec;              // CR_STRIDE * maxcon
+  int auxT;
+  int i_con;             // maxcon : (chain+1) | (slider+1) << 4
+  int i_tl;              // maxcon : time | lane << 16
+  int i_order;           // maxcon : contact index | time << 16, segmented by lane
+  int i_cand;            // max(maxcand, ns)
+  int i_lmask;           // MAXCHAIN : active-limit masks (bit jl: lower, bit 4+jl: upper)
+  int auxI;
+  int aux_in_smem;
+  int smem_stride;       // bytes per world in shared memory (multiple of 16, bank-skewed)
+  int gs_stride;         // bytes per world in the global scratch (0 when aux_in_smem)
+};
+
+enum { M2_NCON = 0, M2_STATUS = 1, M2_TOUCH = 2, M2_NCONTOT = 3, M2_ITERS = 4, M2_NCAND = 5, M2_TMAX = 6, M2_NLIM = 7 };
+
+template <typename T>
+inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw) {
+  Layout2 L{};
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };   // keep every array 16-byte aligned (float4 loads)
+  L.a = take(D.nv + 1); L.row2 = take(2 * D.nrow); L.minv = take(16 * MAXCHAIN);
+  L.hotT = o;
+  L.h_misc = 0; L.hotI = 8;
+  o = 0;
+  L.q = take(D.nv); L.v = take(D.nv); L.qs = take(D.nv); L.jtf = take(D.nv); L.a0 = take(D.nv);
+  const int nu = D.nu > 0 ? D.nu : 1;
+  L.act = take(nu); L.ctrl = take(nu); L.actdot = take(nu);
+  L.g_axis = take(3 * MAXFD); L.g_anchor = take(3 * MAXFD); L.g_box = take(12 * MAXCHAIN * MAXCB);
+  L.s_jv = take(12 * MAXSENS); L.s_ab = take(3 * MAXSENS); L.s_rot = take(9 * MAXSENS); L.sens = take(D.nsd > 0 ? D.nsd : 1);
+  L.lim = take(3 * MAXFD);
+  L.crec = take(CR_STRIDE * D.maxcon);
+  L.auxT = o;
+  int io = 0;
+  auto takei = [&](int n) { int r = io; io += (n + 3) & ~3; return r; };
+  L.i_con = takei(D.maxcon); L.i_tl = takei(D.maxcon); L.i_order = takei(D.maxcon);
+  L.i_cand = takei(D.maxcand > D.ns ? D.maxcand : D.ns); L.i_lmask = takei(MAXCHAIN);
+  L.auxI = io;
+  L.aux_in_smem = aux_in_smem;
+  size_t hot = sizeof(T) * (size_t)L.hotT + sizeof(int) * (size_t)L.hotI;
+  size_t aux = sizeof(T) * (size_t)L.auxT + sizeof(int) * (size_t)L.auxI;
+  size_t sb = hot + (aux_in_smem ? aux : 0);
+  sb = (sb + 15) & ~(size_t)15;
+  // skew consecutive worlds of a warp by 32/wpw banks so that the same offset in different groups hits different banks
+  if (wpw > 1) { const size_t want = (size_t)(128 / wpw) < 16 ? 16 : (size_t)(128 / wpw); while (sb % 128 != want % 128) sb += 16; }
+  L.smem_stride = (int)sb;
+  L.gs_stride = aux_in_smem ? 0 : (int)((aux + 127) & ~(size_t)127);
+  return L;
+}
+
+// model constants in kernel precision
+template <typename T>
+struct Cst {
+  T h, g[3], tol, impratio, impr_scale;
+  T eqj_K, eqj_B, eqj_si[7];
+  T eqt_K, eqt_B, eqt_si[7], ten_iw, ten_k0, ten_d0, ten_lspring, ten_l0;
+  T lim_K, lim_B, lim_si[7];
+  T con_K, con_B, con_si[7], con_fr;
+  T cap_r, cap_hl, sph_r, sph_pos[3], obj_pos[3];
+  int cap_mask, sph_mask;
+};
+
+template <typename T>
+inline void fill_si(T* o, const double* si) {
+  for (int k = 0; k < 5; k++) o[k] = (T)si[k];
+  o[5] = (T)(1.0 / std::pow(si[3], si[4] - 1.0));
+  o[6] = (T)(1.0 / std::pow(1.0 - si[3], si[4] - 1.0));
+}
+template <typename T>
+inline Cst<T> make_cst(const PlanDims& D) {
+  Cst<T> C{};
+  C.h = (T)D.h; for (int k = 0; k < 3; k++) { C.g[k] = (T)D.g[k]; C.sph_pos[k] = (T)D.sph_pos[k]; C.obj_pos[k] = (T)D.obj_pos[k]; }
+  C.tol = (T)D.tol; C.impratio = (T)D.impratio; C.impr_scale = (T)D.impr_scale;
+  C.eqj_K = (T)D.eqj_K; C.eqj_B = (T)D.eqj_B; fill_si(C.eqj_si, D.eqj_solimp);
+  C.eqt_K = (T)D.eqt_K; C.eqt_B = (T)D.eqt_B; fill_si(C.eqt_si, D.eqt_solimp);
+  C.ten_iw = (T)D.ten_iw; C.ten_k0 = (T)D.ten_k0; C.ten_d0 = (T)D.ten_d0; C.ten_lspring = (T)D.ten_lspring; C.ten_l0 = (T)D.ten_l0;
+  C.lim_K = (T)D.lim_K; C.lim_B = (T)D.lim_B; fill_si(C.lim_si, D.lim_solimp);
+  C.con_K = (T)D.con_K; C.con_B = (T)D.con_B; fill_si(C.con_si, D.con_solimp); C.con_fr = (T)D.con_fr;
+  C.cap_r = (T)D.cap_r; C.cap_hl = (T)D.cap_hl; C.sph_r = (T)D.sph_r;
+  C.cap_mask = (int)D.cap_mask; C.sph_mask = (int)D.sph_mask;
+  return C;
+}
+
+template <typename T>
+struct KArgs2 {
+  PlanDims D;
+  Cst<T> C;
+  Layout2 L;
+  const T* tab;
+  const int* itab;
+  int nworlds;
+  unsigned char* scratch;      // global aux slots [gridDim.x * WPW][L.gs_stride] (null when aux_in_smem)
+  // state, world-major
+  T *qpos, *qvel, *warm, *act, *ctrl;
+  const double *p_stiff, *p_damp, *p_tdamp, *p_objoff;
+  int* status;
+  T* sens_out;          // step: [W][nsd]; rollout: [W][nrows][nsd]
+  int* touch_out;       // step: [W];      rollout: [W][nrows]
+  int nsub, integrate;
+  int rollout, sim_start, sim_step, nrows;
+  const int* ctrl_event;
+  const double* ctrl_value;
+  int debug_world;
+  double* debug_out;
+  int debug_cap;
+};
+
+// reciprocal used inside the sweeps: one MUFU on the fp32 fast path, an IEEE division in the verification build
+template <typename T> __device__ __forceinline__ T trcp(T x);
+template <> __device__ __forceinline__ double trcp<double>(double x) { return 1.0 / x; }
+template <> __device__ __forceinline__ float trcp<float>(float x) {
+#ifdef __CUDA_ARCH__
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return 1.0f / x;
+#endif
+}
+
+template <typename T> __device__ __forceinline__ T powp(T x, T pw) { return pw == T(2) ? x * x : tpow(x, pw); }
+// getimpedance with pre-sanitised solimp and host-precomputed 1/mid^(p-1), 1/(1-mid)^(p-1)  
+template <typename T> __device__ __forceinline__ T impedance2(const T* si, T pos) {
+  const T d0 = si[0], d1 = si[1], w = si[2], mid = si[3], pw = si[4];
+  if (d0 == d1 || w <= T(SG_MINVAL)) return T(0.5) * (d0 + d1);
+  const T x = tabs(pos / w);
+  if (x >= T(1)) return d1;
+  if (x <= T(0)) return d0;
+  T y;
+  if (pw == T(1)) y = x;
+  else if (x <= mid) y = powp(x, pw) * si[5];
+  else y = T(1) - powp(T(1) - x, pw) * si[6];
+  return d0 + y * (d1 - d0);
+}
+
+template <typename T> __device__ __forceinline__ void ld4(const T* p, T* o);
+template <> __device__ __forceinline__ void ld4<float>(const float* p, float* o) {
+  const float4 v = *reinterpret_cast<const float4*>(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+template <> __device__ __forceinline__ void ld4<double>(const double* p, double* o) {
+  const double2 v0 = *reinterpret_cast<const double2*>(p), v1 = *reinterpret_cast<const double2*>(p + 2);
+  o[0] = v0.x; o[1] = v0.y; o[2] = v1.x; o[3] = v1.y;
+}
+template <typename T> __device__ __forceinline__ void ld2(const T* p, T& x, T& y);
+template <> __device__ __forceinline__ void ld2<float>(const float* p, float& x, float& y) { const float2 v = *reinterpret_cast<const float2*>(p); x = v.x; y = v.y; }
+template <> __device__ __forceinline__ void ld2<double>(const double* p, double& x, double& y) { const double2 v = *reinterpret_cast<const double2*>(p); x = v.x; y = v.y; }
+
+// ---------------------------------------------------------------------------------------------
+// the world
+// ---------------------------------------------------------------------------------------------
+template <typename T, int LPW>
+struct World2 {
+  static_assert(LPW >= MAXCHAIN && LPW <= 32 && (LPW & (LPW - 1)) == 0, "lanes per world: power of two, one lane per finger chain");
+  static constexpr int WPW = 32 / LPW;
+  static constexpr unsigned LOWMASK = LPW == 32 ? 0xffffffffu : ((1u << (LPW & 31)) - 1u);
+  const KArgs2<T>& K;
+  const PlanDims& D;
+  const Cst<T>& C;
+  const Layout2& L;
+  T* hot; int* hoti; T* aux; int* auxi;
+  int lane, grp, sl, gshift, w;
+  bool valid;
+  T kw, dw, tdw, off[3];
+
+  __device__ World2(const KArgs2<T>& k, unsigned char* smem, int wid, bool ok)
+      : K(k), D(k.D), C(k.C), L(k.L), w(wid), valid(ok) {
+    lane = threadIdx.x & 31; grp = lane / LPW; sl = lane % LPW; gshift = grp * LPW;
+    unsigned char* base = smem + (size_t)grp * L.smem_stride;
+    hot = reinterpret_cast<T*>(base);
+    hoti = reinterpret_cast<int*>(hot + L.hotT);
+    if (L.aux_in_smem) aux = reinterpret_cast<T*>(hoti + L.hotI);
+    else aux = reinterpret_cast<T*>(K.scratch + ((size_t)blockIdx.x * WPW + grp) * (size_t)L.gs_stride);
+    auxi = reinterpret_cast<int*>(aux + L.auxT);
+  }
+
+  __device__ __forceinline__ const T* tab(int o) const { return K.tab + o; }
+  __device__ __forceinline__ const int* itab(int o) const { return K.itab + o; }
+  __device__ __forceinline__ T* q() { return aux + L.q; }
+  __device__ __forceinline__ T* v() { return aux + L.v; }
+  __device__ __forceinline__ T* a() { return hot + L.a; }
+  __device__ __forceinline__ T* qs() { return aux + L.qs; }
+  __device__ __forceinline__ int& misc(int i) { return hoti[L.h_misc + i]; }
+  __device__ __forceinline__ T* crec(int i) { return aux + L.crec + CR_STRIDE * i; }
+
+  // sub-warp collectives (every lane of the warp takes part; results are per group)
+  __device__ __forceinline__ T gsum(T x) const {
+#pragma unroll
+    for (int o = LPW / 2; o > 0; o >>= 1) x += __shfl_xor_sync(FULLMASK, x, o);
+    return x;
+  }
+  __device__ __forceinline__ int gmax(int x) const {
+#pragma unroll
+    for (int o = LPW / 2; o > 0; o >>= 1) { const int y = __shfl_xor_sync(FULLMASK, x, o); x = x > y ? x : y; }
+    return x;
+  }
+  __device__ __forceinline__ int gor(int x) const {
+#pragma unroll
+    for (int o = LPW / 2; o > 0; o >>= 1) x |= __shfl_xor_sync(FULLMASK, x, o);
+    return x;
+  }
+  __device__ __forceinline__ unsigned gballot(bool p) const { return (__ballot_sync(FULLMASK, p) >> gshift) & LOWMASK; }
+  __device__ __forceinline__ int wmax(int x) const { return __reduce_max_sync(FULLMASK, x); }
+
+  __device__ void load_params() {
+    kw = K.p_stiff ? T(K.p_stiff[w]) : T(-1);
+    dw = K.p_damp ? T(K.p_damp[w]) : T(-1);
+    tdw = K.p_tdamp ? T(K.p_tdamp[w]) : T(-1);
+#pragma unroll
+    for (int k = 0; k < 3; k++) off[k] = C.obj_pos[k] + (K.p_objoff ? T(K.p_objoff[3 * (size_t)w + k]) : T(0));
+  }
+  __device__ __forceinline__ T stiffness(int e) const { return (kw >= T(0) && itab(D.io_kmask)[e]) ? kw : tab(D.o_sl_k0)[e]; }
+  __device__ __forceinline__ T damping(int e) const { return dw >= T(0) ? dw : tab(D.o_sl_d0)[e]; }
+  __device__ __forceinline__ T ten_stiffness() const { return (kw >= T(0) && D.stiff_tendon0) ? kw : C.ten_k0; }
+  __device__ __forceinline__ T ten_damping() const { return tdw >= T(0) ? tdw : C.ten_d0; }
+
+  // ------------------------------------------------------------------------------------------
+  // finger chains: kinematics, inertia, bias, actuation, sensors (one lane per chain)
+  // world-frame Jacobian formulation (independent of the oracle's com-based spatial algebra)
+  // ------------------------------------------------------------------------------------------
+  __device__ void gripper(int c) {
+    const T* ch = tab(D.o_chain + c * CH_STRIDE);
+    const int nd = D.ncd[c], nb = D.ncb[c], dof0 = D.chain_dof0[c];
+    T P[3], R[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) P[k] = ch[CH_BASEPOS + k];
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = ch[CH_BASEROT + k];
+    T axis[MAXCD][3], anch[MAXCD][3], bpos[MAXCB][3], brot[MAXCB][9], com[MAXCB][3], Iw[MAXCB][6], om[MAXCB][3];
+    int nsup[MAXCB];
+    int j = 0;
+#pragma unroll
+    for (int k = 0; k < MAXCB; k++) {
+      if (k >= nb) break;
+      const T* cb = ch + CH_BODY + k * CB_STRIDE;
+      T pos[3], Rc[9], t[3];
+      matvec3(t, R, cb + CB_POS);
+#pragma unroll
+      for (int i = 0; i < 3; i++) pos[i] = P[i] + t[i];
+      matmul3(Rc, R, cb + CB_ROT);
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) {
+        if (jj != j || j >= nd) continue;
+        const T* cd = ch + CH_DOF + j * CD_STRIDE;
+        if ((int)cd[CD_BODY] != k) continue;
+        matvec3(axis[j], Rc, cd + CD_AXIS);
+        matvec3(t, Rc, cd + CD_JPOS);
+#pragma unroll
+        for (int i = 0; i < 3; i++) anch[j][i] = pos[i] + t[i];
+        // Rodrigues rotation about the local axis by q
+        T s, co; tsincos(q()[dof0 + j], &s, &co);
+        const T ux = cd[CD_AXIS], uy = cd[CD_AXIS + 1], uz = cd[CD_AXIS + 2], oc = T(1) - co;
+        T Rj[9] = {co + ux * ux * oc, ux * uy * oc - uz * s, ux * uz * oc + uy * s,
+                   uy * ux * oc + uz * s, co + uy * uy * oc, uy * uz * oc - ux * s,
+                   uz * ux * oc - uy * s, uz * uy * oc + ux * s, co + uz * uz * oc};
+        matmul3(Rc, Rc, Rj);
+        matvec3(t, Rc, cd + CD_JPOS);
+#pragma unroll
+        for (int i = 0; i < 3; i++) pos[i] = anch[j][i] - t[i];
+        j++;
+      }
+      nsup[k] = j;
+#pragma unroll
+      for (int i = 0; i < 3; i++) { bpos[k][i] = pos[i]; P[i] = pos[i]; }
+#pragma unroll
+      for (int i = 0; i < 9; i++) { brot[k][i] = Rc[i]; R[i] = Rc[i]; }
+      matvec3(t, Rc, cb + CB_IPOS);
+#pragma unroll
+      for (int i = 0; i < 3; i++) com[k][i] = pos[i] + t[i];
+      T Ri[9]; matmul3(Ri, Rc, cb + CB_IROT);
+      const T I0 = cb[CB_INERTIA], I1 = cb[CB_INERTIA + 1], I2 = cb[CB_INERTIA + 2];
+      Iw[k][0] = Ri[0] * Ri[0] * I0 + Ri[1] * Ri[1] * I1 + Ri[2] * Ri[2] * I2;   // xx
+      Iw[k][1] = Ri[3] * Ri[3] * I0 + Ri[4] * Ri[4] * I1 + Ri[5] * Ri[5] * I2;   // yy
+      Iw[k][2] = Ri[6] * Ri[6] * I0 + Ri[7] * Ri[7] * I1 + Ri[8] * Ri[8] * I2;   // zz
+      Iw[k][3] = Ri[0] * Ri[3] * I0 + Ri[1] * Ri[4] * I1 + Ri[2] * Ri[5] * I2;   // xy
+      Iw[k][4] = Ri[0] * Ri[6] * I0 + Ri[1] * Ri[7] * I1 + Ri[2] * Ri[8] * I2;   // xz
+      Iw[k][5] = Ri[3] * Ri[6] * I0 + Ri[4] * Ri[7] * I1 + Ri[5] * Ri[8] * I2;   // yz
+      // box geom pose -> aux
+      T* gb = aux + L.g_box + 12 * (c * MAXCB + k);
+      matvec3(t, Rc, cb + CB_GPOS);
+#pragma unroll
+      for (int i = 0; i < 3; i++) gb[i] = pos[i] + t[i];
+      T Rg[9]; matmul3(Rg, Rc, cb + CB_GROT);
+#pragma unroll
+      for (int i = 0; i < 9; i++) gb[3 + i] = Rg[i];
+    }
+#pragma unroll
+    for (int jj = 0; jj < MAXCD; jj++) {
+      if (jj >= nd) break;
+#pragma unroll
+      for (int i = 0; i < 3; i++) { aux[L.g_axis + 3 * (dof0 + jj) + i] = axis[jj][i]; aux[L.g_anchor + 3 * (dof0 + jj) + i] = anch[jj][i]; }
+    }
+    // velocity-dependent terms
+    T qv[MAXCD], da[MAXCD][3], va[MAXCD][3];
+#pragma unroll
+    for (int jj = 0; jj < MAXCD; jj++) qv[jj] = jj < nd ? v()[dof0 + jj] : T(0);
+#pragma unroll
+    for (int jj = 0; jj < MAXCD; jj++) {
+      T wb[3] = {0, 0, 0};
+      va[jj][0] = va[jj][1] = va[jj][2] = 0;
+      if (jj < nd) {
+#pragma unroll
+        for (int i = 0; i < MAXCD; i++) {
+          if (i >= jj) break;
+          T r[3] = {anch[jj][0] - anch[i][0], anch[jj][1] - anch[i][1], anch[jj][2] - anch[i][2]}, t[3];
+          cross3(t, axis[i], r);
+#pragma unroll
+          for (int k = 0; k < 3; k++) { wb[k] += axis[i][k] * qv[i]; va[jj][k] += t[k] * qv[i]; }
+        }
+        cross3(da[jj], wb, axis[jj]);
+      } else { da[jj][0] = da[jj][1] = da[jj][2] = 0; }
+    }
+    auto point_terms = [&](const T* p, int ns_, T Jv[MAXCD][3], T* vp, T* ab) {
+      vp[0] = vp[1] = vp[2] = 0; ab[0] = ab[1] = ab[2] = 0;
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) {
+        if (jj >= ns_) { Jv[jj][0] = Jv[jj][1] = Jv[jj][2] = 0; continue; }
+        T r[3] = {p[0] - anch[jj][0], p[1] - anch[jj][1], p[2] - anch[jj][2]};
+        cross3(Jv[jj], axis[jj], r);
+#pragma unroll
+        for (int k = 0; k < 3; k++) vp[k] += Jv[jj][k] * qv[jj];
+      }
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) {
+        if (jj >= ns_) continue;
+        T r[3] = {p[0] - anch[jj][0], p[1] - anch[jj][1], p[2] - anch[jj][2]}, t1[3], t2[3];
+        T dv[3] = {vp[0] - va[jj][0], vp[1] - va[jj][1], vp[2] - va[jj][2]};
+        cross3(t1, da[jj], r); cross3(t2, axis[jj], dv);
+#pragma unroll
+        for (int k = 0; k < 3; k++) ab[k] += (t1[k] + t2[k]) * qv[jj];
+      }
+    };
+    T M[MAXCD][MAXCD], frc[MAXCD];
+#pragma unroll
+    for (int i = 0; i < MAXCD; i++) { frc[i] = 0;
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) M[i][jj] = (i == jj && i >= nd) ? T(1) : T(0); }
+    const T g[3] = {C.g[0], C.g[1], C.g[2]};
+#pragma unroll
+    for (int k = 0; k < MAXCB; k++) {
+      if (k >= nb) break;
+      const T* cb = ch + CH_BODY + k * CB_STRIDE;
+      const T mass = cb[CB_MASS];
+      T Jv[MAXCD][3], vc[3], ac[3], al[3] = {0, 0, 0};
+      om[k][0] = om[k][1] = om[k][2] = 0;
+      point_terms(com[k], nsup[k], Jv, vc, ac);
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) {
+        if (jj >= nsup[k]) break;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { om[k][i] += axis[jj][i] * qv[jj]; al[i] += da[jj][i] * qv[jj]; }
+      }
+      auto Imul = [&](const T* x, T* y) {
+        y[0] = Iw[k][0] * x[0] + Iw[k][3] * x[1] + Iw[k][4] * x[2];
+        y[1] = Iw[k][3] * x[0] + Iw[k][1] * x[1] + Iw[k][5] * x[2];
+        y[2] = Iw[k][4] * x[0] + Iw[k][5] * x[1] + Iw[k][2] * x[2];
+      };
+      T F[3] = {mass * (ac[0] - g[0]), mass * (ac[1] - g[1]), mass * (ac[2] - g[2])};
+      T Ial[3], Iom[3], N[3];
+      Imul(al, Ial); Imul(om[k], Iom); cross3(N, om[k], Iom);
+#pragma unroll
+      for (int i = 0; i < 3; i++) N[i] += Ial[i];
+#pragma unroll
+      for (int i = 0; i < MAXCD; i++) {
+        if (i >= nsup[k]) break;
+        frc[i] -= dot3(Jv[i], F) + dot3(axis[i], N);       // -qfrc_bias
+        T Ia[3]; Imul(axis[i], Ia);
+#pragma unroll
+        for (int jj = 0; jj < MAXCD; jj++) {
+          if (jj > i) break;
+          T mij = mass * dot3(Jv[i], Jv[jj]) + dot3(axis[jj], Ia);
+          M[i][jj] += mij;
+          if (jj != i) M[jj][i] += mij;
+        }
+      }
+    }
+    // actuation through the chain's spatial tendon (cylinder: filter dynamics, force = gain*act)
+    const T* ct = ch + CH_TEN;
+    if (ct[CT_HAS] != T(0)) {
+      const int kb = (int)ct[CT_BODY], u = (int)ct[CT_ACT];
+      T s1[3], t[3], dir[3];
+      matvec3(t, brot[kb], ct + CT_S1);
+#pragma unroll
+      for (int i = 0; i < 3; i++) { s1[i] = bpos[kb][i] + t[i]; dir[i] = s1[i] - ct[CT_S0 + i]; }
+      normalize3(dir);
+      if (u >= 0) {
+        const T actv = aux[L.act + u], ctrlv = aux[L.ctrl + u];
+        aux[L.actdot + u] = (ctrlv - actv) / tmax(T(SG_MINVAL), ct[CT_TIMECONST]);
+        const T force = ct[CT_GAIN] * actv;
+#pragma unroll
+        for (int jj = 0; jj < MAXCD; jj++) {
+          if (jj >= nsup[kb]) break;
+          T r[3] = {s1[0] - anch[jj][0], s1[1] - anch[jj][1], s1[2] - anch[jj][2]}, jc[3];
+          cross3(jc, axis[jj], r);
+          frc[jj] += ct[CT_GEAR] * dot3(dir, jc) * force;
+        }
+      }
+    }
+    // M^-1 by Gauss-Jordan on the (padded) 4x4 SPD block
+    T Mi[MAXCD][MAXCD];
+#pragma unroll
+    for (int i = 0; i < MAXCD; i++)
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) Mi[i][jj] = i == jj ? T(1) : T(0);
+#pragma unroll
+    for (int p = 0; p < MAXCD; p++) {
+      const T ip = T(1) / M[p][p];
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) { M[p][jj] *= ip; Mi[p][jj] *= ip; }
+#pragma unroll
+      for (int i = 0; i < MAXCD; i++) {
+        if (i == p) continue;
+        const T f = M[i][p];
+#pragma unroll
+        for (int jj = 0; jj < MAXCD; jj++) { M[i][jj] -= f * M[p][jj]; Mi[i][jj] -= f * Mi[p][jj]; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXCD; i++) {
+      T s = 0;
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) { hot[L.minv + 16 * c + 4 * i + jj] = Mi[i][jj]; s += Mi[i][jj] * frc[jj]; }
+      if (i < nd) qs()[dof0 + i] = s;
+    }
+    // sensors on this chain (gyro now; accelerometer pre-data, finished after the solve)
+    for (int s = 0; s < D.nsens; s++) {
+      const T* se = tab(D.o_sens + s * SE_STRIDE);
+      if ((int)se[SE_CHAIN] != c) continue;
+      const int k = (int)se[SE_BODY], adr = (int)se[SE_ADR];
+      T Rs[9]; matmul3(Rs, brot[k], se + SE_ROT);
+      if ((int)se[SE_TYPE] == SENS_GYRO) {
+        T o[3]; matTvec3(o, Rs, om[k]);
+#pragma unroll
+        for (int i = 0; i < 3; i++) aux[L.sens + adr + i] = o[i];
+      } else {
+        T p[3], t[3], Jv[MAXCD][3], vp[3], ab[3];
+        matvec3(t, brot[k], se + SE_POS);
+#pragma unroll
+        for (int i = 0; i < 3; i++) p[i] = bpos[k][i] + t[i];
+        point_terms(p, nsup[k], Jv, vp, ab);
+#pragma unroll
+        for (int jj = 0; jj < MAXCD; jj++)
+#pragma unroll
+          for (int i = 0; i < 3; i++) aux[L.s_jv + 12 * s + 3 * jj + i] = Jv[jj][i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) aux[L.s_ab + 3 * s + i] = ab[i] - g[i];
+#pragma unroll
+        for (int i = 0; i < 9; i++) aux[L.s_rot + 9 * s + i] = Rs[i];
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // collision + contact rows
+  // ------------------------------------------------------------------------------------------
+  __device__ __forceinline__ void capsule_center(int e, T* c) {
+    const T* c0 = tab(D.o_sl_cap0) + 3 * e; const T* ax = tab(D.o_sl_axis) + 3 * e;
+    const T qe = q()[D.nfd + e];
+#pragma unroll
+    for (int k = 0; k < 3; k++) c[k] = off[k] + c0[k] + ax[k] * qe;
+  }
+  __device__ __forceinline__ void collider_pose(int ci, T* pos, T* rot) {
+    const T* co = tab(D.o_coll + ci * CO_STRIDE);
+    const int c = (int)co[CO_CHAIN];
+    if (c < 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) pos[k] = co[CO_POS + k];
+#pragma unroll
+      for (int k = 0; k < 9; k++) rot[k] = co[CO_ROT + k];
+    } else {
+      const T* gb = aux + L.g_box + 12 * (c * MAXCB + (int)co[CO_BODY]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) pos[k] = gb[k];
+#pragma unroll
+      for (int k = 0; k < 9; k++) rot[k] = gb[3 + k];
+    }
+  }
+
+  // builds the three rows of one contact into record `slot` (mj_instantiateContact + mj_makeImpedance +
+  // mj_referenceConstraint + the diagonal block of efc_AR)
+  __device__ void contact_rows(int slot, const RawCon<T>& rc, int ci, int e, T slider_sign, bool dbg, int dbg_index) {
+    const T* co = tab(D.o_coll + ci * CO_STRIDE);
+    const int c = (int)co[CO_CHAIN];
+    T fr[9];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { fr[k] = rc.nrm[k]; fr[3 + k] = rc.hint[k]; }
+    make_frame(fr);
+    T Jg[3][MAXCD];
+    T* cr = crec(slot);
+    int nsupp = 0, dof0 = 0;
+    if (c >= 0) {
+      dof0 = D.chain_dof0[c];
+      const T* ch = tab(D.o_chain + c * CH_STRIDE);
+      const int kb = (int)co[CO_BODY];
+      for (int jj = 0; jj < D.ncd[c]; jj++) if ((int)ch[CH_DOF + jj * CD_STRIDE + CD_BODY] <= kb) nsupp = jj + 1;
+    }
+#pragma unroll
+    for (int jj = 0; jj < MAXCD; jj++) {
+      T col[3] = {0, 0, 0};
+      if (jj < nsupp) {
+        const T* ax = aux + L.g_axis + 3 * (dof0 + jj); const T* an = aux + L.g_anchor + 3 * (dof0 + jj);
+        T r[3] = {rc.pos[0] - an[0], rc.pos[1] - an[1], rc.pos[2] - an[2]};
+        cross3(col, ax, r);
+      }
+#pragma unroll
+      for (int r = 0; r < 3; r++) { Jg[r][jj] = dot3(fr + 3 * r, col); cr[CR_JG + 4 * r + jj] = Jg[r][jj]; }
+    }
+    T ns[3] = {0, 0, 0}, iw_e = 0, biw = co[CO_BIW], ve = 0;
+    if (e >= 0) {
+      const T* ax = tab(D.o_sl_axis) + 3 * e;
+#pragma unroll
+      for (int r = 0; r < 3; r++) ns[r] = slider_sign * dot3(fr + 3 * r, ax);
+      iw_e = T(1) / tab(D.o_sl_m)[e];
+      biw += tab(D.o_sl_biw)[e];
+      ve = v()[D.nfd + e];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++) cr[CR_NS + r] = ns[r];
+    cr[CR_IWE] = iw_e;
+    const T imp = impedance2<T>(C.con_si, rc.dist);
+    const T R0 = tmax(T(SG_MINVAL), (T(1) - imp) * biw / imp);
+    const T R1 = R0 / tmax(T(SG_MINVAL), C.impratio);
+    cr[CR_R0] = R0; cr[CR_R1] = R1;
+    // velocity, aref
+    T vel[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      T s = ns[r] * ve;
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) if (jj < nsupp) s += Jg[r][jj] * v()[dof0 + jj];
+      vel[r] = s;
+    }
+    cr[CR_AREF] = -C.con_B * vel[0] - C.con_K * imp * rc.dist;
+    cr[CR_AREF + 1] = -C.con_B * vel[1];
+    cr[CR_AREF + 2] = -C.con_B * vel[2];
+    // A = Jg Minv Jg' + ns ns'/m + diag(R)
+    T MJ[3][MAXCD];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int i = 0; i < MAXCD; i++) {
+        T s = 0;
+        if (c >= 0) {
+#pragma unroll
+          for (int jj = 0; jj < MAXCD; jj++) s += hot[L.minv + 16 * c + 4 * i + jj] * Jg[r][jj];
+        }
+        MJ[r][i] = s;
+      }
+    int idx = 0;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int s2 = r; s2 < 3; s2++) {
+        T s = ns[r] * ns[s2] * iw_e;
+#pragma unroll
+        for (int jj = 0; jj < MAXCD; jj++) s += Jg[r][jj] * MJ[s2][jj];
+        if (r == s2) s += (r == 0 ? R0 : R1);
+        cr[CR_A + idx++] = s;    // order: 00 01 02 11 12 22
+      }
+    auxi[L.i_con + slot] = (c + 1) | ((e + 1) << 4);
+    if (dbg && K.debug_out) {
+      double* o = K.debug_out + 64 + 16 * (size_t)dbg_index;   // dist, pos3, frame9
+      if (64 + 16 * (dbg_index + 1) <= K.debug_cap) {
+        o[0] = (double)rc.dist;
+        for (int k = 0; k < 3; k++) o[1 + k] = (double)rc.pos[k];
+        for (int k = 0; k < 9; k++) o[4 + k] = (double)fr[k];
+      }
+    }
+  }
+
+  __device__ void collide() {
+    const bool dbg = valid && (w == K.debug_world);
+    // ---- broadphase: bounding spheres, candidates compacted in pair order ----
+    int ncand = 0, flags = 0;
+    for (int base = 0; base < D.npair; base += LPW) {
+      const int p = base + sl;
+      bool pass = false;
+      if (p < D.npair) {
+        const int pt = itab(D.io_pair_t)[p], pa = itab(D.io_pair_a)[p], pb = itab(D.io_pair_b)[p];
+        const T* co = tab(D.o_coll + pa * CO_STRIDE);
+        T c2[3], rb2;
+        if (pt == PAIR_PLANE_CAPSULE || pt == PAIR_BOX_CAPSULE) { capsule_center(pb, c2); rb2 = C.cap_r + C.cap_hl; }
+        else if (pt == PAIR_SPHERE_BOX) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) c2[k] = off[k] + C.sph_pos[k];
+          rb2 = C.sph_r;
+        } else { T rot[9]; collider_pose(pb, c2, rot); rb2 = tab(D.o_coll + pb * CO_STRIDE)[CO_RBOUND]; }
+        T c1[3], rot1[9];
+        collider_pose(pa, c1, rot1);
+        T dif[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
+        if ((int)co[CO_TYPE] == GEOM_PLANE) { T nrm[3] = {rot1[2], rot1[5], rot1[8]}; pass = !(dot3(dif, nrm) > rb2); }
+        else { T bound = co[CO_RBOUND] + rb2; pass = !(dot3(dif, dif) > bound * bound); }
+        if (pass && pt == PAIR_BOX_CAPSULE) {
+          // mid-phase (prunes only): the capsule's bounding box in the frame of the box must overlap the box
+          T dl[3], al[3];
+          matTvec3(dl, rot1, dif);
+          matTvec3(al, rot1, tab(D.o_sl_axis) + 3 * pb);
+#pragma unroll
+          for (int k = 0; k < 3; k++) if (tabs(dl[k]) > co[CO_SIZE + k] + C.cap_r + C.cap_hl * tabs(al[k])) pass = false;
+        }
+      }
+      const unsigned m = gballot(pass);
+      if (pass) {
+        const int slot = ncand + __popc(m & ((1u << sl) - 1));
+        if (slot < D.maxcand) auxi[L.i_cand + slot] = p; else flags |= SG_ST_CON_FULL_BIT;
+      }
+      ncand += __popc(m);
+    }
+    if (ncand > D.maxcand) ncand = D.maxcand;
+    const int ncand_w = wmax(ncand);   // also orders the candidate writes before the reads below
+    // ---- narrowphase over the candidate list; contacts keep the pair order ----
+    int ncon = 0, ncontot = 0, touch = 0;
+    for (int base = 0; base < ncand_w; base += LPW) {
+      const int ci_ = base + sl;
+      RawCon<T> rc[2];
+      int n = 0, pa = 0, e = -1; T ssign = 0;
+      if (ci_ < ncand) {
+        const int p = auxi[L.i_cand + ci_];
+        const int pt = itab(D.io_pair_t)[p]; pa = itab(D.io_pair_a)[p]; const int pb = itab(D.io_pair_b)[p];
+        const T* co = tab(D.o_coll + pa * CO_STRIDE);
+        T c1[3], rot1[9];
+        collider_pose(pa, c1, rot1);
+        T size1[3] = {co[CO_SIZE], co[CO_SIZE + 1], co[CO_SIZE + 2]};
+        int mask = (int)co[CO_MASK];
+        if (pt == PAIR_PLANE_CAPSULE) {
+          T cc[3]; capsule_center(pb, cc);
+          n = plane_capsule(rc, c1, rot1, cc, tab(D.o_sl_axis) + 3 * pb, C.cap_r, C.cap_hl);
+          e = pb; ssign = 1; mask |= C.cap_mask;
+        } else if (pt == PAIR_BOX_CAPSULE) {
+          T cc[3]; capsule_center(pb, cc);
+          n = capsule_box(rc, cc, tab(D.o_sl_axis) + 3 * pb, C.cap_r, C.cap_hl, c1, rot1, size1);
+          e = pb; ssign = -1; mask |= C.cap_mask;
+        } else if (pt == PAIR_SPHERE_BOX) {
+          T sc[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) sc[k] = off[k] + C.sph_pos[k];
+          n = sphere_box(rc[0], sc, C.sph_r, c1, rot1, size1);
+          e = -1; mask |= C.sph_mask;
+        } else if (pt == PAIR_BOX_BOX) {
+          const T* co2 = tab(D.o_coll + pb * CO_STRIDE);
+          T c2[3], rot2[9]; collider_pose(pb, c2, rot2);
+          T size2[3] = {co2[CO_SIZE], co2[CO_SIZE + 1], co2[CO_SIZE + 2]};
+          if (box_box_overlap(c1, rot1, size1, c2, rot2, size2)) flags |= SG_ST_UNSUPPORTED_BIT;
+        } else flags |= SG_ST_UNSUPPORTED_BIT;
+        if (n > 0) { touch |= (1 << 30); if (mask & 1) touch |= (mask >> 1); }
+      }
+      // contacts with dist >= 0 (== includemargin) exist but carry no constraint rows
+      const int n_act = (n > 0 && rc[0].dist < T(0) ? 1 : 0) + (n > 1 && rc[1].dist < T(0) ? 1 : 0);
+      const unsigned m1 = gballot(n_act >= 1), m2 = gballot(n_act >= 2);
+      const unsigned t1 = gballot(n >= 1), t2 = gballot(n >= 2);
+      const unsigned lt = (1u << sl) - 1;
+      int slot = ncon + __popc(m1 & lt) + __popc(m2 & lt);
+      int dslot = ncontot + __popc(t1 & lt) + __popc(t2 & lt);
+      for (int i = 0; i < n; i++) {
+        if (rc[i].dist < T(0)) {
+          if (slot < D.maxcon) contact_rows(slot, rc[i], pa, e, ssign, dbg, dslot + i);
+          else flags |= SG_ST_CON_FULL_BIT;
+          slot++;
+        }
+      }
+      ncon += __popc(m1) + __popc(m2);
+      ncontot += __popc(t1) + __popc(t2);
+    }
+    if (ncon > D.maxcon) ncon = D.maxcon;
+    touch = gor(touch);
+    flags = gor(flags);
+    if (sl == 0) { misc(M2_NCON) = ncon; misc(M2_TOUCH) = touch; misc(M2_NCONTOT) = ncontot; misc(M2_STATUS) |= flags; misc(M2_NCAND) = ncand; }
+    __syncwarp();
+    // ---- Gauss-Seidel schedule of the contact blocks.  A block is processed by the lane of its finger chain
+    // (blocks against static colliders: the remaining lanes, round robin); its time slot is one more than the
+    // latest earlier block on the same lane or on the same slider -- exactly the dependencies of the
+    // sequential sweep of mj_solPGS, so the result equals the sequential one. ----
+    int* lastt = auxi + L.i_cand;     // per-slider latest time slot (the candidate list is dead by now)
+    constexpr int NFREE = LPW > MAXCHAIN ? LPW - MAXCHAIN : 0;
+    for (int i = sl; i < ncon; i += LPW) { const int e = (auxi[L.i_con + i] >> 4) - 1; if (e >= 0) lastt[e] = 0; }
+    __syncwarp();
+    int* lanet = auxi + L.i_order;    // per-lane latest time slot (the order list is built later, in pgs())
+    lanet[sl] = 0;
+    __syncwarp();
+    if (sl == 0) {
+      int tmax_ = 0, nstat = 0;
+      for (int i = 0; i < ncon; i++) {
+        const int ce = auxi[L.i_con + i];
+        const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
+        int ln;
+        if (c >= 0) ln = c % LPW;
+        else { ln = NFREE > 0 ? MAXCHAIN + (nstat % (NFREE > 0 ? NFREE : 1)) : nstat % LPW; nstat++; }
+        int t = lanet[ln];
+        if (e >= 0) { const int te = lastt[e]; if (te > t) t = te; }
+        t += 1;
+        lanet[ln] = t;
+        if (e >= 0) lastt[e] = t;
+        auxi[L.i_tl + i] = t | (ln << 16);
+        if (t > tmax_) tmax_ = t;
+      }
+      misc(M2_TMAX) = tmax_;
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // equality / tendon / limit rows and smooth dynamics of the shell
+  // ------------------------------------------------------------------------------------------
+  struct Tendon { T u, R, A, aref; };     // group-uniform registers: u = R f - aref
+  struct ChainRows {                      // registers of the lane that owns a finger chain
+    T ag[MAXCD];                          // running qacc of the chain dofs
+    T mv[MAXCD * MAXCD];                  // M^-1 block
+    T lf[MAXCD], laref[MAXCD], lR[MAXCD], lsgn[MAXCD];
+    int lmask;                            // bit jl: limit of local dof jl is active
+  };
+
+  __device__ void rows_and_smooth(Tendon& tn, T& Ft_out) {
+    const int nfd = D.nfd, ns = D.ns;
+    const bool dbg = valid && (w == K.debug_world) && K.debug_out;
+    // volume tendon: L = sum c_e q_e, Ldot = sum c_e v_e
+    T Ls = 0, Lv = 0, As = 0;
+    for (int e = sl; e < ns; e += LPW) {
+      const T tc = tab(D.o_sl_tc)[e];
+      Ls += tc * q()[nfd + e]; Lv += tc * v()[nfd + e]; As += tc * tc / tab(D.o_sl_m)[e];
+    }
+    Ls = gsum(Ls); Lv = gsum(Lv); As = gsum(As);
+    const T Ft = -ten_stiffness() * (Ls - C.ten_lspring) - ten_damping() * Lv;
+    Ft_out = Ft;
+    // sliders: qfrc_smooth = passive - bias  (bias = -m axis.g for a slider on a static parent)
+    for (int e = sl; e < ns; e += LPW) {
+      const T qe = q()[nfd + e], ve = v()[nfd + e], m = tab(D.o_sl_m)[e];
+      const T* ax = tab(D.o_sl_axis) + 3 * e;
+      T f = -stiffness(e) * qe - damping(e) * ve;
+      f += tab(D.o_sl_tc)[e] * Ft;
+      f -= -(m * (ax[0] * C.g[0] + ax[1] * C.g[1] + ax[2] * C.g[2]));
+      qs()[nfd + e] = f;
+    }
+    // joint-equality rows in schedule order: row2 = (aref, R) until the warm start turns aref into u
+    const int* rd = itab(D.io_row_d12);
+    T* row2 = hot + L.row2;
+    for (int p = sl; p < D.nrow; p += LPW) {
+      const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
+      T pos = q()[nfd + d1], vel = v()[nfd + d1], diag = tab(D.o_sl_iw)[d1];
+      if (d2 != 0xffff) { pos -= q()[nfd + d2]; vel -= v()[nfd + d2]; diag += tab(D.o_sl_iw)[d2]; }
+      const T imp = impedance2<T>(C.eqj_si, pos);
+      const T aref = -C.eqj_B * vel - C.eqj_K * imp * pos;
+      row2[2 * p] = aref;
+      row2[2 * p + 1] = tmax(T(SG_MINVAL), (T(1) - imp) * diag / imp);
+      if (dbg) K.debug_out[K.debug_cap - (D.nrow + 1) + p] = (double)aref;
+    }
+    {
+      const T pos = Ls - C.ten_l0;
+      const T imp = impedance2<T>(C.eqt_si, pos);
+      tn.R = tmax(T(SG_MINVAL), (T(1) - imp) * C.ten_iw / imp);
+      tn.aref = -C.eqt_B * Lv - C.eqt_K * imp * pos;
+      tn.A = As + tn.R;
+      tn.u = 0;
+    }
+    __syncwarp();
+  }
+
+  // joint limits of the chain owned by this lane, lower then upper, in joint order (mj_instantiateLimit)
+  __device__ void chain_limits(int c, ChainRows& cr) {
+    cr.lmask = 0;
+    const int d0 = D.chain_dof0[c];
+#pragma unroll
+    for (int jl = 0; jl < MAXCD; jl++) {
+      cr.lf[jl] = 0; cr.laref[jl] = 0; cr.lR[jl] = 1; cr.lsgn[jl] = 0;
+      if (jl >= D.ncd[c]) continue;
+      const T* cd = tab(D.o_chain + c * CH_STRIDE + CH_DOF + jl * CD_STRIDE);
+      if (cd[CD_LIMITED] == T(0)) continue;
+      const T qq = q()[d0 + jl];
+      const T dlo = qq - cd[CD_LO], dhi = cd[CD_HI] - qq;
+      T dist = 0, sgn = 0;
+      if (dlo < T(0)) { dist = dlo; sgn = 1; }
+      else if (dhi < T(0)) { dist = dhi; sgn = -1; }
+      else continue;
+      const T imp = impedance2<T>(C.lim_si, dist);
+      cr.lR[jl] = tmax(T(SG_MINVAL), (T(1) - imp) * cd[CD_IW] / imp);
+      cr.laref[jl] = -C.lim_B * (sgn * v()[d0 + jl]) - C.lim_K * imp * dist;
+      cr.lsgn[jl] = sgn;
+      cr.lmask |= 1 << jl;
+    }
+#pragma unroll
+    for (int k = 0; k < MAXCD * MAXCD; k++) cr.mv[k] = hot[L.minv + 16 * c + k];
+  }
+
+  __device__ __forceinline__ int chain_of(int dof) const {
+    int c = 0;
+    for (int k = 1; k < D.nchain; k++) if (dof >= D.chain_dof0[k]) c = k;
+    return c;
+  }
+
+  // elliptic-cone warm-start force of one contact from jar (mj_constraintUpdate zones)
+  __device__ __forceinline__ void cone_force(const T* jar, T R0, T R1, T* f) {
+    const T frc = C.con_fr, mu = frc * tsqrt(R1 / R0);
+    f[0] = -(T(1) / R0) * jar[0]; f[1] = -(T(1) / R1) * jar[1]; f[2] = -(T(1) / R1) * jar[2];
+    const T U0 = jar[0] * mu, U1 = jar[1] * frc, U2 = jar[2] * frc;
+    const T N = U0, Tn = tsqrt(U1 * U1 + U2 * U2);
+    if (N >= mu * Tn || (Tn <= T(0) && N >= T(0))) { f[0] = f[1] = f[2] = 0; }
+    else if (mu * N + Tn <= T(0) || (Tn <= T(0) && N < T(0))) { }
+    else {
+      const T Dm = (T(1) / R0) / (mu * mu * (T(1) + mu * mu)), NT = N - mu * Tn;
+      f[0] = -Dm * NT * mu;
+      f[1] = -f[0] / Tn * U1 * frc; f[2] = -f[0] / Tn * U2 * frc;
+    }
+  }
+
+  // warm start: forces from qacc_warmstart (in a()), kept only if the dual cost
+  // f.b + 0.5 f'AR f is not positive; leaves a() = qacc_smooth + M^-1 J^T f and row2 = (u, R)
+  __device__ void warmstart(Tendon& tn, ChainRows& cr) {
+    const int nfd = D.nfd, ns = D.ns;
+    const int ncon = misc(M2_NCON);
+    const int* rd = itab(D.io_row_d12);
+    T* row2 = hot + L.row2;
+    T* jtf = aux + L.jtf;
+    T cost = 0;
+    // equality rows: per-dof gather of J^T f over the rows of each slider (no scatter, no atomics)
+    T tja = 0, tjs = 0;
+    for (int e = sl; e < ns; e += LPW) {
+      const int* dr = itab(D.io_dof_rows) + e * MAXDOFROWS;
+      const T iwe = T(1) / tab(D.o_sl_m)[e];
+      T s = 0;
+#pragma unroll
+      for (int k = 0; k < MAXDOFROWS; k++) {
+        const int code = dr[k];
+        if (code >= 0) {
+          const int p = code >> 1;
+          const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
+          T ja = a()[nfd + d1], js = qs()[nfd + d1] / tab(D.o_sl_m)[d1];
+          if (d2 != 0xffff) { ja -= a()[nfd + d2]; js -= qs()[nfd + d2] / tab(D.o_sl_m)[d2]; }
+          const T ar = row2[2 * p], R = row2[2 * p + 1];
+          const T f = -(T(1) / R) * (ja - ar);
+          if (code & 1) s -= f;
+          else { s += f; cost += f * (js - ar) + T(0.5) * R * f * f; }   // the row's own cost: counted once, by its first dof
+        }
+      }
+      const T tc = tab(D.o_sl_tc)[e];
+      tja += tc * a()[nfd + e]; tjs += tc * qs()[nfd + e] * iwe;
+      jtf[nfd + e] = s;
+    }
+    tja = gsum(tja); tjs = gsum(tjs);
+    const T tf = -(T(1) / tn.R) * (tja - tn.aref);
+    if (sl == 0) cost += tf * (tjs - tn.aref) + T(0.5) * tn.R * tf * tf;
+    for (int e = sl; e < ns; e += LPW) jtf[nfd + e] += tab(D.o_sl_tc)[e] * tf;
+    // limits (registers of the chain lanes)
+    if (sl < D.nchain) {
+      const int d0 = D.chain_dof0[sl];
+#pragma unroll
+      for (int jl = 0; jl < MAXCD; jl++) {
+        if (jl < D.ncd[sl]) jtf[d0 + jl] = 0;
+        if (!(cr.lmask & (1 << jl))) continue;
+        const T sgn = cr.lsgn[jl];
+        const T jar = sgn * a()[d0 + jl] - cr.laref[jl];
+        const T f = jar >= T(0) ? T(0) : -(T(1) / cr.lR[jl]) * jar;
+        cr.lf[jl] = f;
+        jtf[d0 + jl] = sgn * f;
+        cost += f * (sgn * qs()[d0 + jl] - cr.laref[jl]) + T(0.5) * cr.lR[jl] * f * f;
+      }
+    }
+    // contacts
+    for (int i = sl; i < ncon; i += LPW) {
+      const int ce = auxi[L.i_con + i];
+      const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
+      T* r = crec(i);
+      const T R0 = r[CR_R0], R1 = r[CR_R1];
+      T jar[3], b[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        T sa = 0, sb = 0;
+        if (e >= 0) { sa = r[CR_NS + k] * a()[nfd + e]; sb = r[CR_NS + k] * (qs()[nfd + e] / tab(D.o_sl_m)[e]); }
+        if (c >= 0) for (int jj = 0; jj < D.ncd[c]; jj++) { sa += r[CR_JG + 4 * k + jj] * a()[D.chain_dof0[c] + jj]; sb += r[CR_JG + 4 * k + jj] * qs()[D.chain_dof0[c] + jj]; }
+        jar[k] = sa - r[CR_AREF + k]; b[k] = sb - r[CR_AREF + k];
+      }
+      T f[3];
+      cone_force(jar, R0, R1, f);
+      const T Rr[3] = {R0, R1, R1};
+#pragma unroll
+      for (int k = 0; k < 3; k++) { r[CR_F + k] = f[k]; cost += f[k] * b[k] + T(0.5) * Rr[k] * f[k] * f[k]; }
+    }
+    __syncwarp();
+    // J^T f of the contacts, added after the limits: serial in row order on one lane (deterministic)
+    if (sl == 0) {
+      for (int i = 0; i < ncon; i++) {
+        const int ce = auxi[L.i_con + i];
+        const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
+        const T* r = crec(i);
+        const T* f = r + CR_F;
+        if (e >= 0) jtf[nfd + e] += r[CR_NS] * f[0] + r[CR_NS + 1] * f[1] + r[CR_NS + 2] * f[2];
+        if (c >= 0) {
+          const int d0 = D.chain_dof0[c];
+          for (int jj = 0; jj < D.ncd[c]; jj++) jtf[d0 + jj] += r[CR_JG + jj] * f[0] + r[CR_JG + 4 + jj] * f[1] + r[CR_JG + 8 + jj] * f[2];
+        }
+      }
+    }
+    __syncwarp();
+    // 0.5 f' J M^-1 J' f = 0.5 jtf . (M^-1 jtf)
+    for (int e = sl; e < ns; e += LPW) { const T x = jtf[nfd + e]; cost += T(0.5) * x * x / tab(D.o_sl_m)[e]; }
+    for (int dof = sl; dof < nfd; dof += LPW) {
+      const int c = chain_of(dof), jl = dof - D.chain_dof0[c];
+      T s = 0;
+      for (int jj = 0; jj < D.ncd[c]; jj++) s += hot[L.minv + 16 * c + 4 * jl + jj] * jtf[D.chain_dof0[c] + jj];
+      cost += T(0.5) * jtf[dof] * s;
+    }
+    cost = gsum(cost);
+    const bool keep = !(cost > T(0));
+    // u = R f - aref:  kept -> -(J.qacc_warm),  dropped -> -aref
+    for (int p = sl; p < D.nrow; p += LPW) {
+      T u;
+      if (keep) {
+        const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
+        T ja = a()[nfd + d1];
+        if (d2 != 0xffff) ja -= a()[nfd + d2];
+        u = -ja;
+      } else u = -row2[2 * p];
+      row2[2 * p] = u;
+    }
+    tn.u = keep ? -tja : -tn.aref;
+    if (!keep) {
+      if (sl < D.nchain) {
+#pragma unroll
+        for (int jl = 0; jl < MAXCD; jl++) cr.lf[jl] = 0;
+      }
+      for (int i = sl; i < ncon; i += LPW) { T* r = crec(i); r[CR_F] = 0; r[CR_F + 1] = 0; r[CR_F + 2] = 0; }
+    }
+    __syncwarp();
+    // a = qacc_smooth + M^-1 jtf (or qacc_smooth alone)
+    for (int e = sl; e < ns; e += LPW) {
+      const T iw = T(1) / tab(D.o_sl_m)[e];
+      a()[nfd + e] = qs()[nfd + e] * iw + (keep ? jtf[nfd + e] * iw : T(0));
+    }
+    for (int dof = sl; dof < nfd; dof += LPW) {
+      const int c = chain_of(dof), jl = dof - D.chain_dof0[c];
+      T s = 0;
+      if (keep) for (int jj = 0; jj < D.ncd[c]; jj++) s += hot[L.minv + 16 * c + 4 * jl + jj] * jtf[D.chain_dof0[c] + jj];
+      a()[dof] = qs()[dof] + s;
+    }
+    __syncwarp();
+  }
+
+  // one elliptic contact block (mj_solPGS inner body, dim 3) on the lane that owns its chain
+  __device__ __forceinline__ T contact_block(int i, ChainRows& cr, bool has_chain) {
+    const int nfd = D.nfd;
+    T* r = crec(i);
+    T jg[12], w1[4], w2[4], w3[4];
+    ld4(r + CR_JG, jg); ld4(r + CR_JG + 4, jg + 4); ld4(r + CR_JG + 8, jg + 8);
+    ld4(r + CR_NS, w1);          // ns0 ns1 ns2 iwe
+    ld4(r + CR_AREF, w2);        // aref0 aref1 aref2 R0
+    T Aw[8]; ld4(r + CR_A, Aw); ld4(r + CR_A + 4, Aw + 4);   // A00 A01 A02 A11 | A12 A22 R1 -
+    ld4(r + CR_F, w3);           // f0 f1 f2 -
+    const int e = (auxi[L.i_con + i] >> 4) - 1;
+    const T A00 = Aw[0], A01 = Aw[1], A02 = Aw[2], A11 = Aw[3], A12 = Aw[4], A22 = Aw[5];
+    const T R0 = w2[3], R1 = Aw[6];
+    const T old0 = w3[0], old1 = w3[1], old2 = w3[2];
+    T ae = 0;
+    if (e >= 0) ae = a()[nfd + e];
+    T res[3];
+    const T Rr[3] = {R0, R1, R1};
+    const T fo[3] = {old0, old1, old2};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      T s = w1[k] * ae;
+      if (has_chain) {
+#pragma unroll
+        for (int jj = 0; jj < MAXCD; jj++) s += jg[4 * k + jj] * cr.ag[jj];
+      }
+      res[k] = s - w2[k] + Rr[k] * fo[k];
+    }
+    T f0 = old0, f1 = old1, f2 = old2;
+    if (f0 < T(SG_MINVAL)) {
+      f0 -= res[0] / A00;
+      if (f0 < T(0)) f0 = 0;
+      f1 = 0; f2 = 0;
+    } else {
+      const T v0 = f0, v1 = f1, v2 = f2;
+      const T x0 = A00 * v0 + A01 * v1 + A02 * v2, x1 = A01 * v0 + A11 * v1 + A12 * v2, x2 = A02 * v0 + A12 * v1 + A22 * v2;
+      const T denom = v0 * x0 + v1 * x1 + v2 * x2;
+      if (denom >= T(SG_MINVAL)) {
+        T x = -(v0 * res[0] + v1 * res[1] + v2 * res[2]) / denom;
+        if (f0 + x * v0 < T(0)) x = T(-1);
+        f0 += x * v0; f1 += x * v1; f2 += x * v2;
+      }
+    }
+    // friction update with the normal force fixed
+    {
+      T bc[2];
+      bc[0] = res[1] - (A11 * old1 + A12 * old2) + A01 * (f0 - old0);
+      bc[1] = res[2] - (A12 * old1 + A22 * old2) + A02 * (f0 - old0);
+      if (f0 < T(SG_MINVAL)) { f1 = 0; f2 = 0; }
+      else {
+        const T frc = C.con_fr;
+        T vv[2];
+        const int active = qcqp2<T>(vv, A11, A12, A22, bc, frc, frc, f0);
+        if (active) {
+          T s = vv[0] * vv[0] / (frc * frc) + vv[1] * vv[1] / (frc * frc);
+          s = tsqrt(f0 * f0 / tmax(T(SG_MINVAL), s));
+          vv[0] *= s; vv[1] *= s;
+        }
+        f1 = vv[0]; f2 = vv[1];
+      }
+    }
+    // cost change, revert if positive
+    T d0f = f0 - old0, d1f = f1 - old1, d2f = f2 - old2;
+    T change = T(0.5) * (d0f * (A00 * d0f + A01 * d1f + A02 * d2f) + d1f * (A01 * d0f + A11 * d1f + A12 * d2f) + d2f * (A02 * d0f + A12 * d1f + A22 * d2f))
+             + d0f * res[0] + d1f * res[1] + d2f * res[2];
+    if (change > T(1e-10)) { f0 = old0; f1 = old1; f2 = old2; d0f = d1f = d2f = 0; change = 0; }
+    r[CR_F] = f0; r[CR_F + 1] = f1; r[CR_F + 2] = f2;
+    // qacc += M^-1 J^T delta
+    if (d0f != T(0) || d1f != T(0) || d2f != T(0)) {
+      if (e >= 0) a()[nfd + e] = ae + (w1[0] * d0f + w1[1] * d1f + w1[2] * d2f) * w1[3];
+      if (has_chain) {
+        T gv[MAXCD];
+#pragma unroll
+        for (int jj = 0; jj < MAXCD; jj++) gv[jj] = jg[jj] * d0f + jg[4 + jj] * d1f + jg[8 + jj] * d2f;
+#pragma unroll
+        for (int ii = 0; ii < MAXCD; ii++) {
+          T s = 0;
+#pragma unroll
+          for (int jj = 0; jj < MAXCD; jj++) s += cr.mv[4 * ii + jj] * gv[jj];
+          cr.ag[ii] += s;
+        }
+      }
+    }
+    return change;
+  }
+
+  // one equality row of the level sweep, split so that two independent rows can be in flight
+  struct RowRegs { int d1, d2; T iw1, iw2, a1, a2, u, R; };
+  __device__ __forceinline__ void row_load(RowRegs& rr, int p, const int* rd, const T* riw, const T* av, const T* row2) {
+    const int d12 = __ldg(rd + p);
+    rr.d1 = d12 & 0xffff; rr.d2 = (d12 >> 16) & 0xffff;
+    rr.iw1 = __ldg(riw + 2 * p); rr.iw2 = __ldg(riw + 2 * p + 1);
+    rr.a1 = av[rr.d1];
+    rr.a2 = rr.d2 != 0xffff ? av[rr.d2] : T(0);
+    ld2(row2 + 2 * p, rr.u, rr.R);
+  }
+  __device__ __forceinline__ void row_solve(RowRegs& rr, T& impr) {
+    const T res = (rr.a1 - rr.a2) + rr.u;
+    const T dl = -res * trcp<T>(rr.iw1 + rr.iw2 + rr.R);
+    impr -= T(0.5) * dl * res;
+    rr.u += rr.R * dl;
+    rr.a1 += rr.iw1 * dl;
+    rr.a2 -= rr.iw2 * dl;
+  }
+  __device__ __forceinline__ void row_store(const RowRegs& rr, int p, T* av, T* row2) {
+    row2[2 * p] = rr.u;
+    av[rr.d1] = rr.a1;
+    if (rr.d2 != 0xffff) av[rr.d2] = rr.a2;
+  }
+
+  // projected Gauss-Seidel (mj_solPGS) in MuJoCo's row order
+  __device__ void pgs(Tendon& tn, ChainRows& cr) {
+    const int nfd = D.nfd, ns = D.ns;
+    const int* lev_start = itab(D.io_lev_start);
+    const int* rd = itab(D.io_row_d12);
+    const T* riw = tab(D.o_row_iw);
+    const T* tcv = tab(D.o_sl_tc);
+    const T* tciw = tab(D.o_sl_tciw);
+    T* av = a() + nfd;
+    T* row2 = hot + L.row2;
+    const int tmaxw = wmax(misc(M2_TMAX));
+    const bool chain_lane = sl < D.nchain;
+    // this lane's slice of the contact schedule
+    int mystart = 0, mycnt = 0;
+    {
+      const int ncon = misc(M2_NCON);
+      for (int i = 0; i < ncon; i++) {
+        const int ln = auxi[L.i_tl + i] >> 16;
+        if (ln < sl) mystart++;
+        else if (ln == sl) mycnt++;
+      }
+      int k = 0;
+      for (int i = 0; i < ncon; i++) {
+        const int tl = auxi[L.i_tl + i];
+        if ((tl >> 16) == sl) { auxi[L.i_order + mystart + k] = i | ((tl & 0xffff) << 16); k++; }
+      }
+    }
+    if (chain_lane) {
+      const int d0 = D.chain_dof0[sl];
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) cr.ag[jj] = jj < D.ncd[sl] ? a()[d0 + jj] : T(0);
+    }
+    __syncwarp();
+    int iter = 0;
+    bool done = false;
+    for (int it = 0; it < D.iters; it++) {
+      if (!__any_sync(FULLMASK, !done)) break;
+      T impr = 0;
+      // ---- equality block, level by level; up to two rows per lane in flight ----
+      int p0 = __ldg(lev_start);
+      for (int lv = 0; lv < D.nlev; lv++) {
+        const int p1 = __ldg(lev_start + lv + 1);
+        for (int pb = p0; pb < p1; pb += 2 * LPW) {
+          const int pA = pb + sl, pB = pA + LPW;
+          const bool hA = !done && pA < p1, hB = !done && pB < p1;
+          RowRegs ra, rb;
+          if (hA) row_load(ra, pA, rd, riw, av, row2);
+          if (hB) row_load(rb, pB, rd, riw, av, row2);
+          if (hA) row_solve(ra, impr);
+          if (hB) row_solve(rb, impr);
+          if (hA) row_store(ra, pA, av, row2);
+          if (hB) row_store(rb, pB, av, row2);
+        }
+        p0 = p1;
+        __syncwarp();
+      }
+      // ---- volume-tendon row: dense over the shell, sub-warp shuffle reduction ----
+      {
+        T s = 0;
+        for (int e = sl; e < ns; e += LPW) s += __ldg(tcv + e) * av[e];
+        s = gsum(s);
+        const T res = s + tn.u;
+        const T dl = done ? T(0) : -res * trcp<T>(tn.A);
+        if (sl == 0) impr -= T(0.5) * dl * res;
+        tn.u += tn.R * dl;
+        for (int e = sl; e < ns; e += LPW) av[e] += __ldg(tciw + e) * dl;
+        __syncwarp();
+      }
+      // ---- joint limits, then the elliptic contact blocks of this lane in their time slots ----
+      if (chain_lane && !done) {
+#pragma unroll
+        for (int jl = 0; jl < MAXCD; jl++) {
+          if (!(cr.lmask & (1 << jl))) continue;
+          const T sgn = cr.lsgn[jl], f = cr.lf[jl], R = cr.lR[jl];
+          const T A = cr.mv[4 * jl + jl] + R;
+          const T res = sgn * cr.ag[jl] - cr.laref[jl] + R * f;
+          T fn = f - res / A;
+          if (fn < T(0)) fn = 0;
+          T dl = fn - f;
+          T change = T(0.5) * dl * dl * A + dl * res;
+          if (change > T(1e-10)) { fn = f; dl = 0; change = 0; }
+          impr -= change;
+          cr.lf[jl] = fn;
+          if (dl != T(0)) {
+#pragma unroll
+            for (int ii = 0; ii < MAXCD; ii++) cr.ag[ii] += cr.mv[4 * ii + jl] * sgn * dl;
+          }
+        }
+      }
+      int k = 0;
+      for (int t = 1; t <= tmaxw; t++) {
+        if (!done && k < mycnt) {
+          const int ent = auxi[L.i_order + mystart + k];
+          if ((ent >> 16) == t) { impr -= contact_block(ent & 0xffff, cr, chain_lane); k++; }
+        }
+        __syncwarp();
+      }
+      impr = gsum(impr) * C.impr_scale;
+      if (!done) { iter++; if (impr < C.tol) done = true; }
+    }
+    if (chain_lane) {
+      const int d0 = D.chain_dof0[sl];
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) if (jj < D.ncd[sl]) a()[d0 + jj] = cr.ag[jj];
+    }
+    if (sl == 0) misc(M2_ITERS) = iter;
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // mj_forward for this world; returns true if qacc is bad
+  // ------------------------------------------------------------------------------------------
+  __device__ bool forward() {
+    Tendon tn; ChainRows cr; T Ft;
+    if (sl < D.nchain) gripper(sl);
+    __syncwarp();
+    collide();
+    rows_and_smooth(tn, Ft);
+    if (sl < D.nchain) chain_limits(sl, cr); else cr.lmask = 0;
+    warmstart(tn, cr);
+    pgs(tn, cr);
+    // accelerometers (mj_sensorAcc): R_site^T (Jv qacc + bias - g)
+    for (int s = sl; s < D.nsens; s += LPW) {
+      const T* se = tab(D.o_sens + s * SE_STRIDE);
+      if ((int)se[SE_TYPE] == SENS_ACCEL) {
+        const int c = (int)se[SE_CHAIN], d0 = D.chain_dof0[c], adr = (int)se[SE_ADR];
+        T acc[3] = {aux[L.s_ab + 3 * s], aux[L.s_ab + 3 * s + 1], aux[L.s_ab + 3 * s + 2]};
+        for (int jj = 0; jj < D.ncd[c]; jj++) {
+          const T aj = a()[d0 + jj];
+#pragma unroll
+          for (int k = 0; k < 3; k++) acc[k] += aux[L.s_jv + 12 * s + 3 * jj + k] * aj;
+        }
+        T o[3]; matTvec3(o, aux + L.s_rot + 9 * s, acc);
+#pragma unroll
+        for (int k = 0; k < 3; k++) aux[L.sens + adr + k] = o[k];
+      }
+    }
+    // limit forces of the last step (diagnostics, and the touch of registers keeps them live only here)
+    if (sl < D.nchain) {
+      auxi[L.i_lmask + sl] = cr.lmask;
+#pragma unroll
+      for (int jl = 0; jl < MAXCD; jl++) {
+        T* lr = aux + L.lim + 3 * (D.chain_dof0[sl] + jl);
+        lr[0] = cr.lf[jl]; lr[1] = cr.laref[jl]; lr[2] = cr.lR[jl];
+      }
+    }
+    {
+      int s = (sl < D.nchain) ? __popc((unsigned)cr.lmask) : 0;
+#pragma unroll
+      for (int o = LPW / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULLMASK, s, o);
+      if (sl == 0) misc(M2_NLIM) = s;
+    }
+    __syncwarp();
+    if (valid && w == K.debug_world) debug_dump(tn);
+    bool badacc = false;
+    for (int i = sl; i < D.nv; i += LPW) if (!(tabs(a()[i]) <= T(SG_MAXVAL))) badacc = true;
+    __syncwarp();
+    return gballot(badacc) != 0u;
+  }
+
+  // mj_Euler with implicit joint damping: (M + h diag(d)) qacc' = qfrc_smooth + J^T f = M qacc
+  __device__ void euler() {
+    const int nfd = D.nfd; const T h = C.h;
+    for (int e = sl; e < D.ns; e += LPW) {
+      const T m = tab(D.o_sl_m)[e];
+      const T qa = m * a()[nfd + e] / (m + h * damping(e));
+      const T vn = v()[nfd + e] + h * qa;
+      v()[nfd + e] = vn; q()[nfd + e] += h * vn;
+    }
+    for (int i = sl; i < nfd; i += LPW) { const T vn = v()[i] + h * a()[i]; v()[i] = vn; q()[i] += h * vn; }
+    if (sl < D.nu) aux[L.act + sl] += h * aux[L.actdot + sl];
+    __syncwarp();
+  }
+
+  // mj_step
+  __device__ void step() {
+    bool badpv = false;
+    for (int i = sl; i < D.nv; i += LPW) if (!(tabs(q()[i]) <= T(SG_MAXVAL)) || !(tabs(v()[i]) <= T(SG_MAXVAL))) badpv = true;
+    const bool gbad = gballot(badpv) != 0u;
+    if (gbad && sl == 0) misc(M2_STATUS) |= 1;
+    // reset_if contains a warp collective: every group goes through it, only the bad ones write
+    reset_if(gbad);
+    T* a0 = aux + L.a0;
+    for (int i = sl; i < D.nv; i += LPW) a0[i] = a()[i];
+    bool bad = forward();
+    if (__any_sync(FULLMASK, bad)) {
+      // mj_step re-runs mj_forward after mj_resetData.  forward() is full of warp collectives, so the other
+      // groups of the warp re-run it too, from their saved warm start: they recompute identical values.
+      if (bad && sl == 0) misc(M2_STATUS) |= 1;
+      if (!bad) for (int i = sl; i < D.nv; i += LPW) a()[i] = a0[i];
+      reset_if(bad);
+      bad = forward();
+      if (bad && sl == 0) misc(M2_STATUS) |= 1;
+      reset_if(bad);
+    }
+    euler();
+  }
+  __device__ void reset_if(bool doit) {
+    if (doit) {
+      for (int i = sl; i < D.nv; i += LPW) { q()[i] = 0; v()[i] = 0; a()[i] = 0; }
+      if (sl < D.nu) { aux[L.act + sl] = 0; aux[L.ctrl + sl] = 0; }
+    }
+    __syncwarp();
+  }
+
+  __device__ void debug_dump(const Tendon& tn) {
+    // header: [0]=ncon_total [1]=nefc [2]=iters [3]=ncon(rows) [4]=nlim [5]=tmax [6]=ncand ; contacts at 64+16*i ;
+    // then at 64+16*maxcon*2: qacc[nv], efc_force / aref / R (equality block in schedule order, then MuJoCo order);
+    // the last nrow+1 doubles of the buffer hold the equality arefs written by rows_and_smooth
+    double* o = K.debug_out;
+    if (!o) return;
+    const int ncon = misc(M2_NCON), nlim = misc(M2_NLIM);
+    const int nefc = D.nrow + 1 + nlim + 3 * ncon;
+    if (sl == 0) { o[0] = misc(M2_NCONTOT); o[1] = nefc; o[2] = misc(M2_ITERS); o[3] = ncon; o[4] = nlim; o[5] = misc(M2_TMAX); o[6] = misc(M2_NCAND); }
+    const int base = 64 + 16 * 2 * D.maxcon;
+    for (int i = sl; i < D.nv; i += LPW) if (base + i < K.debug_cap) o[base + i] = (double)a()[i];
+    const int eb = base + D.nv;
+    const int tail = K.debug_cap - (D.nrow + 1);
+    if (eb + 3 * nefc > tail) return;
+    const T* row2 = hot + L.row2;
+    for (int p = sl; p < D.nrow; p += LPW) {
+      const double ar = o[tail + p], R = (double)row2[2 * p + 1];
+      o[eb + p] = ((double)row2[2 * p] + ar) / R; o[eb + nefc + p] = ar; o[eb + 2 * nefc + p] = R;
+    }
+    if (sl == 0) {
+      int r = D.nrow;
+      o[eb + r] = ((double)tn.u + (double)tn.aref) / (double)tn.R; o[eb + nefc + r] = (double)tn.aref; o[eb + 2 * nefc + r] = (double)tn.R; r++;
+      for (int c = 0; c < D.nchain; c++)
+        for (int jl = 0; jl < D.ncd[c]; jl++)
+          if (auxi[L.i_lmask + c] & (1 << jl)) {
+            const T* lr = aux + L.lim + 3 * (D.chain_dof0[c] + jl);
+            o[eb + r] = (double)lr[0]; o[eb + nefc + r] = (double)lr[1]; o[eb + 2 * nefc + r] = (double)lr[2]; r++;
+          }
+      for (int i = 0; i < ncon; i++)
+        for (int k = 0; k < 3; k++, r++) {
+          const T* cr = crec(i);
+          o[eb + r] = (double)cr[CR_F + k]; o[eb + nefc + r] = (double)cr[CR_AREF + k];
+          o[eb + 2 * nefc + r] = (double)(k ? cr[CR_R1] : cr[CR_R0]);
+        }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+#ifndef SG_SHARED_BYTES
+#define SG_SHARED_BYTES(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+template <typename T, int LPW>
+__global__ void __launch_bounds__(32) sg_step_kernel2(const __grid_constant__ KArgs2<T> K) {
+  SG_SHARED_BYTES(smem_raw);
+  constexpr int WPW = 32 / LPW;
+  const PlanDims& D = K.D;
+  const Layout2& L = K.L;
+  const int lane = threadIdx.x & 31, grp = lane / LPW, sl = lane % LPW;
+  const int ngroups = gridDim.x * WPW;
+  for (int w0 = blockIdx.x * WPW; w0 < K.nworlds; w0 += ngroups) {
+    const int wi = w0 + grp;
+    const bool valid = wi < K.nworlds;
+    World2<T, LPW> W(K, smem_raw, valid ? wi : K.nworlds - 1, valid);
+    W.load_params();
+    if (sl == 0) W.misc(M2_STATUS) = 0;
+    const int w = W.w;
+    const size_t sb = (size_t)w * D.nv;
+    T* aux = W.aux;
+    if (sl < D.nu) { aux[L.act + sl] = K.act[(size_t)w * D.nu + sl]; aux[L.ctrl + sl] = K.ctrl[(size_t)w * D.nu + sl]; }
+    if (!K.rollout) {
+      for (int i = sl; i < D.nv; i += LPW) { W.q()[i] = K.qpos[sb + i]; W.v()[i] = K.qvel[sb + i]; W.a()[i] = K.warm[sb + i]; }
+      __syncwarp();
+      if (K.integrate) { for (int s = 0; s < K.nsub; s++) W.step(); }
+      else {
+        // mj_forward: sensors/contacts refreshed, nothing integrated, warm start left untouched
+        W.forward();
+        __syncwarp();
+        for (int i = sl; i < D.nv; i += LPW) W.a()[i] = K.warm[sb + i];
+        __syncwarp();
+      }
+      if (valid) {
+        for (int i = sl; i < D.nv; i += LPW) { K.qpos[sb + i] = W.q()[i]; K.qvel[sb + i] = W.v()[i]; K.warm[sb + i] = W.a()[i]; }
+        if (K.sens_out) for (int i = sl; i < D.nsd; i += LPW) K.sens_out[(size_t)w * D.nsd + i] = aux[L.sens + i];
+        if (K.touch_out && sl == 0) K.touch_out[w] = W.misc(M2_TOUCH);
+      }
+    } else {
+      // whole episode on-chip (create_dataset.log_into_file, ref: create_dataset.py:33-60)
+      W.reset_if(true);
+      for (int s = 0; s < K.sim_start; s++) W.step();
+      for (int t = 0; t < K.nrows; t++) {
+        if (K.ctrl_event[t] && sl < D.nu) aux[L.ctrl + sl] = T(K.ctrl_value[t * D.nu + sl]);
+        __syncwarp();
+        for (int s = 0; s < K.sim_step; s++) W.step();
+        if (valid) {
+          for (int i = sl; i < D.nsd; i += LPW) K.sens_out[((size_t)w * K.nrows + t) * D.nsd + i] = aux[L.sens + i];
+          if (K.touch_out && sl == 0) K.touch_out[(size_t)w * K.nrows + t] = W.misc(M2_TOUCH);
+        }
+      }
+      if (valid) for (int i = sl; i < D.nv; i += LPW) { K.qpos[sb + i] = W.q()[i]; K.qvel[sb + i] = W.v()[i]; K.warm[sb + i] = W.a()[i]; }
+    }
+    __syncwarp();
+    if (valid) {
+      if (sl < D.nu) { K.act[(size_t)w * D.nu + sl] = aux[L.act + sl]; K.ctrl[(size_t)w * D.nu + sl] = aux[L.ctrl + sl]; }
+      if (sl == 0 && W.misc(M2_STATUS)) atomicOr(&K.status[w], W.misc(M2_STATUS));
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace sg

@@ -63,8 +63,11 @@ struct PlanDims {
   double obj_pos[3];
   // offsets into the double table
   int o_sl_axis, o_sl_cap0, o_sl_k0, o_sl_d0, o_sl_m, o_sl_tc, o_sl_biw, o_sl_iw, o_chain, o_coll, o_sens;
+  int o_row_iw;     // 2*nrow: 1/m of the row's first and second slider (0 when the row has one dof), schedule order
+  int o_sl_tciw;    // ns: tendon coefficient / slider mass
   // offsets into the int table
   int io_kmask, io_row_d1, io_row_d2, io_lev_start, io_dof_rows, io_pair_t, io_pair_a, io_pair_b;
+  int io_row_d12;   // nrow: first slider | second slider << 16 (0xffff: none), schedule order
 };
 
 struct Blob {
@@ -399,6 +402,18 @@ inline Plan build_plan(const void* blob, size_t nbytes) {
   }
   for (int l = 0; l <= D.nlev; l++) P.itab[D.io_lev_start + l] = lev_start[l];
   P.sched_eq = sched;
+  // packed per-row descriptors of the level sweep
+  SG_REQUIRE(ns < 0xffff, "too many shell joints for the packed row descriptors");
+  D.io_row_d12 = alloc_i(nrow);
+  D.o_row_iw = alloc_d(2 * (size_t)nrow);
+  D.o_sl_tciw = alloc_d(ns);
+  for (int p = 0; p < nrow; p++) {
+    const int d1 = P.itab[D.io_row_d1 + p], d2 = P.itab[D.io_row_d2 + p];
+    P.itab[D.io_row_d12 + p] = d1 | ((d2 >= 0 ? d2 : 0xffff) << 16);
+    P.tab[D.o_row_iw + 2 * p] = 1.0 / P.tab[D.o_sl_m + d1];
+    P.tab[D.o_row_iw + 2 * p + 1] = d2 >= 0 ? 1.0 / P.tab[D.o_sl_m + d2] : 0.0;
+  }
+  for (int e = 0; e < ns; e++) P.tab[D.o_sl_tciw + e] = P.tab[D.o_sl_tc + e] / P.tab[D.o_sl_m + e];
 
   // ---- contact parameters must be uniform over all geoms ----
   for (int g = 0; g < ngeom; g++) {

@@ -51,45 +51,80 @@ def main():
         print("%-90s %s" % (h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
     out = ncu(rep, "--page", "source", "--print-source", "cuda,sass", "--csv")
     rows = list(csv.reader(io.StringIO(out)))
-    hi = next((i for i, r in enumerate(rows) if r and r[0] == "Line No"), None)
-    if hi is None:
-        return
-    hdr = rows[hi]
-    ii = hdr.index("Instructions Executed")
-    per = {}
-    text = {}
-    for r in rows[hi + 1:]:
-        if len(r) < len(hdr) or not r[0]:
+    # the page is a sequence of per-file tables: ["File Name", path], header row ["Line No", "Source", ...], lines
+    per, samp, text, stalls = {}, {}, {}, {}
+    cur_file, hdr = "?", None
+    STALL = ["stall_long_sb", "stall_no_inst", "stall_wait", "stall_short_sb", "stall_barrier", "stall_branch_resolving", "stall_mio", "stall_math", "stall_not_selected", "stall_selected", "stall_lg", "stall_dispatch"]
+    for r in rows:
+        if not r:
+            continue
+        if r[0] == "File Name":
+            cur_file = r[1].split("/")[-1]; continue
+        if r[0] == "Line No":
+            hdr = r; continue
+        if hdr is None or len(r) < len(hdr):
             continue
         try:
-            ln, inst = int(r[0]), int(r[ii])
+            ln = int(r[0]); inst = int(r[hdr.index("Instructions Executed")])
         except ValueError:
             continue
-        per[ln] = per.get(ln, 0) + inst
-        text[ln] = r[1]
+        key = (cur_file, ln)
+        per[key] = per.get(key, 0) + inst
+        try:
+            samp[key] = samp.get(key, 0) + int(r[hdr.index("# Samples")])
+        except ValueError:
+            pass
+        text[key] = r[1]
+        st = stalls.setdefault(key, {})
+        for name in STALL:
+            if name in hdr:
+                try:
+                    st[name] = st.get(name, 0) + int(r[hdr.index(name)])
+                except ValueError:
+                    pass
+    if not per:
+        return
     tot = float(sum(per.values())) or 1.0
-    print("## executed warp-instructions by CUDA source line (top 30 of %d lines; total %.4g)" % (len(per), tot))
-    # group by enclosing function using the source text when available
-    if src_file:
-        src = open(src_file).read().split("\n")
-        fn_of = {}
-        cur = "?"
-        pat = re.compile(r"__device__[^;(]*?\b(\w+)\s*\(|__global__[^;(]*?\b(\w+)\s*\(")
-        for n, line in enumerate(src, 1):
-            m = pat.search(line)
-            if m and not line.strip().startswith("//"):
-                cur = m.group(1) or m.group(2)
-            fn_of[n] = cur
-        agg = {}
-        for ln, v in per.items():
-            agg[fn_of.get(ln, "?")] = agg.get(fn_of.get(ln, "?"), 0) + v
-        print("## share by function")
-        for f, v in sorted(agg.items(), key=lambda t: -t[1]):
-            if v / tot >= 0.001:
-                print("%-28s %6.2f %%" % (f, 100 * v / tot))
-        print("## top lines")
-    for ln, v in sorted(per.items(), key=lambda t: -t[1])[:30]:
-        print("%5d %6.2f %%  %s" % (ln, 100 * v / tot, text[ln].strip()[:120]))
+    stot = float(sum(samp.values())) or 1.0
+    print("## executed warp-instructions and stall samples by CUDA source line (%d lines; total %.4g instructions, %.4g samples)" % (len(per), tot, stot))
+    import os
+    fn_of = {}
+    srcdir = os.path.dirname(src_file) if src_file else None
+    pat = re.compile(r"__device__[^;(]*?\b(\w+)\s*\(|__global__[^;(]*?\b(\w+)\s*\(")
+    for f in set(k[0] for k in per):
+        path = os.path.join(srcdir, f) if srcdir else None
+        if path and os.path.exists(path):
+            cur = "?"
+            for n, line in enumerate(open(path).read().split("\n"), 1):
+                m = pat.search(line)
+                if m and not line.strip().startswith("//"):
+                    cur = m.group(1) or m.group(2)
+                fn_of[(f, n)] = cur
+    agg, sagg, stagg = {}, {}, {}
+    for key, v in per.items():
+        fn = fn_of.get(key, key[0])
+        agg[fn] = agg.get(fn, 0) + v
+        sagg[fn] = sagg.get(fn, 0) + samp.get(key, 0)
+        d = stagg.setdefault(fn, {})
+        for name, c in stalls.get(key, {}).items():
+            d[name] = d.get(name, 0) + c
+    print("## share by function:  function, %% of executed instructions, %% of stall samples, top stall reasons (%% of the function's samples)")
+    for f, v in sorted(sagg.items(), key=lambda t: -t[1]):
+        if v / stot >= 0.002 or agg[f] / tot >= 0.002:
+            d = stagg.get(f, {}); dt = float(sum(d.values())) or 1.0
+            top = ", ".join("%s %.0f" % (n.replace("stall_", ""), 100 * c / dt) for n, c in sorted(d.items(), key=lambda t: -t[1])[:4])
+            print("%-22s %6.2f %% inst %6.2f %% samples   %s" % (f, 100 * agg[f] / tot, 100 * v / stot, top))
+    tots = {}
+    for d in stalls.values():
+        for n, c in d.items():
+            tots[n] = tots.get(n, 0) + c
+    tt = float(sum(tots.values())) or 1.0
+    print("## stall samples by reason: " + ", ".join("%s %.1f%%" % (n.replace("stall_", ""), 100 * c / tt) for n, c in sorted(tots.items(), key=lambda t: -t[1])[:8]))
+    print("## top lines by stall samples")
+    for key, v in sorted(samp.items(), key=lambda t: -t[1])[:40]:
+        d = stalls.get(key, {}); dt = float(sum(d.values())) or 1.0
+        top = ", ".join("%s %.0f" % (n.replace("stall_", ""), 100 * c / dt) for n, c in sorted(d.items(), key=lambda t: -t[1])[:2])
+        print("%-14s %5d %6.2f %% samples %6.2f %% inst  [%s]  %s" % (key[0][:14], key[1], 100 * v / stot, 100 * per[key] / tot, top, text[key].strip()[:90]))
 
 
 if __name__ == "__main__":

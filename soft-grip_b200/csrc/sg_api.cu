@@ -39,8 +39,12 @@ struct sg_batch {
 #endif
   int kernel = 2;             // 2: sub-warp worlds (sg_kernels2.cuh); 1: one warp per world (sg_kernels.cuh)
   int lpw = 8;                // lanes per world of kernel 2
+  int nwarp = 8;              // warps per CTA of kernel 2
+  size_t smem2 = 0;           // dynamic shared memory per CTA of kernel 2
   Layout2 L2;
   unsigned char* scratch = nullptr;   // global aux slots of kernel 2 (when aux is not in shared memory)
+  std::vector<int> step_d;            // level-sweep step tables of kernel 2 for this batch's lanes per world
+  std::vector<double> step_iw;
   void* tab = nullptr;        // device table in batch precision
   int* itab = nullptr;
   void *qpos = nullptr, *qvel = nullptr, *warm = nullptr, *act = nullptr, *ctrl = nullptr;
@@ -85,7 +89,7 @@ extern "C" int sg_model_info(const sg_model* m, sg_info* out) {
   D.maxcon = m->maxcon_default; D.maxcand = m->maxcand_default;
   out->nv = D.nv; out->nfinger = D.nfd; out->nshell = D.ns; out->neq = m->plan.neq; out->nu = D.nu; out->nsensordata = D.nsd;
   out->nlevels = D.nlev; out->maxcon = D.maxcon; out->ngeom = m->plan.ngeom;
-  out->smem_bytes32 = make_layout2<float>(D, 1, 1).smem_stride; out->smem_bytes64 = make_layout2<double>(D, 1, 1).smem_stride;
+  out->smem_bytes32 = make_layout2<float>(D, 0, 4, 8).smem_stride; out->smem_bytes64 = make_layout2<double>(D, 0, 4, 8).smem_stride;
   return 0;
 }
 
@@ -110,29 +114,43 @@ extern "C" int sg_model_set_geom_mask(sg_model* m, const int* mask) {
   return 0;
 }
 
-template <typename T>
-static int upload_tables(sg_batch* b) {
+// device tables = the model's plan tables + this batch's level-sweep step tables (which depend on lanes per world)
+static void host_tables(const sg_batch* b, std::vector<double>& tab, std::vector<int>& itab) {
   const Plan& P = b->model->plan;
-  std::vector<T> t(P.tab.size());
-  for (size_t i = 0; i < t.size(); i++) t[i] = (T)P.tab[i];
-  CUDA_OK(cudaMalloc(&b->tab, sizeof(T) * (t.size() ? t.size() : 1)));
-  CUDA_OK(cudaMemcpy(b->tab, t.data(), sizeof(T) * t.size(), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMalloc((void**)&b->itab, sizeof(int) * (P.itab.size() ? P.itab.size() : 1)));
-  CUDA_OK(cudaMemcpy(b->itab, P.itab.data(), sizeof(int) * P.itab.size(), cudaMemcpyHostToDevice));
+  tab = P.tab; itab = P.itab;
+  while (tab.size() % 4) tab.push_back(0.0);
+  while (itab.size() % 4) itab.push_back(0);
+  tab.insert(tab.end(), b->step_iw.begin(), b->step_iw.end());
+  itab.insert(itab.end(), b->step_d.begin(), b->step_d.end());
+}
+
+static int upload_tables(sg_batch* b, bool allocate) {
+  std::vector<double> tab; std::vector<int> itab;
+  host_tables(b, tab, itab);
+  if (allocate) {
+    CUDA_OK(cudaMalloc(&b->tab, b->esize * (tab.size() ? tab.size() : 1)));
+    CUDA_OK(cudaMalloc((void**)&b->itab, sizeof(int) * (itab.size() ? itab.size() : 1)));
+  }
+  if (b->precision == 32) {
+    std::vector<float> t(tab.size());
+    for (size_t i = 0; i < t.size(); i++) t[i] = (float)tab[i];
+    CUDA_OK(cudaMemcpy(b->tab, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
+  } else CUDA_OK(cudaMemcpy(b->tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(b->itab, itab.data(), sizeof(int) * itab.size(), cudaMemcpyHostToDevice));
   return 0;
 }
 
 // (precision, lanes-per-world) -> instantiation; the list must match the Makefile's SG_INSTANCES
 #define SG_K2_CASES(X) X(float, 4) X(float, 8) X(float, 16) X(float, 32) X(double, 4) X(double, 8) X(double, 16) X(double, 32)
-static int k2_dispatch_configure(int precision, int lpw, size_t smem, int* per_sm) {
-#define X(T, N) if ((precision == 32) == (sizeof(T) == 4) && lpw == N) return k2_configure<T, N>(smem, per_sm);
+static int k2_dispatch_configure(int precision, int lpw, int block, size_t smem, int* per_sm) {
+#define X(T, N) if ((precision == 32) == (sizeof(T) == 4) && lpw == N) return k2_configure<T, N>(block, smem, per_sm);
   SG_K2_CASES(X)
 #undef X
   return -12345;
 }
 template <typename T>
-static int k2_dispatch_launch(int lpw, const KArgs2<T>& K, int grid, size_t smem, void* stream) {
-#define X(TT, N) if (sizeof(TT) == sizeof(T) && lpw == N) return k2_launch<T, N>(K, grid, smem, stream);
+static int k2_dispatch_launch(int lpw, const KArgs2<T>& K, int grid, int block, size_t smem, void* stream) {
+#define X(TT, N) if (sizeof(TT) == sizeof(T) && lpw == N) return k2_launch<T, N>(K, grid, block, smem, stream);
   SG_K2_CASES(X)
 #undef X
   return -12345;
@@ -159,12 +177,22 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   int aux_in_smem = 0;
   if (const char* e = std::getenv("SOFTGRIP_KERNEL")) b->kernel = std::atoi(e);
   if (const char* e = std::getenv("SOFTGRIP_LPW")) b->lpw = std::atoi(e);
+  if (const char* e = std::getenv("SOFTGRIP_NW")) b->nwarp = std::atoi(e);
   if (const char* e = std::getenv("SOFTGRIP_AUX_SMEM")) aux_in_smem = std::atoi(e);
 #ifdef SG_SIMT_EMU
   b->kernel = 2;
 #endif
   if (b->kernel != 1 && b->kernel != 2) { delete b; return fail("SOFTGRIP_KERNEL must be 1 or 2"); }
-  int rc = precision == 32 ? upload_tables<float>(b) : upload_tables<double>(b);
+  if (b->nwarp < 1 || b->nwarp > SG_MAX_WARPS) { delete b; return fail("SOFTGRIP_NW must be 1..16"); }
+  if (b->lpw != 4 && b->lpw != 8 && b->lpw != 16 && b->lpw != 32) { delete b; return fail("SOFTGRIP_LPW must be 4, 8, 16 or 32"); }
+  if (b->kernel == 2) {
+    const Plan& P = m->plan;
+    build_step_tables(b->D, P.tab, P.itab, b->lpw, b->step_d, b->step_iw);
+    b->D.nstep = (int)(b->step_d.size() / (2 * (size_t)b->lpw));
+    b->D.o_step_iw = (int)((P.tab.size() + 3) / 4 * 4);
+    b->D.io_step_d = (int)((P.itab.size() + 3) / 4 * 4);
+  }
+  int rc = upload_tables(b, true);
   if (rc) { delete b; return rc; }
   const size_t nv = b->D.nv, nu = b->D.nu > 0 ? b->D.nu : 1;
   CUDA_OK(cudaMalloc(&b->qpos, b->esize * nv * nworlds));
@@ -183,19 +211,28 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   int per_sm = 0;
   if (b->kernel == 2) {
     const int wpw = 32 / b->lpw;
-    b->L2 = precision == 32 ? make_layout2<float>(b->D, aux_in_smem, wpw) : make_layout2<double>(b->D, aux_in_smem, wpw);
-    const size_t smem = (size_t)b->L2.smem_stride * wpw;
-    if (smem > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: worlds of one warp do not fit in shared memory (lower SOFTGRIP_LPW packing or use SOFTGRIP_AUX_SMEM=0)"); }
-    int e = k2_dispatch_configure(precision, b->lpw, smem, &per_sm);
+    if (!std::getenv("SOFTGRIP_NW")) {
+      // small batches: smaller CTAs, so that every SM gets work
+      while (b->nwarp > 1 && (nworlds + b->nwarp * wpw - 1) / (b->nwarp * wpw) < 2 * prop.multiProcessorCount) b->nwarp /= 2;
+    }
+    for (;;) {
+      b->L2 = precision == 32 ? make_layout2<float>(b->D, aux_in_smem, wpw, b->lpw) : make_layout2<double>(b->D, aux_in_smem, wpw, b->lpw);
+      b->smem2 = (size_t)b->L2.smem_tables + (size_t)b->L2.smem_stride * wpw * b->nwarp;
+      if (b->smem2 <= prop.sharedMemPerBlockOptin || b->nwarp == 1) break;
+      b->nwarp /= 2;
+    }
+    if (b->smem2 > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: worlds of one warp do not fit in shared memory (use more lanes per world or SOFTGRIP_AUX_SMEM=0)"); }
+    int e = k2_dispatch_configure(precision, b->lpw, 32 * b->nwarp, b->smem2, &per_sm);
     if (e == -12345) { delete b; return fail("SOFTGRIP_LPW: this lanes-per-world value is not compiled in"); }
     if (e) { delete b; return fail(std::string("kernel configuration failed: ") + cudaGetErrorString((cudaError_t)e)); }
     if (per_sm < 1) per_sm = 1;
     b->max_ctas = per_sm * prop.multiProcessorCount;
-    int need = (nworlds + wpw - 1) / wpw;
+    const int cta_worlds = wpw * b->nwarp;
+    int need = (nworlds + cta_worlds - 1) / cta_worlds;
     int slots = need < b->max_ctas ? need : b->max_ctas;
     if (!aux_in_smem) {
-      CUDA_OK(cudaMalloc((void**)&b->scratch, (size_t)slots * wpw * (size_t)b->L2.gs_stride));
-      CUDA_OK(cudaMemset(b->scratch, 0, (size_t)slots * wpw * (size_t)b->L2.gs_stride));
+      CUDA_OK(cudaMalloc((void**)&b->scratch, (size_t)slots * cta_worlds * (size_t)b->L2.gs_stride));
+      CUDA_OK(cudaMemset(b->scratch, 0, (size_t)slots * cta_worlds * (size_t)b->L2.gs_stride));
     }
   }
 #ifndef SG_SIMT_EMU
@@ -361,10 +398,10 @@ static int launch_v2(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
   K.nsub = sp.nsub; K.integrate = sp.integrate; K.sens_out = (T*)sp.sens_out; K.touch_out = sp.touch_out;
   K.rollout = sp.rollout; K.sim_start = sp.sim_start; K.sim_step = sp.sim_step; K.nrows = sp.nrows;
   K.ctrl_event = b->d_ctrl_event; K.ctrl_value = b->d_ctrl_value;
-  const int wpw = 32 / b->lpw;
-  int grid = (b->W + wpw - 1) / wpw;
-  if (grid > b->max_ctas) grid = b->max_ctas;   // persistent: each CTA walks its groups of worlds
-  int e = k2_dispatch_launch<T>(b->lpw, K, grid, (size_t)b->L2.smem_stride * wpw, (void*)s);
+  const int cta_worlds = (32 / b->lpw) * b->nwarp;
+  int grid = (b->W + cta_worlds - 1) / cta_worlds;
+  if (grid > b->max_ctas) grid = b->max_ctas;   // persistent: each CTA walks its batches of worlds
+  int e = k2_dispatch_launch<T>(b->lpw, K, grid, 32 * b->nwarp, b->smem2, (void*)s);
   if (e) return fail(std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)e));
   return 0;
 }
@@ -381,16 +418,7 @@ static int launch_any(sg_batch* b, const LaunchSpec& sp, void* stream) {
 
 // tables are uploaded at batch creation; model-level edits made later (masks, stiffness targets) are
 // re-synchronised lazily here
-static int sync_tables(sg_batch* b) {
-  const Plan& P = b->model->plan;
-  if (b->precision == 32) {
-    std::vector<float> t(P.tab.size());
-    for (size_t i = 0; i < t.size(); i++) t[i] = (float)P.tab[i];
-    CUDA_OK(cudaMemcpy(b->tab, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
-  } else CUDA_OK(cudaMemcpy(b->tab, P.tab.data(), sizeof(double) * P.tab.size(), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(b->itab, P.itab.data(), sizeof(int) * P.itab.size(), cudaMemcpyHostToDevice));
-  return 0;
-}
+static int sync_tables(sg_batch* b) { return upload_tables(b, false); }
 
 extern "C" int sg_batch_step(sg_batch* b, int nsub, void* sens_out, int* touch_out, void* stream) {
   if (!b) return fail("sg_batch_step: null batch");

@@ -5,23 +5,23 @@
 namespace sg {
 
 template <typename T, int LPW>
-int k2_launch(const KArgs2<T>& K, int grid, size_t smem, void* stream) {
+int k2_launch(const KArgs2<T>& K, int grid, int block, size_t smem, void* stream) {
   auto kp = sg_step_kernel2<T, LPW>;
-  SG_LAUNCH(kp, grid, 32, smem, (cudaStream_t)stream, K);
+  SG_LAUNCH(kp, grid, block, smem, (cudaStream_t)stream, K);
   return (int)cudaGetLastError();
 }
 
 template <typename T, int LPW>
-int k2_configure(size_t smem, int* per_sm) {
+int k2_configure(int block, size_t smem, int* per_sm) {
   auto kp = sg_step_kernel2<T, LPW>;
   cudaError_t e = cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(kp, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kp, 32, smem);
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kp, block, smem);
 }
 
-template int k2_launch<SG_INST_T, SG_INST_LPW>(const KArgs2<SG_INST_T>&, int, size_t, void*);
-template int k2_configure<SG_INST_T, SG_INST_LPW>(size_t, int*);
+template int k2_launch<SG_INST_T, SG_INST_LPW>(const KArgs2<SG_INST_T>&, int, int, size_t, void*);
+template int k2_configure<SG_INST_T, SG_INST_LPW>(int, size_t, int*);
 
 }  // namespace sg

@@ -46,8 +46,9 @@ enum { CR_JG = 0 /*12*/, CR_NS = 12 /*3*/, CR_IWE = 15, CR_AREF = 16 /*3*/, CR_R
 struct Layout2 {
   // hot, always shared memory
   int a;                 // nv (+ pad)
-  int row2;              // 2*nrow : (u, R) per equality row, schedule order
+  int row2;              // 2*(nrow+1) : (u, R) per equality row, schedule order; the last pair is the dummy row (0, 1)
   int minv;              // 16*MAXCHAIN
+  int hlim;              // 4*MAXFD : f, aref, R, sign per finger dof (meaningful where the limit is active)
   int hotT;
   int h_misc;            // 8 ints
   int hotI;
@@ -58,7 +59,6 @@ struct Layout2 {
   int g_box;             // 12 per moving box
   int s_jv, s_ab, s_rot; // per sensor: 12, 3, 9
   int sens;              // nsd
-  int lim;               // 3*MAXFD : f, aref, R per finger dof (valid where the limit is active)
   int crec;              // CR_STRIDE * maxcon
   int auxT;
   int i_con;             // maxcon : (chain+1) | (slider+1) << 4
@@ -69,17 +69,18 @@ struct Layout2 {
   int auxI;
   int aux_in_smem;
   int smem_stride;       // bytes per world in shared memory (multiple of 16, bank-skewed)
+  int smem_tables;       // bytes of the CTA-shared level-sweep step tables at the start of shared memory
   int gs_stride;         // bytes per world in the global scratch (0 when aux_in_smem)
 };
 
 enum { M2_NCON = 0, M2_STATUS = 1, M2_TOUCH = 2, M2_NCONTOT = 3, M2_ITERS = 4, M2_NCAND = 5, M2_TMAX = 6, M2_NLIM = 7 };
 
 template <typename T>
-inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw) {
+inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw) {
   Layout2 L{};
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };   // keep every array 16-byte aligned (float4 loads)
-  L.a = take(D.nv + 1); L.row2 = take(2 * D.nrow); L.minv = take(16 * MAXCHAIN);
+  L.a = take(D.nv + 1); L.row2 = take(2 * (D.nrow + 1)); L.minv = take(16 * MAXCHAIN); L.hlim = take(4 * MAXFD);
   L.hotT = o;
   L.h_misc = 0; L.hotI = 8;
   o = 0;
@@ -88,7 +89,6 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw) {
   L.act = take(nu); L.ctrl = take(nu); L.actdot = take(nu);
   L.g_axis = take(3 * MAXFD); L.g_anchor = take(3 * MAXFD); L.g_box = take(12 * MAXCHAIN * MAXCB);
   L.s_jv = take(12 * MAXSENS); L.s_ab = take(3 * MAXSENS); L.s_rot = take(9 * MAXSENS); L.sens = take(D.nsd > 0 ? D.nsd : 1);
-  L.lim = take(3 * MAXFD);
   L.crec = take(CR_STRIDE * D.maxcon);
   L.auxT = o;
   int io = 0;
@@ -105,6 +105,7 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw) {
   if (wpw > 1) { const size_t want = (size_t)(128 / wpw) < 16 ? 16 : (size_t)(128 / wpw); while (sb % 128 != want % 128) sb += 16; }
   L.smem_stride = (int)sb;
   L.gs_stride = aux_in_smem ? 0 : (int)((aux + 127) & ~(size_t)127);
+  L.smem_tables = (int)(((size_t)D.nstep * lpw * (8 + 2 * sizeof(T)) + 127) & ~(size_t)127);
   return L;
 }
 
@@ -176,6 +177,46 @@ template <> __device__ __forceinline__ float trcp<float>(float x) {
 #endif
 }
 
+// one 128-byte contact record ahead into L1 (global scratch only)
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+// division inside the contact blocks: MUFU.RCP + FMUL on the fp32 fast path (2 ulp), IEEE in the verification build
+template <typename T> __device__ __forceinline__ T tdiv(T a, T b);
+template <> __device__ __forceinline__ double tdiv<double>(double a, double b) { return a / b; }
+template <> __device__ __forceinline__ float tdiv<float>(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+
+// mju_QCQP2 with tdiv (same algorithm as sg_math.cuh qcqp2)
+template <typename T> __device__ __forceinline__ int qcqp2_fast(T* res, T A11i, T A12i, T A22i, const T* bin, T d0, T d1, T r) {
+  T b1 = bin[0] * d0, b2 = bin[1] * d1;
+  T A11 = A11i * d0 * d0, A22 = A22i * d1 * d1, A12 = A12i * d0 * d1;
+  T la = 0, v1 = 0, v2 = 0;
+  for (int iter = 0; iter < 20; iter++) {
+    T det = (A11 + la) * (A22 + la) - A12 * A12;
+    if (det < T(1e-10)) { res[0] = 0; res[1] = 0; return 0; }
+    T detinv = tdiv(T(1), det), P11 = (A22 + la) * detinv, P22 = (A11 + la) * detinv, P12 = -A12 * detinv;
+    v1 = -P11 * b1 - P12 * b2; v2 = -P12 * b1 - P22 * b2;
+    T val = v1 * v1 + v2 * v2 - r * r;
+    if (val < T(1e-10)) break;
+    T deriv = T(-2) * (P11 * v1 * v1 + T(2) * P12 * v1 * v2 + P22 * v2 * v2);
+    T delta = -tdiv(val, deriv);
+    if (delta < T(1e-10)) break;
+    la += delta;
+  }
+  res[0] = v1 * d0; res[1] = v2 * d1;
+  return la != T(0);
+}
+
 template <typename T> __device__ __forceinline__ T powp(T x, T pw) { return pw == T(2) ? x * x : tpow(x, pw); }
 // getimpedance with pre-sanitised solimp and host-precomputed 1/mid^(p-1), 1/(1-mid)^(p-1)  
 template <typename T> __device__ __forceinline__ T impedance2(const T* si, T pos) {
@@ -203,6 +244,11 @@ template <typename T> __device__ __forceinline__ void ld2(const T* p, T& x, T& y
 template <> __device__ __forceinline__ void ld2<float>(const float* p, float& x, float& y) { const float2 v = *reinterpret_cast<const float2*>(p); x = v.x; y = v.y; }
 template <> __device__ __forceinline__ void ld2<double>(const double* p, double& x, double& y) { const double2 v = *reinterpret_cast<const double2*>(p); x = v.x; y = v.y; }
 
+template <typename T> __device__ __forceinline__ void ldg2(const T* p, T& x, T& y);
+template <> __device__ __forceinline__ void ldg2<float>(const float* p, float& x, float& y) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); x = v.x; y = v.y; }
+template <> __device__ __forceinline__ void ldg2<double>(const double* p, double& x, double& y) { const double2 v = __ldg(reinterpret_cast<const double2*>(p)); x = v.x; y = v.y; }
+static_assert(MAXCD == 4, "finger chain blocks are loaded as 4-vectors");
+
 // ---------------------------------------------------------------------------------------------
 // the world
 // ---------------------------------------------------------------------------------------------
@@ -220,14 +266,20 @@ struct World2 {
   bool valid;
   T kw, dw, tdw, off[3];
 
+  const int2* sdesc;     // CTA-shared step tables of the level sweep (shared memory), already offset to this lane
+  const T* siw;
+
   __device__ World2(const KArgs2<T>& k, unsigned char* smem, int wid, bool ok)
       : K(k), D(k.D), C(k.C), L(k.L), w(wid), valid(ok) {
     lane = threadIdx.x & 31; grp = lane / LPW; sl = lane % LPW; gshift = grp * LPW;
-    unsigned char* base = smem + (size_t)grp * L.smem_stride;
+    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    sdesc = reinterpret_cast<const int2*>(smem) + sl;
+    siw = reinterpret_cast<const T*>(smem + (size_t)D.nstep * LPW * 8) + 2 * sl;
+    unsigned char* base = smem + L.smem_tables + (size_t)(warp * WPW + grp) * L.smem_stride;
     hot = reinterpret_cast<T*>(base);
     hoti = reinterpret_cast<int*>(hot + L.hotT);
     if (L.aux_in_smem) aux = reinterpret_cast<T*>(hoti + L.hotI);
-    else aux = reinterpret_cast<T*>(K.scratch + ((size_t)blockIdx.x * WPW + grp) * (size_t)L.gs_stride);
+    else aux = reinterpret_cast<T*>(K.scratch + (((size_t)blockIdx.x * nwarp + warp) * WPW + grp) * (size_t)L.gs_stride);
     auxi = reinterpret_cast<int*>(aux + L.auxT);
   }
 
@@ -760,11 +812,14 @@ struct World2 {
   // ------------------------------------------------------------------------------------------
   struct Tendon { T u, R, A, aref; };     // group-uniform registers: u = R f - aref
   struct ChainRows {                      // registers of the lane that owns a finger chain
-    T ag[MAXCD];                          // running qacc of the chain dofs
-    T mv[MAXCD * MAXCD];                  // M^-1 block
-    T lf[MAXCD], laref[MAXCD], lR[MAXCD], lsgn[MAXCD];
+    T ag[MAXCD];                          // running qacc of the chain dofs during the sweeps
     int lmask;                            // bit jl: limit of local dof jl is active
   };
+  // limit rows live in shared memory (hot): f, aref, R, sign per finger dof
+  __device__ __forceinline__ T& lf(int dof) { return hot[L.hlim + dof]; }
+  __device__ __forceinline__ T& laref(int dof) { return hot[L.hlim + MAXFD + dof]; }
+  __device__ __forceinline__ T& lR(int dof) { return hot[L.hlim + 2 * MAXFD + dof]; }
+  __device__ __forceinline__ T& lsgn(int dof) { return hot[L.hlim + 3 * MAXFD + dof]; }
 
   __device__ void rows_and_smooth(Tendon& tn, T& Ft_out) {
     const int nfd = D.nfd, ns = D.ns;
@@ -817,8 +872,8 @@ struct World2 {
     const int d0 = D.chain_dof0[c];
 #pragma unroll
     for (int jl = 0; jl < MAXCD; jl++) {
-      cr.lf[jl] = 0; cr.laref[jl] = 0; cr.lR[jl] = 1; cr.lsgn[jl] = 0;
       if (jl >= D.ncd[c]) continue;
+      lf(d0 + jl) = 0; laref(d0 + jl) = 0; lR(d0 + jl) = 1; lsgn(d0 + jl) = 0;
       const T* cd = tab(D.o_chain + c * CH_STRIDE + CH_DOF + jl * CD_STRIDE);
       if (cd[CD_LIMITED] == T(0)) continue;
       const T qq = q()[d0 + jl];
@@ -828,13 +883,11 @@ struct World2 {
       else if (dhi < T(0)) { dist = dhi; sgn = -1; }
       else continue;
       const T imp = impedance2<T>(C.lim_si, dist);
-      cr.lR[jl] = tmax(T(SG_MINVAL), (T(1) - imp) * cd[CD_IW] / imp);
-      cr.laref[jl] = -C.lim_B * (sgn * v()[d0 + jl]) - C.lim_K * imp * dist;
-      cr.lsgn[jl] = sgn;
+      lR(d0 + jl) = tmax(T(SG_MINVAL), (T(1) - imp) * cd[CD_IW] / imp);
+      laref(d0 + jl) = -C.lim_B * (sgn * v()[d0 + jl]) - C.lim_K * imp * dist;
+      lsgn(d0 + jl) = sgn;
       cr.lmask |= 1 << jl;
     }
-#pragma unroll
-    for (int k = 0; k < MAXCD * MAXCD; k++) cr.mv[k] = hot[L.minv + 16 * c + k];
   }
 
   __device__ __forceinline__ int chain_of(int dof) const {
@@ -902,12 +955,12 @@ struct World2 {
       for (int jl = 0; jl < MAXCD; jl++) {
         if (jl < D.ncd[sl]) jtf[d0 + jl] = 0;
         if (!(cr.lmask & (1 << jl))) continue;
-        const T sgn = cr.lsgn[jl];
-        const T jar = sgn * a()[d0 + jl] - cr.laref[jl];
-        const T f = jar >= T(0) ? T(0) : -(T(1) / cr.lR[jl]) * jar;
-        cr.lf[jl] = f;
+        const T sgn = lsgn(d0 + jl), ar = laref(d0 + jl), R = lR(d0 + jl);
+        const T jar = sgn * a()[d0 + jl] - ar;
+        const T f = jar >= T(0) ? T(0) : -(T(1) / R) * jar;
+        lf(d0 + jl) = f;
         jtf[d0 + jl] = sgn * f;
-        cost += f * (sgn * qs()[d0 + jl] - cr.laref[jl]) + T(0.5) * cr.lR[jl] * f * f;
+        cost += f * (sgn * qs()[d0 + jl] - ar) + T(0.5) * R * f * f;
       }
     }
     // contacts
@@ -971,7 +1024,7 @@ struct World2 {
     if (!keep) {
       if (sl < D.nchain) {
 #pragma unroll
-        for (int jl = 0; jl < MAXCD; jl++) cr.lf[jl] = 0;
+        for (int jl = 0; jl < MAXCD; jl++) if (jl < D.ncd[sl]) lf(D.chain_dof0[sl] + jl) = 0;
       }
       for (int i = sl; i < ncon; i += LPW) { T* r = crec(i); r[CR_F] = 0; r[CR_F + 1] = 0; r[CR_F + 2] = 0; }
     }
@@ -991,7 +1044,7 @@ struct World2 {
   }
 
   // one elliptic contact block (mj_solPGS inner body, dim 3) on the lane that owns its chain
-  __device__ __forceinline__ T contact_block(int i, ChainRows& cr, bool has_chain) {
+  __device__ __forceinline__ T contact_block(int i, ChainRows& cr, bool has_chain, const T* mv) {
     const int nfd = D.nfd;
     T* r = crec(i);
     T jg[12], w1[4], w2[4], w3[4];
@@ -1020,7 +1073,7 @@ struct World2 {
     }
     T f0 = old0, f1 = old1, f2 = old2;
     if (f0 < T(SG_MINVAL)) {
-      f0 -= res[0] / A00;
+      f0 -= tdiv(res[0], A00);
       if (f0 < T(0)) f0 = 0;
       f1 = 0; f2 = 0;
     } else {
@@ -1028,7 +1081,7 @@ struct World2 {
       const T x0 = A00 * v0 + A01 * v1 + A02 * v2, x1 = A01 * v0 + A11 * v1 + A12 * v2, x2 = A02 * v0 + A12 * v1 + A22 * v2;
       const T denom = v0 * x0 + v1 * x1 + v2 * x2;
       if (denom >= T(SG_MINVAL)) {
-        T x = -(v0 * res[0] + v1 * res[1] + v2 * res[2]) / denom;
+        T x = -tdiv(v0 * res[0] + v1 * res[1] + v2 * res[2], denom);
         if (f0 + x * v0 < T(0)) x = T(-1);
         f0 += x * v0; f1 += x * v1; f2 += x * v2;
       }
@@ -1042,10 +1095,11 @@ struct World2 {
       else {
         const T frc = C.con_fr;
         T vv[2];
-        const int active = qcqp2<T>(vv, A11, A12, A22, bc, frc, frc, f0);
+        const int active = qcqp2_fast<T>(vv, A11, A12, A22, bc, frc, frc, f0);
         if (active) {
-          T s = vv[0] * vv[0] / (frc * frc) + vv[1] * vv[1] / (frc * frc);
-          s = tsqrt(f0 * f0 / tmax(T(SG_MINVAL), s));
+          const T ifr2 = tdiv(T(1), frc * frc);
+          T s = vv[0] * vv[0] * ifr2 + vv[1] * vv[1] * ifr2;
+          s = tsqrt(tdiv(f0 * f0, tmax(T(SG_MINVAL), s)));
           vv[0] *= s; vv[1] *= s;
         }
         f1 = vv[0]; f2 = vv[1];
@@ -1066,52 +1120,30 @@ struct World2 {
         for (int jj = 0; jj < MAXCD; jj++) gv[jj] = jg[jj] * d0f + jg[4 + jj] * d1f + jg[8 + jj] * d2f;
 #pragma unroll
         for (int ii = 0; ii < MAXCD; ii++) {
-          T s = 0;
-#pragma unroll
-          for (int jj = 0; jj < MAXCD; jj++) s += cr.mv[4 * ii + jj] * gv[jj];
-          cr.ag[ii] += s;
+          T m4[4]; ld4(mv + 4 * ii, m4);
+          cr.ag[ii] += m4[0] * gv[0] + m4[1] * gv[1] + m4[2] * gv[2] + m4[3] * gv[3];
         }
       }
     }
     return change;
   }
 
-  // one equality row of the level sweep, split so that two independent rows can be in flight
-  struct RowRegs { int d1, d2; T iw1, iw2, a1, a2, u, R; };
-  __device__ __forceinline__ void row_load(RowRegs& rr, int p, const int* rd, const T* riw, const T* av, const T* row2) {
-    const int d12 = __ldg(rd + p);
-    rr.d1 = d12 & 0xffff; rr.d2 = (d12 >> 16) & 0xffff;
-    rr.iw1 = __ldg(riw + 2 * p); rr.iw2 = __ldg(riw + 2 * p + 1);
-    rr.a1 = av[rr.d1];
-    rr.a2 = rr.d2 != 0xffff ? av[rr.d2] : T(0);
-    ld2(row2 + 2 * p, rr.u, rr.R);
-  }
-  __device__ __forceinline__ void row_solve(RowRegs& rr, T& impr) {
-    const T res = (rr.a1 - rr.a2) + rr.u;
-    const T dl = -res * trcp<T>(rr.iw1 + rr.iw2 + rr.R);
-    impr -= T(0.5) * dl * res;
-    rr.u += rr.R * dl;
-    rr.a1 += rr.iw1 * dl;
-    rr.a2 -= rr.iw2 * dl;
-  }
-  __device__ __forceinline__ void row_store(const RowRegs& rr, int p, T* av, T* row2) {
-    row2[2 * p] = rr.u;
-    av[rr.d1] = rr.a1;
-    if (rr.d2 != 0xffff) av[rr.d2] = rr.a2;
-  }
-
   // projected Gauss-Seidel (mj_solPGS) in MuJoCo's row order
   __device__ void pgs(Tendon& tn, ChainRows& cr) {
     const int nfd = D.nfd, ns = D.ns;
-    const int* lev_start = itab(D.io_lev_start);
-    const int* rd = itab(D.io_row_d12);
-    const T* riw = tab(D.o_row_iw);
+    // step descriptors of the level sweep (built per lanes-per-world by the host, staged in shared memory by the
+    // kernel prologue and shared by all worlds of the CTA): slot = step * LPW + lane.
+    // {first slider | second slider << 16, row | last-step-of-level << 30} and {1/m first, 1/m second}.  Slots
+    // that pad a level and rows with a single slider point at the dummy slider / dummy row, so the loop body has
+    // no predication at all.
+    const int nstep = D.nstep;
     const T* tcv = tab(D.o_sl_tc);
     const T* tciw = tab(D.o_sl_tciw);
     T* av = a() + nfd;
     T* row2 = hot + L.row2;
     const int tmaxw = wmax(misc(M2_TMAX));
     const bool chain_lane = sl < D.nchain;
+    const T* mv = hot + L.minv + 16 * (chain_lane ? sl : 0);
     // this lane's slice of the contact schedule
     int mystart = 0, mycnt = 0;
     {
@@ -1138,23 +1170,29 @@ struct World2 {
     for (int it = 0; it < D.iters; it++) {
       if (!__any_sync(FULLMASK, !done)) break;
       T impr = 0;
-      // ---- equality block, level by level; up to two rows per lane in flight ----
-      int p0 = __ldg(lev_start);
-      for (int lv = 0; lv < D.nlev; lv++) {
-        const int p1 = __ldg(lev_start + lv + 1);
-        for (int pb = p0; pb < p1; pb += 2 * LPW) {
-          const int pA = pb + sl, pB = pA + LPW;
-          const bool hA = !done && pA < p1, hB = !done && pB < p1;
-          RowRegs ra, rb;
-          if (hA) row_load(ra, pA, rd, riw, av, row2);
-          if (hB) row_load(rb, pB, rd, riw, av, row2);
-          if (hA) row_solve(ra, impr);
-          if (hB) row_solve(rb, impr);
-          if (hA) row_store(ra, pA, av, row2);
-          if (hB) row_store(rb, pB, av, row2);
+      // ---- equality block: one row per lane per step, a warp barrier where a dependency level ends.  The next
+      // step's descriptor is fetched before the barrier so that its latency overlaps this step's arithmetic. ----
+      {
+        const T gate = done ? T(0) : T(1);
+        int2 dn = sdesc[0];
+        T iw1n, iw2n; ld2(siw, iw1n, iw2n);
+        for (int st = 0; st < nstep; st++) {
+          const int2 dc = dn; const T iw1 = iw1n, iw2 = iw2n;
+          const int nx = st + 1 < nstep ? st + 1 : st;
+          dn = sdesc[nx * LPW];
+          ld2(siw + 2 * nx * LPW, iw1n, iw2n);
+          const int d1 = dc.x & 0xffff, d2 = (dc.x >> 16) & 0xffff, p = dc.y & 0x3fffffff;
+          T a1 = av[d1], a2 = av[d2];
+          T u, R; ld2(row2 + 2 * p, u, R);
+          const T res = (a1 - a2) + u;
+          const T dl = -res * trcp<T>(iw1 + iw2 + R) * gate;
+          impr -= T(0.5) * dl * res;
+          u += R * dl; a1 += iw1 * dl; a2 -= iw2 * dl;
+          row2[2 * p] = u;
+          av[d1] = a1;
+          av[d2] = a2;
+          if (dc.y >> 30) __syncwarp();
         }
-        p0 = p1;
-        __syncwarp();
       }
       // ---- volume-tendon row: dense over the shell, sub-warp shuffle reduction ----
       {
@@ -1173,19 +1211,20 @@ struct World2 {
 #pragma unroll
         for (int jl = 0; jl < MAXCD; jl++) {
           if (!(cr.lmask & (1 << jl))) continue;
-          const T sgn = cr.lsgn[jl], f = cr.lf[jl], R = cr.lR[jl];
-          const T A = cr.mv[4 * jl + jl] + R;
-          const T res = sgn * cr.ag[jl] - cr.laref[jl] + R * f;
-          T fn = f - res / A;
+          const int dof = D.chain_dof0[sl] + jl;
+          const T sgn = lsgn(dof), f = lf(dof), R = lR(dof);
+          const T A = mv[4 * jl + jl] + R;
+          const T res = sgn * cr.ag[jl] - laref(dof) + R * f;
+          T fn = f - tdiv(res, A);
           if (fn < T(0)) fn = 0;
           T dl = fn - f;
           T change = T(0.5) * dl * dl * A + dl * res;
           if (change > T(1e-10)) { fn = f; dl = 0; change = 0; }
           impr -= change;
-          cr.lf[jl] = fn;
+          lf(dof) = fn;
           if (dl != T(0)) {
 #pragma unroll
-            for (int ii = 0; ii < MAXCD; ii++) cr.ag[ii] += cr.mv[4 * ii + jl] * sgn * dl;
+            for (int ii = 0; ii < MAXCD; ii++) cr.ag[ii] += mv[4 * ii + jl] * sgn * dl;
           }
         }
       }
@@ -1193,7 +1232,10 @@ struct World2 {
       for (int t = 1; t <= tmaxw; t++) {
         if (!done && k < mycnt) {
           const int ent = auxi[L.i_order + mystart + k];
-          if ((ent >> 16) == t) { impr -= contact_block(ent & 0xffff, cr, chain_lane); k++; }
+          if ((ent >> 16) == t) {
+            if (k + 1 < mycnt && !L.aux_in_smem) prefetch_l1(crec(auxi[L.i_order + mystart + k + 1] & 0xffff));
+            impr -= contact_block(ent & 0xffff, cr, chain_lane, mv); k++;
+          }
         }
         __syncwarp();
       }
@@ -1237,15 +1279,7 @@ struct World2 {
         for (int k = 0; k < 3; k++) aux[L.sens + adr + k] = o[k];
       }
     }
-    // limit forces of the last step (diagnostics, and the touch of registers keeps them live only here)
-    if (sl < D.nchain) {
-      auxi[L.i_lmask + sl] = cr.lmask;
-#pragma unroll
-      for (int jl = 0; jl < MAXCD; jl++) {
-        T* lr = aux + L.lim + 3 * (D.chain_dof0[sl] + jl);
-        lr[0] = cr.lf[jl]; lr[1] = cr.laref[jl]; lr[2] = cr.lR[jl];
-      }
-    }
+    if (sl < D.nchain) auxi[L.i_lmask + sl] = cr.lmask;
     {
       int s = (sl < D.nchain) ? __popc((unsigned)cr.lmask) : 0;
 #pragma unroll
@@ -1274,32 +1308,34 @@ struct World2 {
     __syncwarp();
   }
 
-  // mj_step
-  __device__ void step() {
-    bool badpv = false;
-    for (int i = sl; i < D.nv; i += LPW) if (!(tabs(q()[i]) <= T(SG_MAXVAL)) || !(tabs(v()[i]) <= T(SG_MAXVAL))) badpv = true;
-    const bool gbad = gballot(badpv) != 0u;
-    if (gbad && sl == 0) misc(M2_STATUS) |= 1;
-    // reset_if contains a warp collective: every group goes through it, only the bad ones write
-    reset_if(gbad);
-    T* a0 = aux + L.a0;
-    for (int i = sl; i < D.nv; i += LPW) a0[i] = a()[i];
-    bool bad = forward();
-    if (__any_sync(FULLMASK, bad)) {
+  // mj_step (integrate) or mj_forward (!integrate).  forward() is inlined exactly once: the kernel is one loop over
+  // physics steps around this function, so the whole step stays a few thousand instructions (instruction cache).
+  __device__ void step(bool integrate) {
+    if (integrate) {
+      bool badpv = false;
+      for (int i = sl; i < D.nv; i += LPW) if (!(tabs(q()[i]) <= T(SG_MAXVAL)) || !(tabs(v()[i]) <= T(SG_MAXVAL))) badpv = true;
+      const bool gbad = gballot(badpv) != 0u;
+      if (gbad && sl == 0) misc(M2_STATUS) |= 1;
+      // reset_if contains a warp collective: every group goes through it, only the bad ones write
+      reset_if(gbad);
+      T* a0 = aux + L.a0;
+      for (int i = sl; i < D.nv; i += LPW) a0[i] = a()[i];
+    }
+    for (int pass = 0; pass < 2; pass++) {
+      const bool bad = forward();
+      if (!integrate || !__any_sync(FULLMASK, bad)) break;
       // mj_step re-runs mj_forward after mj_resetData.  forward() is full of warp collectives, so the other
       // groups of the warp re-run it too, from their saved warm start: they recompute identical values.
       if (bad && sl == 0) misc(M2_STATUS) |= 1;
-      if (!bad) for (int i = sl; i < D.nv; i += LPW) a()[i] = a0[i];
-      reset_if(bad);
-      bad = forward();
-      if (bad && sl == 0) misc(M2_STATUS) |= 1;
+      if (pass == 0 && !bad) { const T* a0 = aux + L.a0; for (int i = sl; i < D.nv; i += LPW) a()[i] = a0[i]; }
       reset_if(bad);
     }
-    euler();
+    if (integrate) euler();
   }
   __device__ void reset_if(bool doit) {
     if (doit) {
       for (int i = sl; i < D.nv; i += LPW) { q()[i] = 0; v()[i] = 0; a()[i] = 0; }
+      if (sl == 0) a()[D.nv] = 0;      // dummy slider of the level sweep
       if (sl < D.nu) { aux[L.act + sl] = 0; aux[L.ctrl + sl] = 0; }
     }
     __syncwarp();
@@ -1330,8 +1366,8 @@ struct World2 {
       for (int c = 0; c < D.nchain; c++)
         for (int jl = 0; jl < D.ncd[c]; jl++)
           if (auxi[L.i_lmask + c] & (1 << jl)) {
-            const T* lr = aux + L.lim + 3 * (D.chain_dof0[c] + jl);
-            o[eb + r] = (double)lr[0]; o[eb + nefc + r] = (double)lr[1]; o[eb + 2 * nefc + r] = (double)lr[2]; r++;
+            const int dof = D.chain_dof0[c] + jl;
+            o[eb + r] = (double)lf(dof); o[eb + nefc + r] = (double)laref(dof); o[eb + 2 * nefc + r] = (double)lR(dof); r++;
           }
       for (int i = 0; i < ncon; i++)
         for (int k = 0; k < 3; k++, r++) {
@@ -1350,20 +1386,39 @@ struct World2 {
 #define SG_SHARED_BYTES(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
+// A CTA holds 1..SG_MAX_WARPS warps (blockDim.x / 32, chosen by the host).  Warps never exchange data: the CTA exists so
+// that (i) the level-sweep step tables are staged in shared memory once and shared by all its worlds and (ii) its
+// warps start every physics step together (one __syncthreads per step), which keeps them in the same region of the
+// large straight-line set-up code and therefore in the same instruction-cache lines.
+#ifndef SG_MAX_WARPS
+#define SG_MAX_WARPS 16
+#endif
+#ifndef SG_MIN_CTAS
+#define SG_MIN_CTAS 1
+#endif
 template <typename T, int LPW>
-__global__ void __launch_bounds__(32) sg_step_kernel2(const __grid_constant__ KArgs2<T> K) {
+__global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel2(const __grid_constant__ KArgs2<T> K) {
   SG_SHARED_BYTES(smem_raw);
   constexpr int WPW = 32 / LPW;
   const PlanDims& D = K.D;
   const Layout2& L = K.L;
   const int lane = threadIdx.x & 31, grp = lane / LPW, sl = lane % LPW;
-  const int ngroups = gridDim.x * WPW;
-  for (int w0 = blockIdx.x * WPW; w0 < K.nworlds; w0 += ngroups) {
-    const int wi = w0 + grp;
+  const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  {
+    // stage the step tables: int2 descriptors, then the (1/m, 1/m) pairs
+    int* sd = reinterpret_cast<int*>(smem_raw);
+    T* sw = reinterpret_cast<T*>(smem_raw + (size_t)D.nstep * LPW * 8);
+    const int n2 = 2 * D.nstep * LPW;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) { sd[i] = K.itab[D.io_step_d + i]; sw[i] = K.tab[D.o_step_iw + i]; }
+    __syncthreads();
+  }
+  const int cta_worlds = nwarp * WPW;
+  for (int b0 = blockIdx.x * cta_worlds; b0 < K.nworlds; b0 += gridDim.x * cta_worlds) {
+    const int wi = b0 + warp * WPW + grp;
     const bool valid = wi < K.nworlds;
     World2<T, LPW> W(K, smem_raw, valid ? wi : K.nworlds - 1, valid);
     W.load_params();
-    if (sl == 0) W.misc(M2_STATUS) = 0;
+    if (sl == 0) { W.misc(M2_STATUS) = 0; W.a()[D.nv] = 0; W.hot[L.row2 + 2 * D.nrow] = 0; W.hot[L.row2 + 2 * D.nrow + 1] = 1; }
     const int w = W.w;
     const size_t sb = (size_t)w * D.nv;
     T* aux = W.aux;
@@ -1371,33 +1426,37 @@ __global__ void __launch_bounds__(32) sg_step_kernel2(const __grid_constant__ KA
     if (!K.rollout) {
       for (int i = sl; i < D.nv; i += LPW) { W.q()[i] = K.qpos[sb + i]; W.v()[i] = K.qvel[sb + i]; W.a()[i] = K.warm[sb + i]; }
       __syncwarp();
-      if (K.integrate) { for (int s = 0; s < K.nsub; s++) W.step(); }
-      else {
-        // mj_forward: sensors/contacts refreshed, nothing integrated, warm start left untouched
-        W.forward();
-        __syncwarp();
-        for (int i = sl; i < D.nv; i += LPW) W.a()[i] = K.warm[sb + i];
-        __syncwarp();
+    } else W.reset_if(true);     // whole episode on-chip (create_dataset.log_into_file, ref: create_dataset.py:33-60)
+    const int total = K.rollout ? K.sim_start + K.nrows * K.sim_step : (K.integrate ? K.nsub : 1);
+    for (int s = 0; s < total; s++) {
+      if (nwarp > 1) __syncthreads();     // warps start each step together (instruction-cache locality, see above)
+      int t = -1, phase = 0;
+      if (K.rollout && s >= K.sim_start) {
+        const int r = s - K.sim_start;
+        t = r / K.sim_step; phase = r - t * K.sim_step;
+        if (phase == 0) {
+          if (K.ctrl_event[t] && sl < D.nu) aux[L.ctrl + sl] = T(K.ctrl_value[t * D.nu + sl]);
+          __syncwarp();
+        }
       }
-      if (valid) {
-        for (int i = sl; i < D.nv; i += LPW) { K.qpos[sb + i] = W.q()[i]; K.qvel[sb + i] = W.v()[i]; K.warm[sb + i] = W.a()[i]; }
+      W.step(K.rollout || K.integrate);
+      if (t >= 0 && phase == K.sim_step - 1 && valid) {
+        for (int i = sl; i < D.nsd; i += LPW) K.sens_out[((size_t)w * K.nrows + t) * D.nsd + i] = aux[L.sens + i];
+        if (K.touch_out && sl == 0) K.touch_out[(size_t)w * K.nrows + t] = W.misc(M2_TOUCH);
+      }
+    }
+    if (!K.rollout && !K.integrate) {
+      // mj_forward: sensors/contacts refreshed, nothing integrated, warm start left untouched
+      __syncwarp();
+      for (int i = sl; i < D.nv; i += LPW) W.a()[i] = K.warm[sb + i];
+      __syncwarp();
+    }
+    if (valid) {
+      for (int i = sl; i < D.nv; i += LPW) { K.qpos[sb + i] = W.q()[i]; K.qvel[sb + i] = W.v()[i]; K.warm[sb + i] = W.a()[i]; }
+      if (!K.rollout) {
         if (K.sens_out) for (int i = sl; i < D.nsd; i += LPW) K.sens_out[(size_t)w * D.nsd + i] = aux[L.sens + i];
         if (K.touch_out && sl == 0) K.touch_out[w] = W.misc(M2_TOUCH);
       }
-    } else {
-      // whole episode on-chip (create_dataset.log_into_file, ref: create_dataset.py:33-60)
-      W.reset_if(true);
-      for (int s = 0; s < K.sim_start; s++) W.step();
-      for (int t = 0; t < K.nrows; t++) {
-        if (K.ctrl_event[t] && sl < D.nu) aux[L.ctrl + sl] = T(K.ctrl_value[t * D.nu + sl]);
-        __syncwarp();
-        for (int s = 0; s < K.sim_step; s++) W.step();
-        if (valid) {
-          for (int i = sl; i < D.nsd; i += LPW) K.sens_out[((size_t)w * K.nrows + t) * D.nsd + i] = aux[L.sens + i];
-          if (K.touch_out && sl == 0) K.touch_out[(size_t)w * K.nrows + t] = W.misc(M2_TOUCH);
-        }
-      }
-      if (valid) for (int i = sl; i < D.nv; i += LPW) { K.qpos[sb + i] = W.q()[i]; K.qvel[sb + i] = W.v()[i]; K.warm[sb + i] = W.a()[i]; }
     }
     __syncwarp();
     if (valid) {

@@ -7,7 +7,7 @@
 
 namespace sg {
 // returns the CUDA error code of the launch (0 = ok)
-template <typename T, int LPW> int k2_launch(const KArgs2<T>& K, int grid, size_t smem, void* stream);
+template <typename T, int LPW> int k2_launch(const KArgs2<T>& K, int grid, int block, size_t smem, void* stream);
 // sets the dynamic shared-memory limit / carve-out and reports resident CTAs per SM
-template <typename T, int LPW> int k2_configure(size_t smem, int* per_sm);
+template <typename T, int LPW> int k2_configure(int block, size_t smem, int* per_sm);
 }  // namespace sg

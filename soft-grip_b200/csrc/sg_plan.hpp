@@ -68,6 +68,10 @@ struct PlanDims {
   // offsets into the int table
   int io_kmask, io_row_d1, io_row_d2, io_lev_start, io_dof_rows, io_pair_t, io_pair_a, io_pair_b;
   int io_row_d12;   // nrow: first slider | second slider << 16 (0xffff: none), schedule order
+  // per-batch step tables of the level sweep (depend on the lanes per world; appended by sg_api.cu)
+  int io_step_d;    // 2*nstep*lpw ints: {d1 | d2 << 16, row | last-of-level << 30} per slot
+  int o_step_iw;    // 2*nstep*lpw reals: {1/m first, 1/m second} per slot
+  int nstep;
 };
 
 struct Blob {
@@ -136,6 +140,34 @@ struct Plan {
 };
 
 #define SG_REQUIRE(cond, msg) do { if (!(cond)) throw std::runtime_error(std::string("unsupported model: ") + msg); } while (0)
+
+// Level sweep tables for `lpw` lanes per world: every dependency level is cut into steps of `lpw` slots; padding slots
+// and the missing second slider of fix rows point at the dummy slider (index ns, inverse mass 0) and the dummy row
+// (index nrow, u = 0, R = 1), which the sweep leaves unchanged.
+inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab, const std::vector<int>& itab, int lpw,
+                              std::vector<int>& step_d, std::vector<double>& step_iw) {
+  step_d.clear(); step_iw.clear();
+  const int dummy_d = D.ns, dummy_p = D.nrow;
+  for (int lv = 0; lv < D.nlev; lv++) {
+    const int p0 = itab[D.io_lev_start + lv], p1 = itab[D.io_lev_start + lv + 1];
+    // consecutive table levels that were only split at 32 rows belong to one dependency level: no barrier is
+    // needed between them, but keeping one is harmless
+    for (int pb = p0; pb < p1; pb += lpw) {
+      const bool last = pb + lpw >= p1;
+      for (int k = 0; k < lpw; k++) {
+        const int p = pb + k;
+        int d1 = dummy_d, d2 = dummy_d, row = dummy_p; double iw1 = 0, iw2 = 0;
+        if (p < p1) {
+          d1 = itab[D.io_row_d1 + p]; row = p; iw1 = 1.0 / tab[D.o_sl_m + d1];
+          const int dd2 = itab[D.io_row_d2 + p];
+          if (dd2 >= 0) { d2 = dd2; iw2 = 1.0 / tab[D.o_sl_m + dd2]; }
+        }
+        step_d.push_back(d1 | (d2 << 16)); step_d.push_back(row | ((last ? 1 : 0) << 30));
+        step_iw.push_back(iw1); step_iw.push_back(iw2);
+      }
+    }
+  }
+}
 
 inline bool same(const double* a, const double* b, int n) { for (int i = 0; i < n; i++) if (a[i] != b[i]) return false; return true; }
 

@@ -49,13 +49,17 @@ def _p(a):
 class EmuBatch:
     """W worlds stepping under the emulator; mirrors the parts of BatchedManEnv the parity tests use."""
 
-    def __init__(self, blob_path, W, prec=64, lpw=8, aux_smem=0, joint_ids=range(11, 64), tendon0=1):
+    def __init__(self, blob_path, W, prec=64, lpw=8, aux_smem=0, nw=None, joint_ids=range(11, 64), tendon0=1):
         batched = importlib.import_module("soft-grip_b200.batched")
         mjcf = importlib.import_module("soft-grip_b200.mjcf")
         lib_ = importlib.import_module("soft-grip_b200._lib")
         self.L = lib()
         os.environ["SOFTGRIP_LPW"] = str(lpw)
         os.environ["SOFTGRIP_AUX_SMEM"] = str(aux_smem)
+        if nw is None:
+            os.environ.pop("SOFTGRIP_NW", None)
+        else:
+            os.environ["SOFTGRIP_NW"] = str(nw)
         blob = open(blob_path, "rb").read()
         self.model = mjcf.load_blob(blob_path)
         self.m = C.c_void_p()

@@ -6,7 +6,7 @@
 // code (sub-warp shuffles, ballots, __syncwarp-ordered shared memory) whose logic errors are otherwise only
 // observable on a GPU box.  Each lane of a warp is a ucontext fiber; every warp-collective is a rendezvous of
 // all 32 lanes, and the emulator aborts when lanes meet at different collectives (undefined behaviour on a
-// GPU).  One warp per CTA (the kernels use blockDim.x == 32); CTAs run one after another.
+// GPU).  A CTA may hold several warps (__syncthreads is a rendezvous of all of them); CTAs run one after another.
 #pragma once
 #include <ucontext.h>
 
@@ -22,65 +22,100 @@ struct Dim3 { unsigned x = 1, y = 1, z = 1; };
 inline Dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 struct WarpState {
-  ucontext_t sched;
   ucontext_t ctx[32];
   char* stack[32] = {nullptr};
   bool done[32];
   unsigned long long slot[2][32];
   int site[2][32];
   int gen = 0;
-  int cur = 0;
+  bool finished = false, at_cta_barrier = false;
+};
+constexpr int MAX_WARPS = 32;
+struct CtaState {
+  ucontext_t sched;
+  WarpState warp[MAX_WARPS];
+  int nwarps = 1;
+  int cur_warp = 0, cur = 0;          // running fiber
   unsigned char* smem = nullptr;
   size_t smem_bytes = 0;
   void (*entry)(void*) = nullptr;
   void* arg = nullptr;
 };
-inline WarpState W;
+inline CtaState CTA;
 constexpr size_t STACK_BYTES = 512 * 1024;
+enum { SITE_SYNCWARP = 1, SITE_SYNCTHREADS = 2 };
 
 inline void fiber_main() {
-  W.entry(W.arg);
-  W.done[W.cur] = true;
-  swapcontext(&W.ctx[W.cur], &W.sched);
+  CTA.entry(CTA.arg);
+  WarpState& W = CTA.warp[CTA.cur_warp];
+  W.done[CTA.cur] = true;
+  swapcontext(&W.ctx[CTA.cur], &CTA.sched);
 }
 
-// every lane calls this at a collective; returns the generation whose slots hold all lanes' values
+// every lane of a warp calls this at a collective; returns the generation whose slots hold all lanes' values
 inline int rendezvous(unsigned long long v, int site) {
-  const int lane = W.cur, g = W.gen;
+  WarpState& W = CTA.warp[CTA.cur_warp];
+  const int lane = CTA.cur, g = W.gen;
   W.slot[g & 1][lane] = v;
   W.site[g & 1][lane] = site;
-  swapcontext(&W.ctx[lane], &W.sched);
+  swapcontext(&W.ctx[lane], &CTA.sched);
   return g;
 }
+inline WarpState& cur_warp() { return CTA.warp[CTA.cur_warp]; }
+inline int cur_lane() { return CTA.cur; }
 
-inline void run_warp() {
+// resumes every lane of warp `wi` until its next collective (or exit)
+inline void run_round(int wi) {
+  WarpState& W = CTA.warp[wi];
+  int ndone = 0;
   for (int l = 0; l < 32; l++) {
-    if (!W.stack[l]) W.stack[l] = (char*)malloc(STACK_BYTES);
-    getcontext(&W.ctx[l]);
-    W.ctx[l].uc_stack.ss_sp = W.stack[l];
-    W.ctx[l].uc_stack.ss_size = STACK_BYTES;
-    W.ctx[l].uc_link = &W.sched;
-    makecontext(&W.ctx[l], (void (*)())fiber_main, 0);
-    W.done[l] = false;
+    if (W.done[l]) { ndone++; continue; }
+    CTA.cur_warp = wi; CTA.cur = l;
+    threadIdx.x = (unsigned)(wi * 32 + l);
+    swapcontext(&CTA.sched, &W.ctx[l]);
+    if (W.done[l]) ndone++;
+  }
+  if (ndone == 32) { W.finished = true; return; }
+  if (ndone != 0) { fprintf(stderr, "simt: %d lanes of warp %d exited while others wait at a collective\n", ndone, wi); abort(); }
+  const int g = W.gen & 1;
+  for (int l = 1; l < 32; l++)
+    if (W.site[g][l] != W.site[g][0]) {
+      fprintf(stderr, "simt: divergent collectives: lane 0 at site %d, lane %d at site %d (block %u warp %d)\n", W.site[g][0], l, W.site[g][l], blockIdx.x, wi);
+      abort();
+    }
+  if (W.site[g][0] == SITE_SYNCTHREADS) W.at_cta_barrier = true;
+  W.gen++;
+}
+
+inline void run_cta() {
+  for (int wi = 0; wi < CTA.nwarps; wi++) {
+    WarpState& W = CTA.warp[wi];
+    W.gen = 0; W.finished = false; W.at_cta_barrier = false;
+    for (int l = 0; l < 32; l++) {
+      if (!W.stack[l]) W.stack[l] = (char*)malloc(STACK_BYTES);
+      getcontext(&W.ctx[l]);
+      W.ctx[l].uc_stack.ss_sp = W.stack[l];
+      W.ctx[l].uc_stack.ss_size = STACK_BYTES;
+      W.ctx[l].uc_link = &CTA.sched;
+      makecontext(&W.ctx[l], (void (*)())fiber_main, 0);
+      W.done[l] = false;
+    }
   }
   for (;;) {
-    int ndone = 0;
-    for (int l = 0; l < 32; l++) {
-      if (W.done[l]) { ndone++; continue; }
-      W.cur = l;
-      threadIdx.x = (unsigned)l;
-      swapcontext(&W.sched, &W.ctx[l]);
-      if (W.done[l]) ndone++;
+    int nfin = 0, nbar = 0;
+    for (int wi = 0; wi < CTA.nwarps; wi++) {
+      WarpState& W = CTA.warp[wi];
+      if (W.finished) { nfin++; continue; }
+      if (W.at_cta_barrier) { nbar++; continue; }
+      run_round(wi);
+      if (W.finished) nfin++;
+      else if (W.at_cta_barrier) nbar++;
     }
-    if (ndone == 32) break;
-    if (ndone != 0) { fprintf(stderr, "simt: %d lanes exited while others wait at a collective\n", ndone); abort(); }
-    const int g = W.gen & 1;
-    for (int l = 1; l < 32; l++)
-      if (W.site[g][l] != W.site[g][0]) {
-        fprintf(stderr, "simt: divergent collectives: lane 0 at site %d, lane %d at site %d (block %u)\n", W.site[g][0], l, W.site[g][l], blockIdx.x);
-        abort();
-      }
-    W.gen++;
+    if (nfin == CTA.nwarps) break;
+    if (nbar > 0 && nbar + nfin == CTA.nwarps) {
+      if (nfin) { fprintf(stderr, "simt: __syncthreads with %d exited warps\n", nfin); abort(); }
+      for (int wi = 0; wi < CTA.nwarps; wi++) CTA.warp[wi].at_cta_barrier = false;
+    }
   }
 }
 
@@ -89,19 +124,20 @@ struct Thunk { F f; A a; static void call(void* p) { Thunk* t = (Thunk*)p; t->f(
 
 template <typename F, typename A>
 inline void launch(F kernel, unsigned grid, unsigned block, size_t smem, const A& arg) {
-  if (block != 32) { fprintf(stderr, "simt: only blockDim.x == 32 is emulated\n"); abort(); }
-  if (smem > W.smem_bytes) { free(W.smem); W.smem = (unsigned char*)malloc(smem + 64); W.smem_bytes = smem; }
+  if (block % 32 != 0 || block / 32 > (unsigned)MAX_WARPS) { fprintf(stderr, "simt: blockDim.x must be a multiple of 32 (<= %d)\n", 32 * MAX_WARPS); abort(); }
+  if (smem > CTA.smem_bytes) { free(CTA.smem); CTA.smem = (unsigned char*)malloc(smem + 64); CTA.smem_bytes = smem; }
   Thunk<F, A> t{kernel, arg};
-  W.entry = &Thunk<F, A>::call;
-  W.arg = &t;
+  CTA.entry = &Thunk<F, A>::call;
+  CTA.arg = &t;
+  CTA.nwarps = (int)(block / 32);
   gridDim.x = grid; blockDim.x = block;
   for (unsigned b = 0; b < grid; b++) {
     blockIdx.x = b;
-    memset(W.smem, 0xff, smem);   // NaN pattern: reads of never-written shared memory show up as NaNs
-    run_warp();
+    memset(CTA.smem, 0xff, smem);   // NaN pattern: reads of never-written shared memory show up as NaNs
+    run_cta();
   }
 }
-inline unsigned char* smem_ptr() { return W.smem; }
+inline unsigned char* smem_ptr() { return CTA.smem; }
 
 template <typename T> inline unsigned long long to_bits(T v) { unsigned long long b = 0; memcpy(&b, &v, sizeof(T)); return b; }
 template <typename T> inline T from_bits(unsigned long long b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
@@ -121,20 +157,20 @@ using simt::blockIdx;
 using simt::gridDim;
 using simt::threadIdx;
 
-inline void __syncwarp(unsigned = 0xffffffffu) { simt::rendezvous(0, 1); }
-inline void __syncthreads() { simt::rendezvous(0, 2); }
+inline void __syncwarp(unsigned = 0xffffffffu) { simt::rendezvous(0, simt::SITE_SYNCWARP); }
+inline void __syncthreads() { simt::rendezvous(0, simt::SITE_SYNCTHREADS); }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o) {
-  const int lane = simt::W.cur, g = simt::rendezvous(simt::to_bits(v), 3);
-  return simt::from_bits<T>(simt::W.slot[g & 1][(lane ^ o) & 31]);
+  const int lane = simt::cur_lane(), g = simt::rendezvous(simt::to_bits(v), 3);
+  return simt::from_bits<T>(simt::cur_warp().slot[g & 1][(lane ^ o) & 31]);
 }
 template <typename T> inline T __shfl_sync(unsigned, T v, int src) {
   const int g = simt::rendezvous(simt::to_bits(v), 4);
-  return simt::from_bits<T>(simt::W.slot[g & 1][src & 31]);
+  return simt::from_bits<T>(simt::cur_warp().slot[g & 1][src & 31]);
 }
 inline unsigned __ballot_sync(unsigned, int pred) {
   const int g = simt::rendezvous(pred ? 1 : 0, 5);
   unsigned m = 0;
-  for (int l = 0; l < 32; l++) if (simt::W.slot[g & 1][l]) m |= 1u << l;
+  for (int l = 0; l < 32; l++) if (simt::cur_warp().slot[g & 1][l]) m |= 1u << l;
   return m;
 }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
@@ -142,13 +178,13 @@ inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0
 inline unsigned __reduce_or_sync(unsigned, unsigned v) {
   const int g = simt::rendezvous(v, 6);
   unsigned r = 0;
-  for (int l = 0; l < 32; l++) r |= (unsigned)simt::W.slot[g & 1][l];
+  for (int l = 0; l < 32; l++) r |= (unsigned)simt::cur_warp().slot[g & 1][l];
   return r;
 }
 inline int __reduce_max_sync(unsigned, int v) {
   const int g = simt::rendezvous(simt::to_bits(v), 7);
-  int r = simt::from_bits<int>(simt::W.slot[g & 1][0]);
-  for (int l = 1; l < 32; l++) { int x = simt::from_bits<int>(simt::W.slot[g & 1][l]); if (x > r) r = x; }
+  int r = simt::from_bits<int>(simt::cur_warp().slot[g & 1][0]);
+  for (int l = 1; l < 32; l++) { int x = simt::from_bits<int>(simt::cur_warp().slot[g & 1][l]); if (x > r) r = x; }
   return r;
 }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }

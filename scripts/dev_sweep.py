@@ -18,6 +18,7 @@ for cfg in cfgs:
     parts = {x[0]: int(x[1:]) for x in cfg.split(":")}
     k, l, a = parts.get("k", 2), parts.get("l", 8), parts.get("a", 0)
     os.environ["SOFTGRIP_KERNEL"] = str(k); os.environ["SOFTGRIP_LPW"] = str(l); os.environ["SOFTGRIP_AUX_SMEM"] = str(a)
+    os.environ["SOFTGRIP_QV_SMEM"] = str(parts.get("q", 0))
     if "n" in parts: os.environ["SOFTGRIP_NW"] = str(parts["n"])
     else: os.environ.pop("SOFTGRIP_NW", None)
     for dt in (torch.float32,):

@@ -178,6 +178,8 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   if (const char* e = std::getenv("SOFTGRIP_KERNEL")) b->kernel = std::atoi(e);
   if (const char* e = std::getenv("SOFTGRIP_LPW")) b->lpw = std::atoi(e);
   if (const char* e = std::getenv("SOFTGRIP_NW")) b->nwarp = std::atoi(e);
+  int qv_in_smem = 0;
+  if (const char* e = std::getenv("SOFTGRIP_QV_SMEM")) qv_in_smem = std::atoi(e);
   if (const char* e = std::getenv("SOFTGRIP_AUX_SMEM")) aux_in_smem = std::atoi(e);
 #ifdef SG_SIMT_EMU
   b->kernel = 2;
@@ -188,7 +190,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   if (b->kernel == 2) {
     const Plan& P = m->plan;
     build_step_tables(b->D, P.tab, P.itab, b->lpw, b->step_d, b->step_iw);
-    b->D.nstep = (int)(b->step_d.size() / (2 * (size_t)b->lpw));
+    b->D.nstep = (int)(b->step_d.size() / (2 * (size_t)b->lpw)) - 1;   // without the trailing dummy step
     b->D.o_step_iw = (int)((P.tab.size() + 3) / 4 * 4);
     b->D.io_step_d = (int)((P.itab.size() + 3) / 4 * 4);
   }
@@ -216,7 +218,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       while (b->nwarp > 1 && (nworlds + b->nwarp * wpw - 1) / (b->nwarp * wpw) < 2 * prop.multiProcessorCount) b->nwarp /= 2;
     }
     for (;;) {
-      b->L2 = precision == 32 ? make_layout2<float>(b->D, aux_in_smem, wpw, b->lpw) : make_layout2<double>(b->D, aux_in_smem, wpw, b->lpw);
+      b->L2 = precision == 32 ? make_layout2<float>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem) : make_layout2<double>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem);
       b->smem2 = (size_t)b->L2.smem_tables + (size_t)b->L2.smem_stride * wpw * b->nwarp;
       if (b->smem2 <= prop.sharedMemPerBlockOptin || b->nwarp == 1) break;
       b->nwarp /= 2;

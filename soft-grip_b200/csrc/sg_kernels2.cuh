@@ -53,7 +53,8 @@ struct Layout2 {
   int h_misc;            // 8 ints
   int hotI;
   // aux: shared memory or global scratch
-  int q, v, qs, jtf, a0; // nv each (a0: qacc_warmstart at step entry, for the re-run after a divergence reset)
+  int q, v, qs, jtf, a0; // nv each (qs: qacc_smooth; a0: qacc_warmstart at step entry, for the re-run after a divergence reset)
+  int qv_in_smem, hq, hv; // optionally qpos/qvel live in the hot region (offsets hq, hv) instead of aux
   int act, ctrl, actdot; // nu each
   int g_axis, g_anchor;  // 3*MAXFD each
   int g_box;             // 12 per moving box
@@ -76,11 +77,13 @@ struct Layout2 {
 enum { M2_NCON = 0, M2_STATUS = 1, M2_TOUCH = 2, M2_NCONTOT = 3, M2_ITERS = 4, M2_NCAND = 5, M2_TMAX = 6, M2_NLIM = 7 };
 
 template <typename T>
-inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw) {
+inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw, int qv_in_smem = 0) {
   Layout2 L{};
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };   // keep every array 16-byte aligned (float4 loads)
   L.a = take(D.nv + 1); L.row2 = take(2 * (D.nrow + 1)); L.minv = take(16 * MAXCHAIN); L.hlim = take(4 * MAXFD);
+  L.qv_in_smem = qv_in_smem;
+  if (qv_in_smem) { L.hq = take(D.nv); L.hv = take(D.nv); }
   L.hotT = o;
   L.h_misc = 0; L.hotI = 8;
   o = 0;
@@ -102,10 +105,10 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw
   size_t sb = hot + (aux_in_smem ? aux : 0);
   sb = (sb + 15) & ~(size_t)15;
   // skew consecutive worlds of a warp by 32/wpw banks so that the same offset in different groups hits different banks
-  if (wpw > 1) { const size_t want = (size_t)(128 / wpw) < 16 ? 16 : (size_t)(128 / wpw); while (sb % 128 != want % 128) sb += 16; }
+  if (wpw > 1) { const size_t unit = (size_t)(128 / wpw) < 16 ? 16 : (size_t)(128 / wpw); while ((sb / unit) % 2 == 0 || sb % unit) sb += 16; }
   L.smem_stride = (int)sb;
   L.gs_stride = aux_in_smem ? 0 : (int)((aux + 127) & ~(size_t)127);
-  L.smem_tables = (int)(((size_t)D.nstep * lpw * (8 + 2 * sizeof(T)) + 127) & ~(size_t)127);
+  L.smem_tables = (int)(((size_t)(D.nstep + 1) * lpw * (8 + 2 * sizeof(T)) + 3 * (size_t)D.ns * sizeof(T) + 127) & ~(size_t)127);
   return L;
 }
 
@@ -268,13 +271,20 @@ struct World2 {
 
   const int2* sdesc;     // CTA-shared step tables of the level sweep (shared memory), already offset to this lane
   const T* siw;
+  const T *stc, *stciw;   // CTA-shared copies of the tendon coefficients and coefficient / mass
+  const T* stim;          // CTA-shared 1 / slider mass
+  __device__ __forceinline__ T stiw(int e) const { return stim[e]; }
 
   __device__ World2(const KArgs2<T>& k, unsigned char* smem, int wid, bool ok)
       : K(k), D(k.D), C(k.C), L(k.L), w(wid), valid(ok) {
     lane = threadIdx.x & 31; grp = lane / LPW; sl = lane % LPW; gshift = grp * LPW;
     const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     sdesc = reinterpret_cast<const int2*>(smem) + sl;
-    siw = reinterpret_cast<const T*>(smem + (size_t)D.nstep * LPW * 8) + 2 * sl;
+    const T* tw = reinterpret_cast<const T*>(smem + (size_t)(D.nstep + 1) * LPW * 8);
+    siw = tw + 2 * sl;
+    stc = tw + 2 * (D.nstep + 1) * LPW;
+    stciw = stc + D.ns;
+    stim = stciw + D.ns;
     unsigned char* base = smem + L.smem_tables + (size_t)(warp * WPW + grp) * L.smem_stride;
     hot = reinterpret_cast<T*>(base);
     hoti = reinterpret_cast<int*>(hot + L.hotT);
@@ -285,8 +295,8 @@ struct World2 {
 
   __device__ __forceinline__ const T* tab(int o) const { return K.tab + o; }
   __device__ __forceinline__ const int* itab(int o) const { return K.itab + o; }
-  __device__ __forceinline__ T* q() { return aux + L.q; }
-  __device__ __forceinline__ T* v() { return aux + L.v; }
+  __device__ __forceinline__ T* q() { return L.qv_in_smem ? hot + L.hq : aux + L.q; }
+  __device__ __forceinline__ T* v() { return L.qv_in_smem ? hot + L.hv : aux + L.v; }
   __device__ __forceinline__ T* a() { return hot + L.a; }
   __device__ __forceinline__ T* qs() { return aux + L.qs; }
   __device__ __forceinline__ int& misc(int i) { return hoti[L.h_misc + i]; }
@@ -562,9 +572,9 @@ struct World2 {
   // ------------------------------------------------------------------------------------------
   // collision + contact rows
   // ------------------------------------------------------------------------------------------
-  __device__ __forceinline__ void capsule_center(int e, T* c) {
-    const T* c0 = tab(D.o_sl_cap0) + 3 * e; const T* ax = tab(D.o_sl_axis) + 3 * e;
-    const T qe = q()[D.nfd + e];
+  __device__ __forceinline__ void capsule_center(int e, T* c, const T* __restrict__ qsl) {
+    const T* __restrict__ c0 = tab(D.o_sl_cap0) + 3 * e; const T* __restrict__ ax = tab(D.o_sl_axis) + 3 * e;
+    const T qe = qsl[e];
 #pragma unroll
     for (int k = 0; k < 3; k++) c[k] = off[k] + c0[k] + ax[k] * qe;
   }
@@ -679,6 +689,7 @@ struct World2 {
 
   __device__ void collide() {
     const bool dbg = valid && (w == K.debug_world);
+    const T* __restrict__ qsl = q() + D.nfd;     // slider positions are read-only during collision
     // ---- broadphase: bounding spheres, candidates compacted in pair order ----
     int ncand = 0, flags = 0;
     for (int base = 0; base < D.npair; base += LPW) {
@@ -688,7 +699,7 @@ struct World2 {
         const int pt = itab(D.io_pair_t)[p], pa = itab(D.io_pair_a)[p], pb = itab(D.io_pair_b)[p];
         const T* co = tab(D.o_coll + pa * CO_STRIDE);
         T c2[3], rb2;
-        if (pt == PAIR_PLANE_CAPSULE || pt == PAIR_BOX_CAPSULE) { capsule_center(pb, c2); rb2 = C.cap_r + C.cap_hl; }
+        if (pt == PAIR_PLANE_CAPSULE || pt == PAIR_BOX_CAPSULE) { capsule_center(pb, c2, qsl); rb2 = C.cap_r + C.cap_hl; }
         else if (pt == PAIR_SPHERE_BOX) {
 #pragma unroll
           for (int k = 0; k < 3; k++) c2[k] = off[k] + C.sph_pos[k];
@@ -732,11 +743,11 @@ struct World2 {
         T size1[3] = {co[CO_SIZE], co[CO_SIZE + 1], co[CO_SIZE + 2]};
         int mask = (int)co[CO_MASK];
         if (pt == PAIR_PLANE_CAPSULE) {
-          T cc[3]; capsule_center(pb, cc);
+          T cc[3]; capsule_center(pb, cc, qsl);
           n = plane_capsule(rc, c1, rot1, cc, tab(D.o_sl_axis) + 3 * pb, C.cap_r, C.cap_hl);
           e = pb; ssign = 1; mask |= C.cap_mask;
         } else if (pt == PAIR_BOX_CAPSULE) {
-          T cc[3]; capsule_center(pb, cc);
+          T cc[3]; capsule_center(pb, cc, qsl);
           n = capsule_box(rc, cc, tab(D.o_sl_axis) + 3 * pb, C.cap_r, C.cap_hl, c1, rot1, size1);
           e = pb; ssign = -1; mask |= C.cap_mask;
         } else if (pt == PAIR_SPHERE_BOX) {
@@ -825,30 +836,37 @@ struct World2 {
     const int nfd = D.nfd, ns = D.ns;
     const bool dbg = valid && (w == K.debug_world) && K.debug_out;
     // volume tendon: L = sum c_e q_e, Ldot = sum c_e v_e
+    const T* __restrict__ qp = q() + nfd;     // qpos / qvel of the sliders are read-only in this stage
+    const T* __restrict__ vp = v() + nfd;
     T Ls = 0, Lv = 0, As = 0;
+#pragma unroll 4
     for (int e = sl; e < ns; e += LPW) {
-      const T tc = tab(D.o_sl_tc)[e];
-      Ls += tc * q()[nfd + e]; Lv += tc * v()[nfd + e]; As += tc * tc / tab(D.o_sl_m)[e];
+      const T tc = stc[e];
+      Ls += tc * qp[e]; Lv += tc * vp[e]; As += tc * stciw[e];
     }
     Ls = gsum(Ls); Lv = gsum(Lv); As = gsum(As);
     const T Ft = -ten_stiffness() * (Ls - C.ten_lspring) - ten_damping() * Lv;
     Ft_out = Ft;
-    // sliders: qfrc_smooth = passive - bias  (bias = -m axis.g for a slider on a static parent)
+    // sliders: qacc_smooth = (passive - bias) / m  (bias = -m axis.g for a slider on a static parent)
+    T* __restrict__ qsp = qs() + nfd;
+#pragma unroll 2
     for (int e = sl; e < ns; e += LPW) {
-      const T qe = q()[nfd + e], ve = v()[nfd + e], m = tab(D.o_sl_m)[e];
-      const T* ax = tab(D.o_sl_axis) + 3 * e;
+      const T qe = qp[e], ve = vp[e], m = tab(D.o_sl_m)[e];
+      const T* __restrict__ ax = tab(D.o_sl_axis) + 3 * e;
       T f = -stiffness(e) * qe - damping(e) * ve;
-      f += tab(D.o_sl_tc)[e] * Ft;
+      f += stc[e] * Ft;
       f -= -(m * (ax[0] * C.g[0] + ax[1] * C.g[1] + ax[2] * C.g[2]));
-      qs()[nfd + e] = f;
+      qsp[e] = f * stiw(e);
     }
     // joint-equality rows in schedule order: row2 = (aref, R) until the warm start turns aref into u
-    const int* rd = itab(D.io_row_d12);
-    T* row2 = hot + L.row2;
+    const int* __restrict__ rd = itab(D.io_row_d12);
+    const T* __restrict__ siwt = tab(D.o_sl_iw);
+    T* __restrict__ row2 = hot + L.row2;
+#pragma unroll 4
     for (int p = sl; p < D.nrow; p += LPW) {
       const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
-      T pos = q()[nfd + d1], vel = v()[nfd + d1], diag = tab(D.o_sl_iw)[d1];
-      if (d2 != 0xffff) { pos -= q()[nfd + d2]; vel -= v()[nfd + d2]; diag += tab(D.o_sl_iw)[d2]; }
+      T pos = qp[d1], vel = vp[d1], diag = siwt[d1];
+      if (d2 != 0xffff) { pos -= qp[d2]; vel -= vp[d2]; diag += siwt[d2]; }
       const T imp = impedance2<T>(C.eqj_si, pos);
       const T aref = -C.eqj_B * vel - C.eqj_K * imp * pos;
       row2[2 * p] = aref;
@@ -919,12 +937,13 @@ struct World2 {
     const int* rd = itab(D.io_row_d12);
     T* row2 = hot + L.row2;
     T* jtf = aux + L.jtf;
+    // dual cost = sum_rows (0.5 R f^2 - f aref) + (J^T f).qacc_smooth + 0.5 (J^T f)' M^-1 (J^T f): the middle term is
+    // sum_rows f (J qacc_smooth) regrouped per dof, so no row ever has to gather qacc_smooth
     T cost = 0;
     // equality rows: per-dof gather of J^T f over the rows of each slider (no scatter, no atomics)
-    T tja = 0, tjs = 0;
+    T tja = 0;
     for (int e = sl; e < ns; e += LPW) {
       const int* dr = itab(D.io_dof_rows) + e * MAXDOFROWS;
-      const T iwe = T(1) / tab(D.o_sl_m)[e];
       T s = 0;
 #pragma unroll
       for (int k = 0; k < MAXDOFROWS; k++) {
@@ -932,23 +951,22 @@ struct World2 {
         if (code >= 0) {
           const int p = code >> 1;
           const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
-          T ja = a()[nfd + d1], js = qs()[nfd + d1] / tab(D.o_sl_m)[d1];
-          if (d2 != 0xffff) { ja -= a()[nfd + d2]; js -= qs()[nfd + d2] / tab(D.o_sl_m)[d2]; }
-          const T ar = row2[2 * p], R = row2[2 * p + 1];
+          T ja = a()[nfd + d1];
+          if (d2 != 0xffff) ja -= a()[nfd + d2];
+          T ar, R; ld2(row2 + 2 * p, ar, R);
           const T f = -(T(1) / R) * (ja - ar);
           if (code & 1) s -= f;
-          else { s += f; cost += f * (js - ar) + T(0.5) * R * f * f; }   // the row's own cost: counted once, by its first dof
+          else { s += f; cost += f * (T(0.5) * R * f - ar); }   // the row's own cost: counted once, by its first dof
         }
       }
-      const T tc = tab(D.o_sl_tc)[e];
-      tja += tc * a()[nfd + e]; tjs += tc * qs()[nfd + e] * iwe;
+      tja += stc[e] * a()[nfd + e];
       jtf[nfd + e] = s;
     }
-    tja = gsum(tja); tjs = gsum(tjs);
+    tja = gsum(tja);
     const T tf = -(T(1) / tn.R) * (tja - tn.aref);
-    if (sl == 0) cost += tf * (tjs - tn.aref) + T(0.5) * tn.R * tf * tf;
-    for (int e = sl; e < ns; e += LPW) jtf[nfd + e] += tab(D.o_sl_tc)[e] * tf;
-    // limits (registers of the chain lanes)
+    if (sl == 0) cost += tf * (T(0.5) * tn.R * tf - tn.aref);
+    for (int e = sl; e < ns; e += LPW) jtf[nfd + e] += stc[e] * tf;
+    // limits (the chain lanes)
     if (sl < D.nchain) {
       const int d0 = D.chain_dof0[sl];
 #pragma unroll
@@ -960,7 +978,7 @@ struct World2 {
         const T f = jar >= T(0) ? T(0) : -(T(1) / R) * jar;
         lf(d0 + jl) = f;
         jtf[d0 + jl] = sgn * f;
-        cost += f * (sgn * qs()[d0 + jl] - ar) + T(0.5) * R * f * f;
+        cost += f * (T(0.5) * R * f - ar);
       }
     }
     // contacts
@@ -969,19 +987,19 @@ struct World2 {
       const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
       T* r = crec(i);
       const T R0 = r[CR_R0], R1 = r[CR_R1];
-      T jar[3], b[3];
+      T jar[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        T sa = 0, sb = 0;
-        if (e >= 0) { sa = r[CR_NS + k] * a()[nfd + e]; sb = r[CR_NS + k] * (qs()[nfd + e] / tab(D.o_sl_m)[e]); }
-        if (c >= 0) for (int jj = 0; jj < D.ncd[c]; jj++) { sa += r[CR_JG + 4 * k + jj] * a()[D.chain_dof0[c] + jj]; sb += r[CR_JG + 4 * k + jj] * qs()[D.chain_dof0[c] + jj]; }
-        jar[k] = sa - r[CR_AREF + k]; b[k] = sb - r[CR_AREF + k];
+        T sa = 0;
+        if (e >= 0) sa = r[CR_NS + k] * a()[nfd + e];
+        if (c >= 0) for (int jj = 0; jj < D.ncd[c]; jj++) sa += r[CR_JG + 4 * k + jj] * a()[D.chain_dof0[c] + jj];
+        jar[k] = sa - r[CR_AREF + k];
       }
       T f[3];
       cone_force(jar, R0, R1, f);
       const T Rr[3] = {R0, R1, R1};
 #pragma unroll
-      for (int k = 0; k < 3; k++) { r[CR_F + k] = f[k]; cost += f[k] * b[k] + T(0.5) * Rr[k] * f[k] * f[k]; }
+      for (int k = 0; k < 3; k++) { r[CR_F + k] = f[k]; cost += f[k] * (T(0.5) * Rr[k] * f[k] - r[CR_AREF + k]); }
     }
     __syncwarp();
     // J^T f of the contacts, added after the limits: serial in row order on one lane (deterministic)
@@ -999,13 +1017,13 @@ struct World2 {
       }
     }
     __syncwarp();
-    // 0.5 f' J M^-1 J' f = 0.5 jtf . (M^-1 jtf)
-    for (int e = sl; e < ns; e += LPW) { const T x = jtf[nfd + e]; cost += T(0.5) * x * x / tab(D.o_sl_m)[e]; }
+    // (J^T f).qacc_smooth + 0.5 (J^T f)' M^-1 (J^T f)
+    for (int e = sl; e < ns; e += LPW) { const T x = jtf[nfd + e]; cost += x * (qs()[nfd + e] + T(0.5) * x * stiw(e)); }
     for (int dof = sl; dof < nfd; dof += LPW) {
       const int c = chain_of(dof), jl = dof - D.chain_dof0[c];
       T s = 0;
       for (int jj = 0; jj < D.ncd[c]; jj++) s += hot[L.minv + 16 * c + 4 * jl + jj] * jtf[D.chain_dof0[c] + jj];
-      cost += T(0.5) * jtf[dof] * s;
+      cost += jtf[dof] * (qs()[dof] + T(0.5) * s);
     }
     cost = gsum(cost);
     const bool keep = !(cost > T(0));
@@ -1030,10 +1048,7 @@ struct World2 {
     }
     __syncwarp();
     // a = qacc_smooth + M^-1 jtf (or qacc_smooth alone)
-    for (int e = sl; e < ns; e += LPW) {
-      const T iw = T(1) / tab(D.o_sl_m)[e];
-      a()[nfd + e] = qs()[nfd + e] * iw + (keep ? jtf[nfd + e] * iw : T(0));
-    }
+    for (int e = sl; e < ns; e += LPW) a()[nfd + e] = qs()[nfd + e] + (keep ? jtf[nfd + e] * stiw(e) : T(0));
     for (int dof = sl; dof < nfd; dof += LPW) {
       const int c = chain_of(dof), jl = dof - D.chain_dof0[c];
       T s = 0;
@@ -1137,8 +1152,6 @@ struct World2 {
     // that pad a level and rows with a single slider point at the dummy slider / dummy row, so the loop body has
     // no predication at all.
     const int nstep = D.nstep;
-    const T* tcv = tab(D.o_sl_tc);
-    const T* tciw = tab(D.o_sl_tciw);
     T* av = a() + nfd;
     T* row2 = hot + L.row2;
     const int tmaxw = wmax(misc(M2_TMAX));
@@ -1178,9 +1191,8 @@ struct World2 {
         T iw1n, iw2n; ld2(siw, iw1n, iw2n);
         for (int st = 0; st < nstep; st++) {
           const int2 dc = dn; const T iw1 = iw1n, iw2 = iw2n;
-          const int nx = st + 1 < nstep ? st + 1 : st;
-          dn = sdesc[nx * LPW];
-          ld2(siw + 2 * nx * LPW, iw1n, iw2n);
+          dn = sdesc[(st + 1) * LPW];            // the table carries one dummy step past the end
+          ld2(siw + 2 * (st + 1) * LPW, iw1n, iw2n);
           const int d1 = dc.x & 0xffff, d2 = (dc.x >> 16) & 0xffff, p = dc.y & 0x3fffffff;
           T a1 = av[d1], a2 = av[d2];
           T u, R; ld2(row2 + 2 * p, u, R);
@@ -1197,13 +1209,13 @@ struct World2 {
       // ---- volume-tendon row: dense over the shell, sub-warp shuffle reduction ----
       {
         T s = 0;
-        for (int e = sl; e < ns; e += LPW) s += __ldg(tcv + e) * av[e];
+        for (int e = sl; e < ns; e += LPW) s += stc[e] * av[e];
         s = gsum(s);
         const T res = s + tn.u;
         const T dl = done ? T(0) : -res * trcp<T>(tn.A);
         if (sl == 0) impr -= T(0.5) * dl * res;
         tn.u += tn.R * dl;
-        for (int e = sl; e < ns; e += LPW) av[e] += __ldg(tciw + e) * dl;
+        for (int e = sl; e < ns; e += LPW) av[e] += stciw[e] * dl;
         __syncwarp();
       }
       // ---- joint limits, then the elliptic contact blocks of this lane in their time slots ----
@@ -1297,11 +1309,16 @@ struct World2 {
   // mj_Euler with implicit joint damping: (M + h diag(d)) qacc' = qfrc_smooth + J^T f = M qacc
   __device__ void euler() {
     const int nfd = D.nfd; const T h = C.h;
-    for (int e = sl; e < D.ns; e += LPW) {
-      const T m = tab(D.o_sl_m)[e];
-      const T qa = m * a()[nfd + e] / (m + h * damping(e));
-      const T vn = v()[nfd + e] + h * qa;
-      v()[nfd + e] = vn; q()[nfd + e] += h * vn;
+    {
+      T* __restrict__ qp = q() + nfd; T* __restrict__ vp = v() + nfd;
+      const T* __restrict__ ap = a() + nfd;
+#pragma unroll 4
+      for (int e = sl; e < D.ns; e += LPW) {
+        const T m = tab(D.o_sl_m)[e];
+        const T qa = m * ap[e] / (m + h * damping(e));
+        const T vn = vp[e] + h * qa;
+        vp[e] = vn; qp[e] += h * vn;
+      }
     }
     for (int i = sl; i < nfd; i += LPW) { const T vn = v()[i] + h * a()[i]; v()[i] = vn; q()[i] += h * vn; }
     if (sl < D.nu) aux[L.act + sl] += h * aux[L.actdot + sl];
@@ -1407,9 +1424,11 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
   {
     // stage the step tables: int2 descriptors, then the (1/m, 1/m) pairs
     int* sd = reinterpret_cast<int*>(smem_raw);
-    T* sw = reinterpret_cast<T*>(smem_raw + (size_t)D.nstep * LPW * 8);
-    const int n2 = 2 * D.nstep * LPW;
+    T* sw = reinterpret_cast<T*>(smem_raw + (size_t)(D.nstep + 1) * LPW * 8);
+    const int n2 = 2 * (D.nstep + 1) * LPW;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) { sd[i] = K.itab[D.io_step_d + i]; sw[i] = K.tab[D.o_step_iw + i]; }
+    T* tc = sw + n2;
+    for (int i = threadIdx.x; i < D.ns; i += blockDim.x) { tc[i] = K.tab[D.o_sl_tc + i]; tc[D.ns + i] = K.tab[D.o_sl_tciw + i]; tc[2 * D.ns + i] = T(1) / K.tab[D.o_sl_m + i]; }
     __syncthreads();
   }
   const int cta_worlds = nwarp * WPW;

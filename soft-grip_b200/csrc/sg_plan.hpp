@@ -167,6 +167,8 @@ inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab,
       }
     }
   }
+  // one dummy step past the end: the sweep prefetches the next step's descriptors unconditionally
+  for (int k = 0; k < lpw; k++) { step_d.push_back(dummy_d | (dummy_d << 16)); step_d.push_back(dummy_p); step_iw.push_back(0.0); step_iw.push_back(0.0); }
 }
 
 inline bool same(const double* a, const double* b, int n) { for (int i = 0; i < n; i++) if (a[i] != b[i]) return false; return true; }

@@ -115,8 +115,8 @@ def test_emulated_multi_warp_cta_and_persistent_batches(emu, batched):
     W = 21
     ks = 300.0 + 50.0 * np.arange(W)
     out = []
-    for nw, lpw in ((1, 8), (4, 8), (2, 16)):
-        env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=lpw, nw=nw)
+    for nw, lpw, qv in ((1, 8, 0), (4, 8, 1), (2, 16, 0)):
+        env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=lpw, nw=nw, qv_smem=qv)
         env.set_params(stiffness=ks)
         traj, touch, st = env.rollout(sched, want_touch=False)
         assert (st == 0).all() and np.isfinite(traj).all()

@@ -226,7 +226,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="softgrip", choices=["softgrip", "reference"])
     ap.add_argument("--model", default="softbox")
-    ap.add_argument("--worlds-per-gpu", type=int, default=8192)
+    ap.add_argument("--worlds-per-gpu", type=int, default=18944)   # 2 x (148 SMs x 64 resident worlds)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-episodes-per-core", type=int, default=24)
     ap.add_argument("--ref-episodes-per-core", type=int, default=1)
@@ -342,7 +342,7 @@ def main():
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback 6650 GB/s",
-                "kernel": "sg_step_kernel<float> (rollout mode)", "algorithmic_bytes_per_world_episode": bytes_per_world,
+                "kernel": "sg_step_kernel2<float, 8> (rollout mode)", "algorithmic_bytes_per_world_episode": bytes_per_world,
                 "note": "latency/issue-bound Gauss-Seidel kernel: state stays in shared memory for the whole episode, so the HBM fraction is tiny by design"}
 
     cpu = None

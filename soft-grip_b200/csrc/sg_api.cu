@@ -39,7 +39,7 @@ struct sg_batch {
 #endif
   int kernel = 2;             // 2: sub-warp worlds (sg_kernels2.cuh); 1: one warp per world (sg_kernels.cuh)
   int lpw = 8;                // lanes per world of kernel 2
-  int nwarp = 8;              // warps per CTA of kernel 2
+  int nwarp = 16;             // warps per CTA of kernel 2
   size_t smem2 = 0;           // dynamic shared memory per CTA of kernel 2
   Layout2 L2;
   unsigned char* scratch = nullptr;   // global aux slots of kernel 2 (when aux is not in shared memory)
@@ -173,7 +173,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   // kernel selection (environment overrides are development knobs; the defaults are the measured best)
-  b->kernel = 2; b->lpw = 8;
+  b->kernel = 2; b->lpw = 8; b->nwarp = 16;
   int aux_in_smem = 0;
   if (const char* e = std::getenv("SOFTGRIP_KERNEL")) b->kernel = std::atoi(e);
   if (const char* e = std::getenv("SOFTGRIP_LPW")) b->lpw = std::atoi(e);

@@ -53,6 +53,24 @@ def main():
     rows = list(csv.reader(io.StringIO(out)))
     # the page is a sequence of per-file tables: ["File Name", path], header row ["Line No", "Source", ...], lines
     per, samp, text, stalls = {}, {}, {}, {}
+    # the combined cuda,sass view does not name the file of a line: resolve it by matching the line's text
+    import os
+    srcdir0 = os.path.dirname(src_file) if src_file else None
+    file_lines = {}
+    if srcdir0:
+        for f in os.listdir(srcdir0):
+            if f.endswith((".cuh", ".cu", ".hpp")):
+                file_lines[f] = open(os.path.join(srcdir0, f)).read().split("\n")
+
+    def resolve_file(ln, txt):
+        t = txt.strip()
+        main = os.path.basename(src_file) if src_file else None
+        if main and ln <= len(file_lines.get(main, [])) and file_lines[main][ln - 1].strip() == t:
+            return main
+        for f, lines in file_lines.items():
+            if ln <= len(lines) and lines[ln - 1].strip() == t:
+                return f
+        return "?"
     cur_file, hdr = "?", None
     STALL = ["stall_long_sb", "stall_no_inst", "stall_wait", "stall_short_sb", "stall_barrier", "stall_branch_resolving", "stall_mio", "stall_math", "stall_not_selected", "stall_selected", "stall_lg", "stall_dispatch"]
     for r in rows:
@@ -68,7 +86,7 @@ def main():
             ln = int(r[0]); inst = int(r[hdr.index("Instructions Executed")])
         except ValueError:
             continue
-        key = (cur_file, ln)
+        key = (resolve_file(ln, r[1]), ln)
         per[key] = per.get(key, 0) + inst
         try:
             samp[key] = samp.get(key, 0) + int(r[hdr.index("# Samples")])

@@ -40,6 +40,7 @@ struct sg_batch {
   int kernel = 2;             // 2: sub-warp worlds (sg_kernels2.cuh); 1: one warp per world (sg_kernels.cuh)
   int lpw = 8;                // lanes per world of kernel 2
   int nwarp = 16;             // warps per CTA of kernel 2
+  int team = 1;               // kernel 2: one warp sweeps the limit/contact rows of 16 worlds
   size_t smem2 = 0;           // dynamic shared memory per CTA of kernel 2
   Layout2 L2;
   unsigned char* scratch = nullptr;   // global aux slots of kernel 2 (when aux is not in shared memory)
@@ -223,6 +224,8 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       if (b->smem2 <= prop.sharedMemPerBlockOptin || b->nwarp == 1) break;
       b->nwarp /= 2;
     }
+    b->team = (b->nwarp % (b->lpw / 2) == 0) ? 1 : 0;
+    if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) == 0) b->team = 0; }
     if (b->smem2 > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: worlds of one warp do not fit in shared memory (use more lanes per world or SOFTGRIP_AUX_SMEM=0)"); }
     int e = k2_dispatch_configure(precision, b->lpw, 32 * b->nwarp, b->smem2, &per_sm);
     if (e == -12345) { delete b; return fail("SOFTGRIP_LPW: this lanes-per-world value is not compiled in"); }
@@ -391,6 +394,7 @@ static int launch_v2(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
   K.D.cap_mask = b->model->plan.d.cap_mask; K.D.sph_mask = b->model->plan.d.sph_mask;
   K.C = make_cst<T>(K.D);
   K.tab = (const T*)b->tab; K.itab = b->itab; K.nworlds = b->W;
+  K.team = b->team;
   K.scratch = b->scratch;
   K.qpos = (T*)b->qpos; K.qvel = (T*)b->qvel; K.warm = (T*)b->warm; K.act = (T*)b->act; K.ctrl = (T*)b->ctrl;
   K.p_stiff = b->has_stiff ? b->p_stiff : nullptr; K.p_damp = b->has_damp ? b->p_damp : nullptr;

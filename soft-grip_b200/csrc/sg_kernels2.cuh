@@ -49,6 +49,7 @@ struct Layout2 {
   int row2;              // 2*(nrow+1) : (u, R) per equality row, schedule order; the last pair is the dummy row (0, 1)
   int minv;              // 16*MAXCHAIN
   int hlim;              // 4*MAXFD : f, aref, R, sign per finger dof (meaningful where the limit is active)
+  int h_impr;            // 1 (+pad): cost improvement of the limit/contact rows of the current sweep (team mode)
   int hotT;
   int h_misc;            // 8 ints
   int hotI;
@@ -74,18 +75,19 @@ struct Layout2 {
   int gs_stride;         // bytes per world in the global scratch (0 when aux_in_smem)
 };
 
-enum { M2_NCON = 0, M2_STATUS = 1, M2_TOUCH = 2, M2_NCONTOT = 3, M2_ITERS = 4, M2_NCAND = 5, M2_TMAX = 6, M2_NLIM = 7 };
+enum { M2_NCON = 0, M2_STATUS = 1, M2_TOUCH = 2, M2_NCONTOT = 3, M2_ITERS = 4, M2_NCAND = 5, M2_TMAX = 6, M2_NLIM = 7, M2_DONE = 8,
+       M2_LMASK = 9 /* MAXCHAIN entries */ };
 
 template <typename T>
 inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw, int qv_in_smem = 0) {
   Layout2 L{};
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };   // keep every array 16-byte aligned (float4 loads)
-  L.a = take(D.nv + 1); L.row2 = take(2 * (D.nrow + 1)); L.minv = take(16 * MAXCHAIN); L.hlim = take(4 * MAXFD);
+  L.a = take(D.nv + 1); L.row2 = take(2 * (D.nrow + 1)); L.minv = take(16 * MAXCHAIN); L.hlim = take(4 * MAXFD); L.h_impr = take(4);
   L.qv_in_smem = qv_in_smem;
   if (qv_in_smem) { L.hq = take(D.nv); L.hv = take(D.nv); }
   L.hotT = o;
-  L.h_misc = 0; L.hotI = 8;
+  L.h_misc = 0; L.hotI = 16;
   o = 0;
   L.q = take(D.nv); L.v = take(D.nv); L.qs = take(D.nv); L.jtf = take(D.nv); L.a0 = take(D.nv);
   const int nu = D.nu > 0 ? D.nu : 1;
@@ -153,6 +155,7 @@ struct KArgs2 {
   const T* tab;
   const int* itab;
   int nworlds;
+  int team;                    // 1: the limit/contact rows of 16 worlds are swept by one warp (see World2::pgs)
   unsigned char* scratch;      // global aux slots [gridDim.x * WPW][L.gs_stride] (null when aux_in_smem)
   // state, world-major
   T *qpos, *qvel, *warm, *act, *ctrl;
@@ -269,16 +272,20 @@ struct World2 {
   bool valid;
   T kw, dw, tdw, off[3];
 
+  unsigned char* smem_base;
   const int2* sdesc;     // CTA-shared step tables of the level sweep (shared memory), already offset to this lane
   const T* siw;
   const T *stc, *stciw;   // CTA-shared copies of the tendon coefficients and coefficient / mass
   const T* stim;          // CTA-shared 1 / slider mass
   __device__ __forceinline__ T stiw(int e) const { return stim[e]; }
 
-  __device__ World2(const KArgs2<T>& k, unsigned char* smem, int wid, bool ok)
+  // vwarp / vnwarp: position of this warp's worlds in the CTA in units of WPW worlds (the real warp index, except
+  // for the 2-lanes-per-world view that one warp of a team takes of the team's 16 worlds)
+  __device__ World2(const KArgs2<T>& k, unsigned char* smem, int wid, bool ok, int vwarp = -1, int vnwarp = -1)
       : K(k), D(k.D), C(k.C), L(k.L), w(wid), valid(ok) {
     lane = threadIdx.x & 31; grp = lane / LPW; sl = lane % LPW; gshift = grp * LPW;
-    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int warp = vwarp >= 0 ? vwarp : (int)(threadIdx.x >> 5), nwarp = vnwarp >= 0 ? vnwarp : (int)(blockDim.x >> 5);
+    smem_base = smem;
     sdesc = reinterpret_cast<const int2*>(smem) + sl;
     const T* tw = reinterpret_cast<const T*>(smem + (size_t)(D.nstep + 1) * LPW * 8);
     siw = tw + 2 * sl;
@@ -791,7 +798,8 @@ struct World2 {
     // latest earlier block on the same lane or on the same slider -- exactly the dependencies of the
     // sequential sweep of mj_solPGS, so the result equals the sequential one. ----
     int* lastt = auxi + L.i_cand;     // per-slider latest time slot (the candidate list is dead by now)
-    constexpr int NFREE = LPW > MAXCHAIN ? LPW - MAXCHAIN : 0;
+    const int clpw = K.team ? 2 : LPW;                            // lanes that sweep this world's limit/contact rows
+    const int nfree = clpw > MAXCHAIN ? clpw - MAXCHAIN : 0;
     for (int i = sl; i < ncon; i += LPW) { const int e = (auxi[L.i_con + i] >> 4) - 1; if (e >= 0) lastt[e] = 0; }
     __syncwarp();
     int* lanet = auxi + L.i_order;    // per-lane latest time slot (the order list is built later, in pgs())
@@ -803,8 +811,8 @@ struct World2 {
         const int ce = auxi[L.i_con + i];
         const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
         int ln;
-        if (c >= 0) ln = c % LPW;
-        else { ln = NFREE > 0 ? MAXCHAIN + (nstat % (NFREE > 0 ? NFREE : 1)) : nstat % LPW; nstat++; }
+        if (c >= 0) ln = c % clpw;
+        else { ln = nfree > 0 ? MAXCHAIN + (nstat % nfree) : nstat % clpw; nstat++; }
         int t = lanet[ln];
         if (e >= 0) { const int te = lastt[e]; if (te > t) t = te; }
         t += 1;
@@ -906,6 +914,7 @@ struct World2 {
       lsgn(d0 + jl) = sgn;
       cr.lmask |= 1 << jl;
     }
+    misc(M2_LMASK + c) = cr.lmask;
   }
 
   __device__ __forceinline__ int chain_of(int dof) const {
@@ -1059,7 +1068,7 @@ struct World2 {
   }
 
   // one elliptic contact block (mj_solPGS inner body, dim 3) on the lane that owns its chain
-  __device__ __forceinline__ T contact_block(int i, ChainRows& cr, bool has_chain, const T* mv) {
+  __device__ __forceinline__ T contact_block(int i, T* ag, bool has_chain, const T* mv) {
     const int nfd = D.nfd;
     T* r = crec(i);
     T jg[12], w1[4], w2[4], w3[4];
@@ -1082,7 +1091,7 @@ struct World2 {
       T s = w1[k] * ae;
       if (has_chain) {
 #pragma unroll
-        for (int jj = 0; jj < MAXCD; jj++) s += jg[4 * k + jj] * cr.ag[jj];
+        for (int jj = 0; jj < MAXCD; jj++) s += jg[4 * k + jj] * ag[jj];
       }
       res[k] = s - w2[k] + Rr[k] * fo[k];
     }
@@ -1136,128 +1145,199 @@ struct World2 {
 #pragma unroll
         for (int ii = 0; ii < MAXCD; ii++) {
           T m4[4]; ld4(mv + 4 * ii, m4);
-          cr.ag[ii] += m4[0] * gv[0] + m4[1] * gv[1] + m4[2] * gv[2] + m4[3] * gv[3];
+          ag[ii] += m4[0] * gv[0] + m4[1] * gv[1] + m4[2] * gv[2] + m4[3] * gv[3];
         }
       }
     }
     return change;
   }
 
-  // projected Gauss-Seidel (mj_solPGS) in MuJoCo's row order
-  __device__ void pgs(Tendon& tn, ChainRows& cr) {
-    const int nfd = D.nfd, ns = D.ns;
-    // step descriptors of the level sweep (built per lanes-per-world by the host, staged in shared memory by the
-    // kernel prologue and shared by all worlds of the CTA): slot = step * LPW + lane.
-    // {first slider | second slider << 16, row | last-step-of-level << 30} and {1/m first, 1/m second}.  Slots
-    // that pad a level and rows with a single slider point at the dummy slider / dummy row, so the loop body has
-    // no predication at all.
-    const int nstep = D.nstep;
-    T* av = a() + nfd;
-    T* row2 = hot + L.row2;
-    const int tmaxw = wmax(misc(M2_TMAX));
-    const bool chain_lane = sl < D.nchain;
-    const T* mv = hot + L.minv + 16 * (chain_lane ? sl : 0);
-    // this lane's slice of the contact schedule
-    int mystart = 0, mycnt = 0;
-    {
-      const int ncon = misc(M2_NCON);
-      for (int i = 0; i < ncon; i++) {
-        const int ln = auxi[L.i_tl + i] >> 16;
-        if (ln < sl) mystart++;
-        else if (ln == sl) mycnt++;
-      }
-      int k = 0;
-      for (int i = 0; i < ncon; i++) {
-        const int tl = auxi[L.i_tl + i];
-        if ((tl >> 16) == sl) { auxi[L.i_order + mystart + k] = i | ((tl & 0xffff) << 16); k++; }
-      }
+  // ---- limit / contact rows: swept by the lane that owns the finger chain (plus a share of the static contacts) ----
+  struct ChainState {
+    T ag[MAXCD];            // running qacc of the chain dofs, in registers for the whole solve
+    const T* mv;            // the chain's M^-1 block (shared memory)
+    int lmask, mystart, mycnt;
+    bool chain_lane;
+  };
+  // this lane's slice of the contact schedule (contacts in their sequential order) and the chain's qacc
+  __device__ void chain_prologue(ChainState& cs) {
+    cs.chain_lane = sl < D.nchain;
+    cs.mv = hot + L.minv + 16 * (cs.chain_lane ? sl : 0);
+    cs.lmask = cs.chain_lane ? misc(M2_LMASK + sl) : 0;
+    cs.mystart = 0; cs.mycnt = 0;
+    const int ncon = misc(M2_NCON);
+    for (int i = 0; i < ncon; i++) {
+      const int ln = auxi[L.i_tl + i] >> 16;
+      if (ln < sl) cs.mystart++;
+      else if (ln == sl) cs.mycnt++;
     }
-    if (chain_lane) {
-      const int d0 = D.chain_dof0[sl];
+    int k = 0;
+    for (int i = 0; i < ncon; i++) {
+      const int tl = auxi[L.i_tl + i];
+      if ((tl >> 16) == sl) { auxi[L.i_order + cs.mystart + k] = i | ((tl & 0xffff) << 16); k++; }
+    }
 #pragma unroll
-      for (int jj = 0; jj < MAXCD; jj++) cr.ag[jj] = jj < D.ncd[sl] ? a()[d0 + jj] : T(0);
+    for (int jj = 0; jj < MAXCD; jj++) cs.ag[jj] = (cs.chain_lane && jj < D.ncd[sl]) ? a()[D.chain_dof0[sl] + jj] : T(0);
+  }
+  // one sweep over this lane's limit rows and contact blocks (time slots 1..tmaxw, a warp barrier after each);
+  // returns the lane's cost improvement
+  __device__ T chain_phase(ChainState& cs, int tmaxw, bool done) {
+    T impr = 0;
+    if (cs.chain_lane && !done) {
+#pragma unroll
+      for (int jl = 0; jl < MAXCD; jl++) {
+        if (!(cs.lmask & (1 << jl))) continue;
+        const int dof = D.chain_dof0[sl] + jl;
+        const T sgn = lsgn(dof), f = lf(dof), R = lR(dof);
+        const T A = cs.mv[4 * jl + jl] + R;
+        const T res = sgn * cs.ag[jl] - laref(dof) + R * f;
+        T fn = f - tdiv(res, A);
+        if (fn < T(0)) fn = 0;
+        T dl = fn - f;
+        T change = T(0.5) * dl * dl * A + dl * res;
+        if (change > T(1e-10)) { fn = f; dl = 0; change = 0; }
+        impr -= change;
+        lf(dof) = fn;
+        if (dl != T(0)) {
+#pragma unroll
+          for (int ii = 0; ii < MAXCD; ii++) cs.ag[ii] += cs.mv[4 * ii + jl] * sgn * dl;
+        }
+      }
     }
-    __syncwarp();
+    int k = 0;
+    for (int t = 1; t <= tmaxw; t++) {
+      if (!done && k < cs.mycnt) {
+        const int ent = auxi[L.i_order + cs.mystart + k];
+        if ((ent >> 16) == t) {
+          if (k + 1 < cs.mycnt && !L.aux_in_smem) prefetch_l1(crec(auxi[L.i_order + cs.mystart + k + 1] & 0xffff));
+          impr -= contact_block(ent & 0xffff, cs.ag, cs.chain_lane, cs.mv); k++;
+        }
+      }
+      __syncwarp();
+    }
+    return impr;
+  }
+  __device__ void chain_epilogue(const ChainState& cs) {
+    if (cs.chain_lane) {
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) if (jj < D.ncd[sl]) a()[D.chain_dof0[sl] + jj] = cs.ag[jj];
+    }
+  }
+
+  // one sweep over the equality block and the volume-tendon row; returns this lane's cost improvement.
+  // Step descriptors (built per lanes-per-world by the host, staged in shared memory by the kernel prologue and
+  // shared by all worlds of the CTA): slot = step * LPW + lane, {first slider | second slider << 16, row |
+  // last-step-of-level << 30} and {1/m first, 1/m second}.  Slots that pad a level and rows with a single slider point
+  // at the dummy slider / dummy row, so the loop body has no predication at all.
+  __device__ __forceinline__ T equality_sweep(Tendon& tn, bool done) {
+    const int ns = D.ns, nstep = D.nstep;
+    T* av = a() + D.nfd;
+    T* row2 = hot + L.row2;
+    T impr = 0;
+    // one row per lane per step, a warp barrier where a dependency level ends.  The next step's descriptor is fetched
+    // before the barrier so that its latency overlaps this step's arithmetic.
+    {
+      const T gate = done ? T(0) : T(1);
+      int2 dn = sdesc[0];
+      T iw1n, iw2n; ld2(siw, iw1n, iw2n);
+      for (int st = 0; st < nstep; st++) {
+        const int2 dc = dn; const T iw1 = iw1n, iw2 = iw2n;
+        dn = sdesc[(st + 1) * LPW];            // the table carries one dummy step past the end
+        ld2(siw + 2 * (st + 1) * LPW, iw1n, iw2n);
+        const int d1 = dc.x & 0xffff, d2 = (dc.x >> 16) & 0xffff, p = dc.y & 0x3fffffff;
+        T a1 = av[d1], a2 = av[d2];
+        T u, R; ld2(row2 + 2 * p, u, R);
+        const T res = (a1 - a2) + u;
+        const T dl = -res * trcp<T>(iw1 + iw2 + R) * gate;
+        impr -= T(0.5) * dl * res;
+        u += R * dl; a1 += iw1 * dl; a2 -= iw2 * dl;
+        row2[2 * p] = u;
+        av[d1] = a1;
+        av[d2] = a2;
+        if (dc.y >> 30) __syncwarp();
+      }
+    }
+    // volume-tendon row: dense over the shell, sub-warp shuffle reduction
+    {
+      T s = 0;
+      for (int e = sl; e < ns; e += LPW) s += stc[e] * av[e];
+      s = gsum(s);
+      const T res = s + tn.u;
+      const T dl = done ? T(0) : -res * trcp<T>(tn.A);
+      if (sl == 0) impr -= T(0.5) * dl * res;
+      tn.u += tn.R * dl;
+      for (int e = sl; e < ns; e += LPW) av[e] += stciw[e] * dl;
+      __syncwarp();
+    }
+    return impr;
+  }
+
+  __device__ __forceinline__ void team_sync(int id, int nthreads) {
+#ifdef SG_SIMT_EMU
+    simt_named_barrier(id, nthreads);
+#elif defined(__CUDA_ARCH__)
+    // immediate barrier ids (1..8): a register id would make ptxas reserve all 16 hardware barriers for the CTA
+    switch (id) {
+      case 1: asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); break;
+      case 2: asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); break;
+      case 3: asm volatile("bar.sync 3, %0;" ::"r"(nthreads) : "memory"); break;
+      case 4: asm volatile("bar.sync 4, %0;" ::"r"(nthreads) : "memory"); break;
+      case 5: asm volatile("bar.sync 5, %0;" ::"r"(nthreads) : "memory"); break;
+      case 6: asm volatile("bar.sync 6, %0;" ::"r"(nthreads) : "memory"); break;
+      case 7: asm volatile("bar.sync 7, %0;" ::"r"(nthreads) : "memory"); break;
+      default: asm volatile("bar.sync 8, %0;" ::"r"(nthreads) : "memory"); break;
+    }
+#else
+    (void)id; (void)nthreads;
+#endif
+  }
+
+  // projected Gauss-Seidel (mj_solPGS) in MuJoCo's row order.
+  // Team mode (K.team): the LPW/2 warps that hold 16 consecutive worlds form a team.  Every warp sweeps the equality
+  // block of its own worlds with LPW lanes per world; the limit and contact rows -- serial per finger chain, so they
+  // keep at most two lanes of a world busy -- are swept for all 16 worlds at once by the team's first warp through a
+  // 2-lanes-per-world view of the same shared memory (32 chains = 32 lanes), between two team barriers per sweep.
+  __device__ void pgs(Tendon& tn, unsigned char* smem) {
     int iter = 0;
     bool done = false;
-    for (int it = 0; it < D.iters; it++) {
-      if (!__any_sync(FULLMASK, !done)) break;
-      T impr = 0;
-      // ---- equality block: one row per lane per step, a warp barrier where a dependency level ends.  The next
-      // step's descriptor is fetched before the barrier so that its latency overlaps this step's arithmetic. ----
-      {
-        const T gate = done ? T(0) : T(1);
-        int2 dn = sdesc[0];
-        T iw1n, iw2n; ld2(siw, iw1n, iw2n);
-        for (int st = 0; st < nstep; st++) {
-          const int2 dc = dn; const T iw1 = iw1n, iw2 = iw2n;
-          dn = sdesc[(st + 1) * LPW];            // the table carries one dummy step past the end
-          ld2(siw + 2 * (st + 1) * LPW, iw1n, iw2n);
-          const int d1 = dc.x & 0xffff, d2 = (dc.x >> 16) & 0xffff, p = dc.y & 0x3fffffff;
-          T a1 = av[d1], a2 = av[d2];
-          T u, R; ld2(row2 + 2 * p, u, R);
-          const T res = (a1 - a2) + u;
-          const T dl = -res * trcp<T>(iw1 + iw2 + R) * gate;
-          impr -= T(0.5) * dl * res;
-          u += R * dl; a1 += iw1 * dl; a2 -= iw2 * dl;
-          row2[2 * p] = u;
-          av[d1] = a1;
-          av[d2] = a2;
-          if (dc.y >> 30) __syncwarp();
+    if (!K.team) {
+      ChainState cs;
+      chain_prologue(cs);
+      const int tmaxw = wmax(misc(M2_TMAX));
+      __syncwarp();
+      for (int it = 0; it < D.iters; it++) {
+        if (!__any_sync(FULLMASK, !done)) break;
+        T impr = equality_sweep(tn, done);
+        impr += chain_phase(cs, tmaxw, done);
+        impr = gsum(impr) * C.impr_scale;
+        if (!done) { iter++; if (impr < C.tol) done = true; }
+      }
+      chain_epilogue(cs);
+    } else {
+      constexpr int TEAMW = LPW / 2 > 0 ? LPW / 2 : 1;       // warps per team (16 worlds)
+      const int warp = threadIdx.x >> 5, team = warp / TEAMW, wit = warp % TEAMW;
+      const int bar_id = 1 + team, nthr = 32 * TEAMW;
+      World2<T, 2> V(K, smem, 0, false, team, (int)(blockDim.x >> 5) / TEAMW);
+      typename World2<T, 2>::ChainState cs;
+      int tmaxw = 0;
+      if (sl == 0) misc(M2_DONE) = 0;
+      team_sync(bar_id, nthr);                               // warm-start results of all 16 worlds are in place
+      if (wit == 0) { V.chain_prologue(cs); tmaxw = V.wmax(V.misc(M2_TMAX)); }
+      for (int it = 0; it < D.iters; it++) {
+        T impr = equality_sweep(tn, done);
+        team_sync(bar_id, nthr);
+        if (wit == 0) {
+          T ic = V.chain_phase(cs, tmaxw, V.misc(M2_DONE) != 0);
+          ic = V.gsum(ic);
+          if (V.sl == 0) V.hot[L.h_impr] = ic;
         }
+        team_sync(bar_id, nthr);
+        impr = (gsum(impr) + hot[L.h_impr]) * C.impr_scale;
+        if (!done) { iter++; if (impr < C.tol) done = true; }
+        if (sl == 0) misc(M2_DONE) = done ? 1 : 0;
       }
-      // ---- volume-tendon row: dense over the shell, sub-warp shuffle reduction ----
-      {
-        T s = 0;
-        for (int e = sl; e < ns; e += LPW) s += stc[e] * av[e];
-        s = gsum(s);
-        const T res = s + tn.u;
-        const T dl = done ? T(0) : -res * trcp<T>(tn.A);
-        if (sl == 0) impr -= T(0.5) * dl * res;
-        tn.u += tn.R * dl;
-        for (int e = sl; e < ns; e += LPW) av[e] += stciw[e] * dl;
-        __syncwarp();
-      }
-      // ---- joint limits, then the elliptic contact blocks of this lane in their time slots ----
-      if (chain_lane && !done) {
-#pragma unroll
-        for (int jl = 0; jl < MAXCD; jl++) {
-          if (!(cr.lmask & (1 << jl))) continue;
-          const int dof = D.chain_dof0[sl] + jl;
-          const T sgn = lsgn(dof), f = lf(dof), R = lR(dof);
-          const T A = mv[4 * jl + jl] + R;
-          const T res = sgn * cr.ag[jl] - laref(dof) + R * f;
-          T fn = f - tdiv(res, A);
-          if (fn < T(0)) fn = 0;
-          T dl = fn - f;
-          T change = T(0.5) * dl * dl * A + dl * res;
-          if (change > T(1e-10)) { fn = f; dl = 0; change = 0; }
-          impr -= change;
-          lf(dof) = fn;
-          if (dl != T(0)) {
-#pragma unroll
-            for (int ii = 0; ii < MAXCD; ii++) cr.ag[ii] += mv[4 * ii + jl] * sgn * dl;
-          }
-        }
-      }
-      int k = 0;
-      for (int t = 1; t <= tmaxw; t++) {
-        if (!done && k < mycnt) {
-          const int ent = auxi[L.i_order + mystart + k];
-          if ((ent >> 16) == t) {
-            if (k + 1 < mycnt && !L.aux_in_smem) prefetch_l1(crec(auxi[L.i_order + mystart + k + 1] & 0xffff));
-            impr -= contact_block(ent & 0xffff, cr, chain_lane, mv); k++;
-          }
-        }
-        __syncwarp();
-      }
-      impr = gsum(impr) * C.impr_scale;
-      if (!done) { iter++; if (impr < C.tol) done = true; }
-    }
-    if (chain_lane) {
-      const int d0 = D.chain_dof0[sl];
-#pragma unroll
-      for (int jj = 0; jj < MAXCD; jj++) if (jj < D.ncd[sl]) a()[d0 + jj] = cr.ag[jj];
+      if (wit == 0) V.chain_epilogue(cs);
+      team_sync(bar_id, nthr);
     }
     if (sl == 0) misc(M2_ITERS) = iter;
     __syncwarp();
@@ -1274,7 +1354,7 @@ struct World2 {
     rows_and_smooth(tn, Ft);
     if (sl < D.nchain) chain_limits(sl, cr); else cr.lmask = 0;
     warmstart(tn, cr);
-    pgs(tn, cr);
+    pgs(tn, smem_base);
     // accelerometers (mj_sensorAcc): R_site^T (Jv qacc + bias - g)
     for (int s = sl; s < D.nsens; s += LPW) {
       const T* se = tab(D.o_sens + s * SE_STRIDE);
@@ -1291,9 +1371,8 @@ struct World2 {
         for (int k = 0; k < 3; k++) aux[L.sens + adr + k] = o[k];
       }
     }
-    if (sl < D.nchain) auxi[L.i_lmask + sl] = cr.lmask;
     {
-      int s = (sl < D.nchain) ? __popc((unsigned)cr.lmask) : 0;
+      int s = (sl < D.nchain) ? __popc((unsigned)misc(M2_LMASK + sl)) : 0;
 #pragma unroll
       for (int o = LPW / 2; o > 0; o >>= 1) s += __shfl_xor_sync(FULLMASK, s, o);
       if (sl == 0) misc(M2_NLIM) = s;
@@ -1340,7 +1419,8 @@ struct World2 {
     }
     for (int pass = 0; pass < 2; pass++) {
       const bool bad = forward();
-      if (!integrate || !__any_sync(FULLMASK, bad)) break;
+      // CTA-uniform decision: forward() contains team barriers, so all warps of the CTA repeat it together
+      if (!integrate || !cta_any(bad)) break;
       // mj_step re-runs mj_forward after mj_resetData.  forward() is full of warp collectives, so the other
       // groups of the warp re-run it too, from their saved warm start: they recompute identical values.
       if (bad && sl == 0) misc(M2_STATUS) |= 1;
@@ -1348,6 +1428,10 @@ struct World2 {
       reset_if(bad);
     }
     if (integrate) euler();
+  }
+  __device__ __forceinline__ bool cta_any(bool p) const {
+    if (blockDim.x > 32) return __syncthreads_or(p ? 1 : 0) != 0;
+    return __any_sync(FULLMASK, p) != 0;
   }
   __device__ void reset_if(bool doit) {
     if (doit) {
@@ -1382,7 +1466,7 @@ struct World2 {
       o[eb + r] = ((double)tn.u + (double)tn.aref) / (double)tn.R; o[eb + nefc + r] = (double)tn.aref; o[eb + 2 * nefc + r] = (double)tn.R; r++;
       for (int c = 0; c < D.nchain; c++)
         for (int jl = 0; jl < D.ncd[c]; jl++)
-          if (auxi[L.i_lmask + c] & (1 << jl)) {
+          if (misc(M2_LMASK + c) & (1 << jl)) {
             const int dof = D.chain_dof0[c] + jl;
             o[eb + r] = (double)lf(dof); o[eb + nefc + r] = (double)laref(dof); o[eb + 2 * nefc + r] = (double)lR(dof); r++;
           }

@@ -29,6 +29,7 @@ struct WarpState {
   int site[2][32];
   int gen = 0;
   bool finished = false, at_cta_barrier = false;
+  int named_id = -1, named_warps = 0;     // waiting at bar.sync id, nthreads (a subset of the CTA's warps)
 };
 constexpr int MAX_WARPS = 32;
 struct CtaState {
@@ -43,7 +44,7 @@ struct CtaState {
 };
 inline CtaState CTA;
 constexpr size_t STACK_BYTES = 512 * 1024;
-enum { SITE_SYNCWARP = 1, SITE_SYNCTHREADS = 2 };
+enum { SITE_SYNCWARP = 1, SITE_SYNCTHREADS = 2, SITE_NAMED = 1000 };
 
 inline void fiber_main() {
   CTA.entry(CTA.arg);
@@ -84,13 +85,14 @@ inline void run_round(int wi) {
       abort();
     }
   if (W.site[g][0] == SITE_SYNCTHREADS) W.at_cta_barrier = true;
+  if (W.site[g][0] >= SITE_NAMED) { W.named_id = W.site[g][0] - SITE_NAMED; W.named_warps = (int)W.slot[g][0]; }
   W.gen++;
 }
 
 inline void run_cta() {
   for (int wi = 0; wi < CTA.nwarps; wi++) {
     WarpState& W = CTA.warp[wi];
-    W.gen = 0; W.finished = false; W.at_cta_barrier = false;
+    W.gen = 0; W.finished = false; W.at_cta_barrier = false; W.named_id = -1;
     for (int l = 0; l < 32; l++) {
       if (!W.stack[l]) W.stack[l] = (char*)malloc(STACK_BYTES);
       getcontext(&W.ctx[l]);
@@ -107,14 +109,28 @@ inline void run_cta() {
       WarpState& W = CTA.warp[wi];
       if (W.finished) { nfin++; continue; }
       if (W.at_cta_barrier) { nbar++; continue; }
+      if (W.named_id >= 0) continue;
       run_round(wi);
       if (W.finished) nfin++;
       else if (W.at_cta_barrier) nbar++;
     }
     if (nfin == CTA.nwarps) break;
+    // named barriers: release an id once the expected number of warps waits on it
+    int nnamed = 0;
+    for (int id = 0; id < 16; id++) {
+      int cnt = 0, want = 0;
+      for (int wi = 0; wi < CTA.nwarps; wi++) if (CTA.warp[wi].named_id == id) { cnt++; want = CTA.warp[wi].named_warps; }
+      if (cnt && cnt == want) { for (int wi = 0; wi < CTA.nwarps; wi++) if (CTA.warp[wi].named_id == id) CTA.warp[wi].named_id = -1; }
+      else nnamed += cnt;
+      if (cnt > want && want) { fprintf(stderr, "simt: %d warps at named barrier %d that expects %d\n", cnt, id, want); abort(); }
+    }
     if (nbar > 0 && nbar + nfin == CTA.nwarps) {
       if (nfin) { fprintf(stderr, "simt: __syncthreads with %d exited warps\n", nfin); abort(); }
       for (int wi = 0; wi < CTA.nwarps; wi++) CTA.warp[wi].at_cta_barrier = false;
+    } else {
+      int runnable = 0;
+      for (int wi = 0; wi < CTA.nwarps; wi++) if (!CTA.warp[wi].finished && !CTA.warp[wi].at_cta_barrier && CTA.warp[wi].named_id < 0) runnable++;
+      if (!runnable) { fprintf(stderr, "simt: barrier deadlock (named-waiting %d, cta-waiting %d, finished %d)\n", nnamed, nbar, nfin); abort(); }
     }
   }
 }
@@ -159,6 +175,18 @@ using simt::threadIdx;
 
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::rendezvous(0, simt::SITE_SYNCWARP); }
 inline void __syncthreads() { simt::rendezvous(0, simt::SITE_SYNCTHREADS); }
+inline int __syncthreads_or(int p) {
+  static int acc = 0;
+  if (p) acc = 1;
+  __syncthreads();
+  const int r = acc;
+  __syncthreads();
+  acc = 0;
+  __syncthreads();
+  return r;
+}
+// bar.sync id, nthreads: a barrier over nthreads/32 whole warps of the CTA
+inline void simt_named_barrier(int id, int nthreads) { simt::rendezvous((unsigned long long)(nthreads / 32), simt::SITE_NAMED + id); }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int o) {
   const int lane = simt::cur_lane(), g = simt::rendezvous(simt::to_bits(v), 3);
   return simt::from_bits<T>(simt::cur_warp().slot[g & 1][(lane ^ o) & 31]);

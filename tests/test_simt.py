@@ -60,6 +60,27 @@ def test_emulated_single_step_parity_against_golden_states(emu, states, prec, lp
     env.close()
 
 
+@pytest.mark.parametrize("lpw,nw", [(8, 4), (4, 2), (16, 8)])
+def test_emulated_team_mode_parity(emu, states, lpw, nw):
+    """Team mode: the limit/contact rows of 16 worlds are swept by one warp through a 2-lanes-per-world view, between
+    named barriers.  Same parity bar as the per-warp path, on contact-rich golden states."""
+    W = 19                                  # one full team of 16 worlds + a ragged second team
+    env = emu.EmuBatch(blob_path("softbox"), W, prec=64, lpw=lpw, nw=nw, team=1)
+    env.set_params(stiffness=np.full(W, 700.0))
+    env.set_debug_world(17)
+    for i in (4, 6, 7, 9, 11):
+        env.set_state(states["q"][i], states["v"][i], states["act"][i], states["warm"][i])
+        env.set_ctrl([states["ctrl"][i]] * 2)
+        sens, touch = env.step(1)
+        q1, v1, a1, qacc = env.get_state()
+        assert int(env.debug("ncon")[0]) == states["ncon1"][i] and int(env.debug("solver_iter")[0]) == states["iter1"][i]
+        for w in (0, 5, 15, 16, 18):
+            assert rel(q1[w], states["q1"][i]) < 1e-9 and rel(v1[w], states["v1"][i]) < 1e-9 and rel(qacc[w], states["qacc1"][i]) < 1e-9
+            assert rel(sens[w], states["sens1"][i]) < 1e-9
+        assert (env.status() == 0).all()
+    env.close()
+
+
 def test_emulated_stage_diagnostics_match_oracle(emu, states, make_world):
     i = list(states["step"]).index(850)
     env = emu.EmuBatch(blob_path("softbox"), 2, prec=64, lpw=8)
@@ -115,21 +136,23 @@ def test_emulated_multi_warp_cta_and_persistent_batches(emu, batched):
     W = 21
     ks = 300.0 + 50.0 * np.arange(W)
     out = []
-    for nw, lpw, qv in ((1, 8, 0), (4, 8, 1), (2, 16, 0)):
-        env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=lpw, nw=nw, qv_smem=qv)
+    for nw, lpw, qv, team in ((1, 8, 0, 0), (4, 8, 1, 1), (2, 16, 0, 0), (8, 8, 0, 1)):
+        env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=lpw, nw=nw, qv_smem=qv, team=team)
         env.set_params(stiffness=ks)
         traj, touch, st = env.rollout(sched, want_touch=False)
         assert (st == 0).all() and np.isfinite(traj).all()
         out.append(traj)
         env.close()
     np.testing.assert_array_equal(out[0], out[1])
+    np.testing.assert_array_equal(out[0], out[3])
     assert np.abs(out[0] - out[2]).max() / np.abs(out[0]).max() < 1e-4      # other lane count: other summation order
 
 
-def test_emulated_divergence_is_contained_in_its_group(emu):
-    """A diverging world is reset and flagged; the other worlds of the same warp are bit-identical to a clean run."""
-    W = 4
-    env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=8)
+@pytest.mark.parametrize("W,nw", [(4, None), (18, 4)])
+def test_emulated_divergence_is_contained_in_its_group(emu, W, nw):
+    """A diverging world is reset and flagged; the other worlds of the same warp / team / CTA are bit-identical to a
+    clean run (the re-run of mj_forward after the reset is taken by the whole CTA)."""
+    env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=8, nw=nw)
     q = np.zeros((W, 118)); q[1, 30] = 1e11
     z = np.zeros((W, 118))
     env.set_state(q, z, np.zeros((W, 2)), z)
@@ -138,11 +161,11 @@ def test_emulated_divergence_is_contained_in_its_group(emu):
     assert st[1] & 1 and st[0] == 0 and st[2] == 0 and st[3] == 0
     g = env.get_state()
     assert np.abs(g[0][1]).max() < 1e-3
-    ref = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=8)
+    ref = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=8, nw=nw)
     ref.set_state(z, z, np.zeros((W, 2)), z)
     ref.step(2)
     r = ref.get_state()
-    for w in (0, 2, 3):
+    for w in (0, 2, 3, W - 1):
         np.testing.assert_array_equal(g[0][w], r[0][w])
         np.testing.assert_array_equal(g[3][w], r[3][w])
     # acceleration blow-up inside the step (huge velocity): the reset + re-run path
@@ -155,7 +178,7 @@ def test_emulated_divergence_is_contained_in_its_group(emu):
     ref.set_state(z, z, np.zeros((W, 2)), z)
     ref.step(1)
     r = ref.get_state()
-    for w in (0, 1, 3):
+    for w in (0, 1, 3, W - 1):
         np.testing.assert_array_equal(g[0][w], r[0][w])
         np.testing.assert_array_equal(g[3][w], r[3][w])
     env.close(); ref.close()

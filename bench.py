@@ -358,7 +358,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, Wg),
             "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": Wg * 8, "d2h_bytes_per_step": Wg * (T * env.nsd * 4 + 4)},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
-            "worlds_diverged": int(ndiv), "worlds_capacity_or_unsupported": int(nfull), "trajectory_finite": finite}
+            "launch_geometry": env.config(), "worlds_diverged": int(ndiv), "worlds_capacity_or_unsupported": int(nfull), "trajectory_finite": finite}
     if pgs_flops:
         fp32_peak = 148 * 128 * 2 * (line["clocks"]["sm_mhz"] or 1965.0) * 1e6 / 1e12
         line["fp32_pipe"] = {"pgs_flops_per_world_step_last": pgs_flops, "achieved_tflops": value / world * pgs_flops / 1e12,

@@ -11,7 +11,7 @@ W = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 rows = int(sys.argv[3]) if len(sys.argv) > 3 else 60
 cfgs = sys.argv[4:] or ["k1:l32:a1", "k2:l8:a0", "k2:l4:a0", "k2:l16:a0", "k2:l32:a0", "k2:l32:a1", "k2:l16:a1"]
 blob = os.path.join(ROOT, "tests", "golden", name + ".sgm")
-ev, val = batched.default_schedule(2, n_settle=10, n_iter=rows - 10, open_close_div=(rows - 10) // 2)
+ev, val = batched.default_schedule(2) if rows == 200 else batched.default_schedule(2, n_settle=10, n_iter=rows - 10, open_close_div=(rows - 10) // 2)
 dm = batched.DeviceModel(blob)
 ref = None
 for cfg in cfgs:
@@ -19,6 +19,7 @@ for cfg in cfgs:
     k, l, a = parts.get("k", 2), parts.get("l", 8), parts.get("a", 0)
     os.environ["SOFTGRIP_KERNEL"] = str(k); os.environ["SOFTGRIP_LPW"] = str(l); os.environ["SOFTGRIP_AUX_SMEM"] = str(a)
     os.environ["SOFTGRIP_QV_SMEM"] = str(parts.get("q", 0))
+    os.environ["SOFTGRIP_TEAM"] = str(parts.get("t", 1))
     if "n" in parts: os.environ["SOFTGRIP_NW"] = str(parts["n"])
     else: os.environ.pop("SOFTGRIP_NW", None)
     for dt in (torch.float32,):

@@ -57,6 +57,7 @@ SIGNATURES = {
     "sg_batch_set_debug_world": (C.c_int, [P, C.c_int]),
     "sg_batch_debug_get": (C.c_int, [P, C.c_char_p, D, C.c_int]),
     "sg_batch_launch_count": (C.c_longlong, [P]),
+    "sg_batch_config": (C.c_int, [P, I]),
 }
 
 

@@ -305,6 +305,13 @@ class BatchedManEnv:
     def set_debug_world(self, world):
         check(self.L.sg_batch_set_debug_world(self.h, int(world)))
 
+    def config(self):
+        """How the worlds were packed onto the SMs (sg_batch_config)."""
+        out = (C.c_int * 8)()
+        check(self.L.sg_batch_config(self.h, out))
+        keys = ("lanes_per_world", "warps_per_cta", "worlds_per_cta", "ctas_per_sm", "smem_per_cta", "smem_per_world", "team_mode", "kernel")
+        return dict(zip(keys, [int(x) for x in out]))
+
     def launch_count(self):
         return int(self.L.sg_batch_launch_count(self.h))
 

@@ -57,7 +57,7 @@ struct sg_batch {
   void* stage_traj = nullptr; size_t stage_traj_bytes = 0;   // device staging for rollout_host
   int* stage_touch = nullptr; size_t stage_touch_bytes = 0;
   long long launches = 0;
-  int max_ctas = 0;
+  int max_ctas = 0, per_sm = 0;
 };
 
 extern "C" const char* sg_last_error(void) { return g_err.c_str(); }
@@ -222,7 +222,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       b->L2 = precision == 32 ? make_layout2<float>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem) : make_layout2<double>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem);
       b->smem2 = (size_t)b->L2.smem_tables + (size_t)b->L2.smem_stride * wpw * b->nwarp;
       if (b->smem2 <= prop.sharedMemPerBlockOptin || b->nwarp == 1) break;
-      b->nwarp /= 2;
+      b->nwarp -= 1;                       // largest CTA that fits
     }
     b->team = (b->nwarp % (b->lpw / 2) == 0) ? 1 : 0;
     if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) == 0) b->team = 0; }
@@ -231,7 +231,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
     if (e == -12345) { delete b; return fail("SOFTGRIP_LPW: this lanes-per-world value is not compiled in"); }
     if (e) { delete b; return fail(std::string("kernel configuration failed: ") + cudaGetErrorString((cudaError_t)e)); }
     if (per_sm < 1) per_sm = 1;
-    b->max_ctas = per_sm * prop.multiProcessorCount;
+    b->max_ctas = per_sm * prop.multiProcessorCount; b->per_sm = per_sm;
     const int cta_worlds = wpw * b->nwarp;
     int need = (nworlds + cta_worlds - 1) / cta_worlds;
     int slots = need < b->max_ctas ? need : b->max_ctas;
@@ -255,7 +255,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_step_kernel<double>, 32, b->L.bytes));
     }
     if (per_sm < 1) per_sm = 1;
-    b->max_ctas = per_sm * prop.multiProcessorCount;
+    b->max_ctas = per_sm * prop.multiProcessorCount; b->per_sm = per_sm;
   }
 #endif
   *out = b;
@@ -274,6 +274,14 @@ extern "C" void sg_batch_destroy(sg_batch* b) {
 extern "C" int sg_batch_nworlds(const sg_batch* b) { return b ? b->W : -1; }
 extern "C" int sg_batch_precision(const sg_batch* b) { return b ? b->precision : -1; }
 extern "C" long long sg_batch_launch_count(const sg_batch* b) { return b ? b->launches : -1; }
+extern "C" int sg_batch_config(const sg_batch* b, int* out) {
+  if (!b || !out) return fail("sg_batch_config: null argument");
+  const int wpw = 32 / b->lpw;
+  out[0] = b->kernel == 2 ? b->lpw : 32; out[1] = b->kernel == 2 ? b->nwarp : 1; out[2] = b->kernel == 2 ? wpw * b->nwarp : 1;
+  out[3] = b->per_sm; out[4] = b->kernel == 2 ? (int)b->smem2 : 0; out[5] = b->kernel == 2 ? b->L2.smem_stride : 0;
+  out[6] = b->kernel == 2 ? b->team : 0; out[7] = b->kernel;
+  return 0;
+}
 
 extern "C" int sg_batch_set_params(sg_batch* b, const double* stiffness, const double* damping, const double* tdamping,
                                    const double* objoff, void* stream) {

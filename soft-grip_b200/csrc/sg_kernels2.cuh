@@ -83,11 +83,17 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw
   Layout2 L{};
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };   // keep every array 16-byte aligned (float4 loads)
-  L.a = take(D.nv + 1); L.row2 = take(2 * (D.nrow + 1)); L.minv = take(16 * MAXCHAIN); L.hlim = take(4 * MAXFD); L.h_impr = take(4);
+  auto pack = [&](int n) { int r = o; o += n; return r; };               // scalar-access arrays: no padding (shared memory is the
+                                                                         // occupancy limit, every 16 bytes per world count)
+  L.minv = take(16 * MAXCHAIN);          // 4-vector loads
+  L.row2 = pack(2 * (D.nrow + 1));       // 2-vector loads (even offset)
+  L.a = pack(D.nv + 1); L.hlim = pack(4 * MAXFD); L.h_impr = pack(1);
   L.qv_in_smem = qv_in_smem;
-  if (qv_in_smem) { L.hq = take(D.nv); L.hv = take(D.nv); }
+  if (qv_in_smem) { L.hq = pack(D.nv); L.hv = pack(D.nv); }
+  o = (o + 1) & ~1;                      // the int block (and a double-precision aux block) stays 8-byte aligned
   L.hotT = o;
-  L.h_misc = 0; L.hotI = 16;
+  L.h_misc = 0; L.hotI = 12;
+  while ((sizeof(T) * (size_t)L.hotT + 4 * (size_t)L.hotI) % 16) L.hotI++;   // what follows (aux in shared memory) is 16-byte aligned
   o = 0;
   L.q = take(D.nv); L.v = take(D.nv); L.qs = take(D.nv); L.jtf = take(D.nv); L.a0 = take(D.nv);
   const int nu = D.nu > 0 ? D.nu : 1;

@@ -133,6 +133,12 @@ int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int cap);
  * No reference counterpart: it only documents how the worlds were packed onto the SMs (bench.py reports it). */
 int sg_batch_config(const sg_batch* b, int* out);
 
+/* development aid, no reference counterpart: SM-clock cycles per phase of the step kernel, summed over the warps of
+ * all launches since the last call (out[n], n <= 16: gripper, collide, rows, warm start, solver set-up, equality
+ * sweeps, limit/contact sweeps, sensors, Euler, other).  Only for batches created with SOFTGRIP_PROF=1 in the
+ * environment; otherwise an error.  Returns the number of phases. */
+int sg_batch_prof_get(sg_batch* b, unsigned long long* out, int n);
+
 /* number of kernel launches issued by this batch since creation (bench.py's gpu_launches) */
 long long sg_batch_launch_count(const sg_batch* b);
 

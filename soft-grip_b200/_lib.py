@@ -58,6 +58,7 @@ SIGNATURES = {
     "sg_batch_debug_get": (C.c_int, [P, C.c_char_p, D, C.c_int]),
     "sg_batch_launch_count": (C.c_longlong, [P]),
     "sg_batch_config": (C.c_int, [P, I]),
+    "sg_batch_prof_get": (C.c_int, [P, C.POINTER(C.c_ulonglong), C.c_int]),
 }
 
 

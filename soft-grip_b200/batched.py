@@ -312,6 +312,14 @@ class BatchedManEnv:
         keys = ("lanes_per_world", "warps_per_cta", "worlds_per_cta", "ctas_per_sm", "smem_per_cta", "smem_per_world", "team_mode", "kernel")
         return dict(zip(keys, [int(x) for x in out]))
 
+    PHASES = ("gripper", "collide", "rows", "warmstart", "pgs_setup", "pgs_equality", "pgs_chain", "sensors", "euler", "other")
+
+    def phase_cycles(self):
+        """Development aid (SOFTGRIP_PROF=1 at creation): SM cycles per phase of the step kernel, summed over warps."""
+        out = (C.c_ulonglong * 16)()
+        check(self.L.sg_batch_prof_get(self.h, out, 16))
+        return dict(zip(self.PHASES, [int(x) for x in out]))
+
     def launch_count(self):
         return int(self.L.sg_batch_launch_count(self.h))
 

@@ -40,7 +40,7 @@ struct sg_batch {
   int kernel = 2;             // 2: sub-warp worlds (sg_kernels2.cuh); 1: one warp per world (sg_kernels.cuh)
   int lpw = 8;                // lanes per world of kernel 2
   int nwarp = 16;             // warps per CTA of kernel 2
-  int team = 1;               // kernel 2: one warp sweeps the limit/contact rows of 16 worlds
+  int team = 0;               // kernel 2: one warp sweeps the limit/contact rows of 16 worlds (opt-in: measured slower, profiles/r01b_*)
   size_t smem2 = 0;           // dynamic shared memory per CTA of kernel 2
   Layout2 L2;
   unsigned char* scratch = nullptr;   // global aux slots of kernel 2 (when aux is not in shared memory)
@@ -57,6 +57,7 @@ struct sg_batch {
   void* stage_traj = nullptr; size_t stage_traj_bytes = 0;   // device staging for rollout_host
   int* stage_touch = nullptr; size_t stage_touch_bytes = 0;
   long long launches = 0;
+  unsigned long long* prof = nullptr; size_t prof_n = 0;   // SOFTGRIP_PROF=1: phase clocks of kernel 2 (development aid)
   int max_ctas = 0, per_sm = 0;
 };
 
@@ -190,7 +191,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   if (b->lpw != 4 && b->lpw != 8 && b->lpw != 16 && b->lpw != 32) { delete b; return fail("SOFTGRIP_LPW must be 4, 8, 16 or 32"); }
   if (b->kernel == 2) {
     const Plan& P = m->plan;
-    build_step_tables(b->D, P.tab, P.itab, b->lpw, b->step_d, b->step_iw);
+    build_step_tables(b->D, P.tab, P.itab, b->lpw, b->esize, b->step_d, b->step_iw);
     b->D.nstep = (int)(b->step_d.size() / (2 * (size_t)b->lpw)) - 1;   // without the trailing dummy step
     b->D.o_step_iw = (int)((P.tab.size() + 3) / 4 * 4);
     b->D.io_step_d = (int)((P.itab.size() + 3) / 4 * 4);
@@ -208,7 +209,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   CUDA_OK(cudaMalloc((void**)&b->p_damp, sizeof(double) * nworlds));
   CUDA_OK(cudaMalloc((void**)&b->p_tdamp, sizeof(double) * nworlds));
   CUDA_OK(cudaMalloc((void**)&b->p_objoff, sizeof(double) * 3 * nworlds));
-  b->debug_cap = 64 + 16 * 2 * b->D.maxcon + b->D.nv + 3 * (b->D.nrow + 1 + MAXFD + 3 * b->D.maxcon) + 64 + (b->D.nrow + 1);
+  b->debug_cap = 64 + 16 * 2 * b->D.maxcon + b->D.nv + 3 * (b->D.nrow + 1 + MAXFD + 3 * b->D.maxcon) + 64 + 2 * (b->D.nrow + 1);
   CUDA_OK(cudaMalloc((void**)&b->debug_out, sizeof(double) * b->debug_cap));
   CUDA_OK(cudaMemset(b->debug_out, 0, sizeof(double) * b->debug_cap));
   int per_sm = 0;
@@ -216,7 +217,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
     const int wpw = 32 / b->lpw;
     if (!std::getenv("SOFTGRIP_NW")) {
       // small batches: smaller CTAs, so that every SM gets work
-      while (b->nwarp > 1 && (nworlds + b->nwarp * wpw - 1) / (b->nwarp * wpw) < 2 * prop.multiProcessorCount) b->nwarp /= 2;
+      while (b->nwarp > 1 && (nworlds + b->nwarp * wpw - 1) / (b->nwarp * wpw) < prop.multiProcessorCount) b->nwarp /= 2;
     }
     for (;;) {
       b->L2 = precision == 32 ? make_layout2<float>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem) : make_layout2<double>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem);
@@ -224,8 +225,8 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       if (b->smem2 <= prop.sharedMemPerBlockOptin || b->nwarp == 1) break;
       b->nwarp -= 1;                       // largest CTA that fits
     }
-    b->team = (b->nwarp % (b->lpw / 2) == 0) ? 1 : 0;
-    if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) == 0) b->team = 0; }
+    b->team = 0;
+    if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) != 0 && b->lpw >= 4 && b->nwarp % (b->lpw / 2) == 0) b->team = 1; }
     if (b->smem2 > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: worlds of one warp do not fit in shared memory (use more lanes per world or SOFTGRIP_AUX_SMEM=0)"); }
     int e = k2_dispatch_configure(precision, b->lpw, 32 * b->nwarp, b->smem2, &per_sm);
     if (e == -12345) { delete b; return fail("SOFTGRIP_LPW: this lanes-per-world value is not compiled in"); }
@@ -235,6 +236,13 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
     const int cta_worlds = wpw * b->nwarp;
     int need = (nworlds + cta_worlds - 1) / cta_worlds;
     int slots = need < b->max_ctas ? need : b->max_ctas;
+    if (const char* pe = std::getenv("SOFTGRIP_PROF")) {
+      if (std::atoi(pe) != 0) {
+        b->prof_n = PH_COUNT + (size_t)b->max_ctas * b->nwarp;
+        CUDA_OK(cudaMalloc((void**)&b->prof, sizeof(unsigned long long) * b->prof_n));
+        CUDA_OK(cudaMemset(b->prof, 0, sizeof(unsigned long long) * b->prof_n));
+      }
+    }
     if (!aux_in_smem) {
       CUDA_OK(cudaMalloc((void**)&b->scratch, (size_t)slots * cta_worlds * (size_t)b->L2.gs_stride));
       CUDA_OK(cudaMemset(b->scratch, 0, (size_t)slots * cta_worlds * (size_t)b->L2.gs_stride));
@@ -266,7 +274,7 @@ extern "C" void sg_batch_destroy(sg_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   void* ptrs[] = {b->tab, b->itab, b->qpos, b->qvel, b->warm, b->act, b->ctrl, b->status, b->p_stiff, b->p_damp, b->p_tdamp,
-                  b->p_objoff, b->d_ctrl_event, b->d_ctrl_value, b->debug_out, b->stage_traj, b->stage_touch, b->scratch};
+                  b->p_objoff, b->d_ctrl_event, b->d_ctrl_value, b->debug_out, b->stage_traj, b->stage_touch, b->scratch, b->prof};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete b;
 }
@@ -281,6 +289,18 @@ extern "C" int sg_batch_config(const sg_batch* b, int* out) {
   out[3] = b->per_sm; out[4] = b->kernel == 2 ? (int)b->smem2 : 0; out[5] = b->kernel == 2 ? b->L2.smem_stride : 0;
   out[6] = b->kernel == 2 ? b->team : 0; out[7] = b->kernel;
   return 0;
+}
+
+extern "C" int sg_batch_prof_get(sg_batch* b, unsigned long long* out, int n) {
+  if (!b || !out) return fail("sg_batch_prof_get: null argument");
+  if (!b->prof) return fail("sg_batch_prof_get: phase clocks are off (create the batch with SOFTGRIP_PROF=1)");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  std::vector<unsigned long long> h(PH_COUNT);
+  CUDA_OK(cudaMemcpy(h.data(), b->prof, sizeof(unsigned long long) * PH_COUNT, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n && i < PH_COUNT; i++) out[i] = h[i];
+  CUDA_OK(cudaMemset(b->prof, 0, sizeof(unsigned long long) * PH_COUNT));
+  return PH_COUNT;
 }
 
 extern "C" int sg_batch_set_params(sg_batch* b, const double* stiffness, const double* damping, const double* tdamping,
@@ -409,6 +429,7 @@ static int launch_v2(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
   K.p_tdamp = b->has_tdamp ? b->p_tdamp : nullptr; K.p_objoff = b->has_objoff ? b->p_objoff : nullptr;
   K.status = b->status;
   K.debug_world = b->debug_world; K.debug_out = b->debug_out; K.debug_cap = b->debug_cap;
+  K.prof = b->prof;
   K.nsub = sp.nsub; K.integrate = sp.integrate; K.sens_out = (T*)sp.sens_out; K.touch_out = sp.touch_out;
   K.rollout = sp.rollout; K.sim_start = sp.sim_start; K.sim_step = sp.sim_step; K.nrows = sp.nrows;
   K.ctrl_event = b->d_ctrl_event; K.ctrl_value = b->d_ctrl_value;

@@ -176,7 +176,12 @@ struct KArgs2 {
   int debug_world;
   double* debug_out;
   int debug_cap;
+  // development aid (null in production): SM-clock cycles per phase summed over warps, [PH_COUNT] sums followed by
+  // one time stamp per warp of the grid
+  unsigned long long* prof;
 };
+enum { PH_GRIPPER = 0, PH_COLLIDE, PH_ROWS, PH_WARMSTART, PH_PGS_SETUP, PH_PGS_EQUALITY, PH_PGS_CHAIN, PH_SENSORS, PH_EULER, PH_OTHER,
+       PH_COUNT = 16 };
 
 // reciprocal used inside the sweeps: one MUFU on the fp32 fast path, an IEEE division in the verification build
 template <typename T> __device__ __forceinline__ T trcp(T x);
@@ -261,6 +266,12 @@ template <> __device__ __forceinline__ void ldg2<float>(const float* p, float& x
 template <> __device__ __forceinline__ void ldg2<double>(const double* p, double& x, double& y) { const double2 v = __ldg(reinterpret_cast<const double2*>(p)); x = v.x; y = v.y; }
 static_assert(MAXCD == 4, "finger chain blocks are loaded as 4-vectors");
 
+// one slot of the level-sweep step tables in shared memory (host encoding: sg_plan.hpp build_step_tables)
+template <typename T> struct Slot;
+template <> struct alignas(16) Slot<float> { unsigned x, y; float iw1, iw2; };      // one 128-bit shared-memory load
+template <> struct alignas(8) Slot<double> { unsigned x, y; double iw1, iw2; };
+template <typename T> __device__ __forceinline__ Slot<T> ld_slot(const Slot<T>* p) { return *p; }
+
 // ---------------------------------------------------------------------------------------------
 // the world
 // ---------------------------------------------------------------------------------------------
@@ -279,8 +290,7 @@ struct World2 {
   T kw, dw, tdw, off[3];
 
   unsigned char* smem_base;
-  const int2* sdesc;     // CTA-shared step tables of the level sweep (shared memory), already offset to this lane
-  const T* siw;
+  const Slot<T>* slots;  // CTA-shared step tables of the level sweep (shared memory), already offset to this lane
   const T *stc, *stciw;   // CTA-shared copies of the tendon coefficients and coefficient / mass
   const T* stim;          // CTA-shared 1 / slider mass
   __device__ __forceinline__ T stiw(int e) const { return stim[e]; }
@@ -292,10 +302,8 @@ struct World2 {
     lane = threadIdx.x & 31; grp = lane / LPW; sl = lane % LPW; gshift = grp * LPW;
     const int warp = vwarp >= 0 ? vwarp : (int)(threadIdx.x >> 5), nwarp = vnwarp >= 0 ? vnwarp : (int)(blockDim.x >> 5);
     smem_base = smem;
-    sdesc = reinterpret_cast<const int2*>(smem) + sl;
-    const T* tw = reinterpret_cast<const T*>(smem + (size_t)(D.nstep + 1) * LPW * 8);
-    siw = tw + 2 * sl;
-    stc = tw + 2 * (D.nstep + 1) * LPW;
+    slots = reinterpret_cast<const Slot<T>*>(smem) + sl;
+    stc = reinterpret_cast<const T*>(smem + (size_t)(D.nstep + 1) * LPW * sizeof(Slot<T>));
     stciw = stc + D.ns;
     stim = stciw + D.ns;
     unsigned char* base = smem + L.smem_tables + (size_t)(warp * WPW + grp) * L.smem_stride;
@@ -314,6 +322,20 @@ struct World2 {
   __device__ __forceinline__ T* qs() { return aux + L.qs; }
   __device__ __forceinline__ int& misc(int i) { return hoti[L.h_misc + i]; }
   __device__ __forceinline__ T* crec(int i) { return aux + L.crec + CR_STRIDE * i; }
+
+  // phase clock (development aid): charges the cycles since the warp's previous tick to phase `ph`
+  __device__ __forceinline__ void tick(int ph) {
+#if defined(__CUDA_ARCH__)
+    if (K.prof && lane == 0) {
+      unsigned long long* stamp = K.prof + PH_COUNT + (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+      const unsigned long long t = clock64();
+      atomicAdd(K.prof + ph, t - *stamp);
+      *stamp = t;
+    }
+#else
+    (void)ph;
+#endif
+  }
 
   // sub-warp collectives (every lane of the warp takes part; results are per group)
   __device__ __forceinline__ T gsum(T x) const {
@@ -835,7 +857,7 @@ struct World2 {
   // ------------------------------------------------------------------------------------------
   // equality / tendon / limit rows and smooth dynamics of the shell
   // ------------------------------------------------------------------------------------------
-  struct Tendon { T u, R, A, aref; };     // group-uniform registers: u = R f - aref
+  struct Tendon { T u, R, A, nA, aref; }; // group-uniform registers: u = R f - aref, nA = -1 / A
   struct ChainRows {                      // registers of the lane that owns a finger chain
     T ag[MAXCD];                          // running qacc of the chain dofs during the sweeps
     int lmask;                            // bit jl: limit of local dof jl is active
@@ -885,7 +907,7 @@ struct World2 {
       const T aref = -C.eqj_B * vel - C.eqj_K * imp * pos;
       row2[2 * p] = aref;
       row2[2 * p + 1] = tmax(T(SG_MINVAL), (T(1) - imp) * diag / imp);
-      if (dbg) K.debug_out[K.debug_cap - (D.nrow + 1) + p] = (double)aref;
+      if (dbg) { K.debug_out[K.debug_cap - (D.nrow + 1) + p] = (double)aref; K.debug_out[K.debug_cap - 2 * (D.nrow + 1) + p] = (double)row2[2 * p + 1]; }
     }
     {
       const T pos = Ls - C.ten_l0;
@@ -893,6 +915,7 @@ struct World2 {
       tn.R = tmax(T(SG_MINVAL), (T(1) - imp) * C.ten_iw / imp);
       tn.aref = -C.eqt_B * Lv - C.eqt_K * imp * pos;
       tn.A = As + tn.R;
+      tn.nA = T(-1) / tn.A;
       tn.u = 0;
     }
     __syncwarp();
@@ -1042,16 +1065,15 @@ struct World2 {
     }
     cost = gsum(cost);
     const bool keep = !(cost > T(0));
-    // u = R f - aref:  kept -> -(J.qacc_warm),  dropped -> -aref
+    // (aref, R) -> (u, n):  u = R f - aref is -(J.qacc_warm) when the warm start is kept and -aref when it is dropped;
+    // n = -1 / (1/m1 + 1/m2 + R) is what the sweep multiplies the residual with
     for (int p = sl; p < D.nrow; p += LPW) {
-      T u;
-      if (keep) {
-        const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
-        T ja = a()[nfd + d1];
-        if (d2 != 0xffff) ja -= a()[nfd + d2];
-        u = -ja;
-      } else u = -row2[2 * p];
-      row2[2 * p] = u;
+      const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
+      T ar, R; ld2(row2 + 2 * p, ar, R);
+      T ja = a()[nfd + d1], diag = stiw(d1);
+      if (d2 != 0xffff) { ja -= a()[nfd + d2]; diag += stiw(d2); }
+      row2[2 * p] = keep ? -ja : -ar;
+      row2[2 * p + 1] = T(-1) / (diag + R);
     }
     tn.u = keep ? -tja : -tn.aref;
     if (!keep) {
@@ -1231,45 +1253,57 @@ struct World2 {
   }
 
   // one sweep over the equality block and the volume-tendon row; returns this lane's cost improvement.
-  // Step descriptors (built per lanes-per-world by the host, staged in shared memory by the kernel prologue and
-  // shared by all worlds of the CTA): slot = step * LPW + lane, {first slider | second slider << 16, row |
-  // last-step-of-level << 30} and {1/m first, 1/m second}.  Slots that pad a level and rows with a single slider point
-  // at the dummy slider / dummy row, so the loop body has no predication at all.
-  __device__ __forceinline__ T equality_sweep(Tendon& tn, bool done) {
-    const int ns = D.ns, nstep = D.nstep;
-    T* av = a() + D.nfd;
-    T* row2 = hot + L.row2;
-    T impr = 0;
-    // one row per lane per step, a warp barrier where a dependency level ends.  The next step's descriptor is fetched
+  // Step slots (built per lanes-per-world by the host, staged in shared memory by the kernel prologue and shared by all
+  // worlds of the CTA): slot = step * LPW + lane.  Slots that pad a step and rows with a single slider point at the dummy
+  // slider / dummy row, so the loop body has no predication at all.
+  // Per row the sweep keeps (u, n) with u = R f - aref and n = -1 / (1/m1 + 1/m2 + R): the residual is a1 - a2 + u, the
+  // force change dl = res * n, and since an (unclamped) equality row has zero residual right after its own update, the
+  // new u is simply a2' - a1' -- neither R nor f is needed, and there is no division in the sweep.
+  template <bool GATED>
+  __device__ __forceinline__ T equality_rows(bool done) {
+    const int nstep = D.nstep;
+    char* avb = reinterpret_cast<char*>(a() + D.nfd);
+    char* rwb = reinterpret_cast<char*>(hot + L.row2);
+    T acc = 0;                                   // sum of res * dl = -2 * cost improvement
+    // one row per lane per step, a warp barrier where the schedule asks for one.  The next step's slot is fetched
     // before the barrier so that its latency overlaps this step's arithmetic.
-    {
-      const T gate = done ? T(0) : T(1);
-      int2 dn = sdesc[0];
-      T iw1n, iw2n; ld2(siw, iw1n, iw2n);
-      for (int st = 0; st < nstep; st++) {
-        const int2 dc = dn; const T iw1 = iw1n, iw2 = iw2n;
-        dn = sdesc[(st + 1) * LPW];            // the table carries one dummy step past the end
-        ld2(siw + 2 * (st + 1) * LPW, iw1n, iw2n);
-        const int d1 = dc.x & 0xffff, d2 = (dc.x >> 16) & 0xffff, p = dc.y & 0x3fffffff;
-        T a1 = av[d1], a2 = av[d2];
-        T u, R; ld2(row2 + 2 * p, u, R);
-        const T res = (a1 - a2) + u;
-        const T dl = -res * trcp<T>(iw1 + iw2 + R) * gate;
-        impr -= T(0.5) * dl * res;
-        u += R * dl; a1 += iw1 * dl; a2 -= iw2 * dl;
-        row2[2 * p] = u;
-        av[d1] = a1;
-        av[d2] = a2;
-        if (dc.y >> 30) __syncwarp();
-      }
+    Slot<T> sn = ld_slot<T>(slots);
+#pragma unroll 2
+    for (int st = 0; st < nstep; st++) {
+      const Slot<T> sc = sn;
+      sn = ld_slot<T>(slots + (st + 1) * LPW);   // the table carries one dummy step past the end
+      T* pa1 = reinterpret_cast<T*>(avb + (sc.x & 0xffffu));
+      T* pa2 = reinterpret_cast<T*>(avb + (sc.x >> 16));
+      T* pr = reinterpret_cast<T*>(rwb + (sc.y & 0x7fffffffu));
+      T a1 = *pa1, a2 = *pa2;
+      T u, n; ld2(pr, u, n);
+      const T res = (a1 - a2) + u;
+      if (GATED) n = done ? T(0) : n;
+      const T dl = res * n;
+      acc += dl * res;
+      a1 += sc.iw1 * dl; a2 -= sc.iw2 * dl;
+      T un = a2 - a1;
+      if (GATED) un = done ? u : un;
+      *pr = un;
+      *pa1 = a1;
+      *pa2 = a2;
+      if ((int)sc.y < 0) __syncwarp();
     }
+    return T(-0.5) * acc;
+  }
+  __device__ __forceinline__ T equality_sweep(Tendon& tn, bool done) {
+    const int ns = D.ns;
+    T* av = a() + D.nfd;
+    // worlds stop sweeping one by one (rarely before the last sweep): the gated loop is only taken by a warp that
+    // holds a finished world
+    T impr = __any_sync(FULLMASK, done) ? equality_rows<true>(done) : equality_rows<false>(false);
     // volume-tendon row: dense over the shell, sub-warp shuffle reduction
     {
       T s = 0;
       for (int e = sl; e < ns; e += LPW) s += stc[e] * av[e];
       s = gsum(s);
       const T res = s + tn.u;
-      const T dl = done ? T(0) : -res * trcp<T>(tn.A);
+      const T dl = done ? T(0) : res * tn.nA;
       if (sl == 0) impr -= T(0.5) * dl * res;
       tn.u += tn.R * dl;
       for (int e = sl; e < ns; e += LPW) av[e] += stciw[e] * dl;
@@ -1311,10 +1345,13 @@ struct World2 {
       chain_prologue(cs);
       const int tmaxw = wmax(misc(M2_TMAX));
       __syncwarp();
+      tick(PH_PGS_SETUP);
       for (int it = 0; it < D.iters; it++) {
         if (!__any_sync(FULLMASK, !done)) break;
         T impr = equality_sweep(tn, done);
+        tick(PH_PGS_EQUALITY);
         impr += chain_phase(cs, tmaxw, done);
+        tick(PH_PGS_CHAIN);
         impr = gsum(impr) * C.impr_scale;
         if (!done) { iter++; if (impr < C.tol) done = true; }
       }
@@ -1329,8 +1366,10 @@ struct World2 {
       if (sl == 0) misc(M2_DONE) = 0;
       team_sync(bar_id, nthr);                               // warm-start results of all 16 worlds are in place
       if (wit == 0) { V.chain_prologue(cs); tmaxw = V.wmax(V.misc(M2_TMAX)); }
+      tick(PH_PGS_SETUP);
       for (int it = 0; it < D.iters; it++) {
         T impr = equality_sweep(tn, done);
+        tick(PH_PGS_EQUALITY);
         team_sync(bar_id, nthr);
         if (wit == 0) {
           T ic = V.chain_phase(cs, tmaxw, V.misc(M2_DONE) != 0);
@@ -1338,6 +1377,7 @@ struct World2 {
           if (V.sl == 0) V.hot[L.h_impr] = ic;
         }
         team_sync(bar_id, nthr);
+        tick(PH_PGS_CHAIN);
         impr = (gsum(impr) + hot[L.h_impr]) * C.impr_scale;
         if (!done) { iter++; if (impr < C.tol) done = true; }
         if (sl == 0) misc(M2_DONE) = done ? 1 : 0;
@@ -1354,12 +1394,17 @@ struct World2 {
   // ------------------------------------------------------------------------------------------
   __device__ bool forward() {
     Tendon tn; ChainRows cr; T Ft;
+    tick(PH_OTHER);
     if (sl < D.nchain) gripper(sl);
     __syncwarp();
+    tick(PH_GRIPPER);
     collide();
+    tick(PH_COLLIDE);
     rows_and_smooth(tn, Ft);
     if (sl < D.nchain) chain_limits(sl, cr); else cr.lmask = 0;
+    tick(PH_ROWS);
     warmstart(tn, cr);
+    tick(PH_WARMSTART);
     pgs(tn, smem_base);
     // accelerometers (mj_sensorAcc): R_site^T (Jv qacc + bias - g)
     for (int s = sl; s < D.nsens; s += LPW) {
@@ -1384,6 +1429,7 @@ struct World2 {
       if (sl == 0) misc(M2_NLIM) = s;
     }
     __syncwarp();
+    tick(PH_SENSORS);
     if (valid && w == K.debug_world) debug_dump(tn);
     bool badacc = false;
     for (int i = sl; i < D.nv; i += LPW) if (!(tabs(a()[i]) <= T(SG_MAXVAL))) badacc = true;
@@ -1433,7 +1479,7 @@ struct World2 {
       if (pass == 0 && !bad) { const T* a0 = aux + L.a0; for (int i = sl; i < D.nv; i += LPW) a()[i] = a0[i]; }
       reset_if(bad);
     }
-    if (integrate) euler();
+    if (integrate) { tick(PH_OTHER); euler(); tick(PH_EULER); }
   }
   __device__ __forceinline__ bool cta_any(bool p) const {
     if (blockDim.x > 32) return __syncthreads_or(p ? 1 : 0) != 0;
@@ -1451,7 +1497,7 @@ struct World2 {
   __device__ void debug_dump(const Tendon& tn) {
     // header: [0]=ncon_total [1]=nefc [2]=iters [3]=ncon(rows) [4]=nlim [5]=tmax [6]=ncand ; contacts at 64+16*i ;
     // then at 64+16*maxcon*2: qacc[nv], efc_force / aref / R (equality block in schedule order, then MuJoCo order);
-    // the last nrow+1 doubles of the buffer hold the equality arefs written by rows_and_smooth
+    // the last nrow+1 doubles of the buffer hold the equality arefs written by rows_and_smooth, the nrow+1 before them the R's
     double* o = K.debug_out;
     if (!o) return;
     const int ncon = misc(M2_NCON), nlim = misc(M2_NLIM);
@@ -1460,11 +1506,11 @@ struct World2 {
     const int base = 64 + 16 * 2 * D.maxcon;
     for (int i = sl; i < D.nv; i += LPW) if (base + i < K.debug_cap) o[base + i] = (double)a()[i];
     const int eb = base + D.nv;
-    const int tail = K.debug_cap - (D.nrow + 1);
-    if (eb + 3 * nefc > tail) return;
+    const int tail = K.debug_cap - (D.nrow + 1), tailR = tail - (D.nrow + 1);
+    if (eb + 3 * nefc > tailR) return;
     const T* row2 = hot + L.row2;
     for (int p = sl; p < D.nrow; p += LPW) {
-      const double ar = o[tail + p], R = (double)row2[2 * p + 1];
+      const double ar = o[tail + p], R = o[tailR + p];
       o[eb + p] = ((double)row2[2 * p] + ar) / R; o[eb + nefc + p] = ar; o[eb + 2 * nefc + p] = R;
     }
     if (sl == 0) {
@@ -1512,22 +1558,28 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
   const int lane = threadIdx.x & 31, grp = lane / LPW, sl = lane % LPW;
   const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   {
-    // stage the step tables: int2 descriptors, then the (1/m, 1/m) pairs
-    int* sd = reinterpret_cast<int*>(smem_raw);
-    T* sw = reinterpret_cast<T*>(smem_raw + (size_t)(D.nstep + 1) * LPW * 8);
-    const int n2 = 2 * (D.nstep + 1) * LPW;
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) { sd[i] = K.itab[D.io_step_d + i]; sw[i] = K.tab[D.o_step_iw + i]; }
-    T* tc = sw + n2;
+    // stage the step tables: one {descriptor, (1/m, 1/m)} slot per (step, lane)
+    Slot<T>* ss = reinterpret_cast<Slot<T>*>(smem_raw);
+    const int nslot = (D.nstep + 1) * LPW;
+    for (int i = threadIdx.x; i < nslot; i += blockDim.x) {
+      Slot<T> t; t.x = (unsigned)K.itab[D.io_step_d + 2 * i]; t.y = (unsigned)K.itab[D.io_step_d + 2 * i + 1];
+      t.iw1 = K.tab[D.o_step_iw + 2 * i]; t.iw2 = K.tab[D.o_step_iw + 2 * i + 1];
+      ss[i] = t;
+    }
+    T* tc = reinterpret_cast<T*>(smem_raw + (size_t)nslot * sizeof(Slot<T>));
     for (int i = threadIdx.x; i < D.ns; i += blockDim.x) { tc[i] = K.tab[D.o_sl_tc + i]; tc[D.ns + i] = K.tab[D.o_sl_tciw + i]; tc[2 * D.ns + i] = T(1) / K.tab[D.o_sl_m + i]; }
     __syncthreads();
   }
+#if defined(__CUDA_ARCH__)
+  if (K.prof && lane == 0) K.prof[PH_COUNT + (size_t)blockIdx.x * nwarp + warp] = clock64();
+#endif
   const int cta_worlds = nwarp * WPW;
   for (int b0 = blockIdx.x * cta_worlds; b0 < K.nworlds; b0 += gridDim.x * cta_worlds) {
     const int wi = b0 + warp * WPW + grp;
     const bool valid = wi < K.nworlds;
     World2<T, LPW> W(K, smem_raw, valid ? wi : K.nworlds - 1, valid);
     W.load_params();
-    if (sl == 0) { W.misc(M2_STATUS) = 0; W.a()[D.nv] = 0; W.hot[L.row2 + 2 * D.nrow] = 0; W.hot[L.row2 + 2 * D.nrow + 1] = 1; }
+    if (sl == 0) { W.misc(M2_STATUS) = 0; W.a()[D.nv] = 0; W.hot[L.row2 + 2 * D.nrow] = 0; W.hot[L.row2 + 2 * D.nrow + 1] = -1; }
     const int w = W.w;
     const size_t sb = (size_t)w * D.nv;
     T* aux = W.aux;

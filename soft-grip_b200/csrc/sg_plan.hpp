@@ -6,6 +6,7 @@
 // It replaces what mj_loadXML/mj_makeData hand to mj_step in the reference (ref: environment/manenv.py:27-28).
 // Anything outside that model family is rejected with an error -- there is no generic/CPU fallback.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -69,7 +70,7 @@ struct PlanDims {
   int io_kmask, io_row_d1, io_row_d2, io_lev_start, io_dof_rows, io_pair_t, io_pair_a, io_pair_b;
   int io_row_d12;   // nrow: first slider | second slider << 16 (0xffff: none), schedule order
   // per-batch step tables of the level sweep (depend on the lanes per world; appended by sg_api.cu)
-  int io_step_d;    // 2*nstep*lpw ints: {d1 | d2 << 16, row | last-of-level << 30} per slot
+  int io_step_d;    // 2*(nstep+1)*lpw ints: {byte offset of d1 | of d2 << 16, byte offset of the row pair | barrier << 31} per slot
   int o_step_iw;    // 2*nstep*lpw reals: {1/m first, 1/m second} per slot
   int nstep;
 };
@@ -141,34 +142,78 @@ struct Plan {
 
 #define SG_REQUIRE(cond, msg) do { if (!(cond)) throw std::runtime_error(std::string("unsupported model: ") + msg); } while (0)
 
-// Level sweep tables for `lpw` lanes per world: every dependency level is cut into steps of `lpw` slots; padding slots
-// and the missing second slider of fix rows point at the dummy slider (index ns, inverse mass 0) and the dummy row
-// (index nrow, u = 0, R = 1), which the sweep leaves unchanged.
-inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab, const std::vector<int>& itab, int lpw,
+// Level sweep tables for `lpw` lanes per world.  The rows (schedule positions p) are list-scheduled onto steps of `lpw`
+// slots: a row is ready once every earlier row (in MuJoCo's sequential order) that shares one of its sliders has run in an
+// earlier step; among the ready rows the ones with the longest chain of dependants go first.  A step carries the
+// "barrier" flag when a row of a later step, up to the next flagged step, depends on one of its rows or of an earlier
+// unflagged step.  The result equals the sequential sweep (rows that share a slider keep their order, rows that do not
+// commute).  Padding slots and the missing second slider of fix rows point at the dummy slider (index ns, inverse
+// mass 0) and the dummy row (index nrow), which the sweep leaves unchanged.
+// Slot encoding (esize = bytes per real of the kernel precision): {first slider * esize | second slider * esize << 16,
+// row * 2 * esize | barrier << 31}, {1/m first, 1/m second}.
+inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab, const std::vector<int>& itab, int lpw, int esize,
                               std::vector<int>& step_d, std::vector<double>& step_iw) {
   step_d.clear(); step_iw.clear();
-  const int dummy_d = D.ns, dummy_p = D.nrow;
-  for (int lv = 0; lv < D.nlev; lv++) {
-    const int p0 = itab[D.io_lev_start + lv], p1 = itab[D.io_lev_start + lv + 1];
-    // consecutive table levels that were only split at 32 rows belong to one dependency level: no barrier is
-    // needed between them, but keeping one is harmless
-    for (int pb = p0; pb < p1; pb += lpw) {
-      const bool last = pb + lpw >= p1;
-      for (int k = 0; k < lpw; k++) {
-        const int p = pb + k;
-        int d1 = dummy_d, d2 = dummy_d, row = dummy_p; double iw1 = 0, iw2 = 0;
-        if (p < p1) {
-          d1 = itab[D.io_row_d1 + p]; row = p; iw1 = 1.0 / tab[D.o_sl_m + d1];
-          const int dd2 = itab[D.io_row_d2 + p];
-          if (dd2 >= 0) { d2 = dd2; iw2 = 1.0 / tab[D.o_sl_m + dd2]; }
-        }
-        step_d.push_back(d1 | (d2 << 16)); step_d.push_back(row | ((last ? 1 : 0) << 30));
-        step_iw.push_back(iw1); step_iw.push_back(iw2);
+  const int dummy_d = D.ns, dummy_p = D.nrow, nrow = D.nrow;
+  SG_REQUIRE((size_t)(D.ns + 1) * esize <= 0xffff, "too many shell joints for the packed step descriptors");
+  // dependency chains per slider, in schedule order (which respects MuJoCo's row order along every slider)
+  std::vector<int> last(D.ns, -1), npred(nrow, 0), height(nrow, 1), step_of(nrow, -1);
+  std::vector<std::vector<int>> pred(nrow), succ(nrow);
+  for (int p = 0; p < nrow; p++) {
+    const int ds[2] = {itab[D.io_row_d1 + p], itab[D.io_row_d2 + p]};
+    for (int k = 0; k < 2; k++) {
+      const int d = ds[k];
+      if (d < 0) continue;
+      const int q = last[d];
+      if (q >= 0 && (pred[p].empty() || pred[p].back() != q)) { pred[p].push_back(q); succ[q].push_back(p); }
+      last[d] = p;
+    }
+    npred[p] = (int)pred[p].size();
+  }
+  for (int p = nrow - 1; p >= 0; p--) for (int s : succ[p]) if (height[s] + 1 > height[p]) height[p] = height[s] + 1;
+  std::vector<std::vector<int>> steps;
+  std::vector<int> ready;
+  for (int p = 0; p < nrow; p++) if (npred[p] == 0) ready.push_back(p);
+  int done = 0;
+  while (done < nrow) {
+    SG_REQUIRE(!ready.empty(), "cyclic equality schedule");
+    std::stable_sort(ready.begin(), ready.end(), [&](int a, int b) { return height[a] != height[b] ? height[a] > height[b] : a < b; });
+    const int take = (int)ready.size() < lpw ? (int)ready.size() : lpw;
+    std::vector<int> cur(ready.begin(), ready.begin() + take);
+    ready.erase(ready.begin(), ready.begin() + take);
+    for (int p : cur) step_of[p] = (int)steps.size();
+    for (int p : cur) for (int s : succ[p]) if (--npred[s] == 0) ready.push_back(s);
+    done += take;
+    steps.push_back(cur);
+  }
+  const int nstep = (int)steps.size();
+  std::vector<int> flag(nstep, 0);
+  int synced = -1;                                   // every step <= synced is followed by a barrier somewhere before the current one
+  for (int s = 0; s < nstep; s++) {
+    bool need = false;
+    for (int p : steps[s]) for (int q : pred[p]) if (step_of[q] > synced) need = true;
+    if (need) { flag[s - 1] = 1; synced = s - 1; }
+  }
+  if (nstep > 0) flag[nstep - 1] = 1;                // the tendon row reads every slider
+  for (int s = 0; s < nstep; s++) {
+    for (int k = 0; k < lpw; k++) {
+      int d1 = dummy_d, d2 = dummy_d, row = dummy_p; double iw1 = 0, iw2 = 0;
+      if (k < (int)steps[s].size()) {
+        const int p = steps[s][k];
+        d1 = itab[D.io_row_d1 + p]; row = p; iw1 = 1.0 / tab[D.o_sl_m + d1];
+        const int dd2 = itab[D.io_row_d2 + p];
+        if (dd2 >= 0) { d2 = dd2; iw2 = 1.0 / tab[D.o_sl_m + dd2]; }
       }
+      step_d.push_back((int)((unsigned)(d1 * esize) | ((unsigned)(d2 * esize) << 16)));
+      step_d.push_back((int)((unsigned)(row * 2 * esize) | ((unsigned)flag[s] << 31)));
+      step_iw.push_back(iw1); step_iw.push_back(iw2);
     }
   }
   // one dummy step past the end: the sweep prefetches the next step's descriptors unconditionally
-  for (int k = 0; k < lpw; k++) { step_d.push_back(dummy_d | (dummy_d << 16)); step_d.push_back(dummy_p); step_iw.push_back(0.0); step_iw.push_back(0.0); }
+  for (int k = 0; k < lpw; k++) {
+    step_d.push_back((int)((unsigned)(dummy_d * esize) | ((unsigned)(dummy_d * esize) << 16))); step_d.push_back(dummy_p * 2 * esize);
+    step_iw.push_back(0.0); step_iw.push_back(0.0);
+  }
 }
 
 inline bool same(const double* a, const double* b, int n) { for (int i = 0; i < n; i++) if (a[i] != b[i]) return false; return true; }

@@ -40,7 +40,7 @@ namespace sg {
 
 // contact record: 32 words of T, 16-byte aligned groups
 enum { CR_JG = 0 /*12*/, CR_NS = 12 /*3*/, CR_IWE = 15, CR_AREF = 16 /*3*/, CR_R0 = 19, CR_A = 20 /*6: 00 01 02 11 12 22*/,
-       CR_R1 = 26, CR_F = 28 /*3*/, CR_STRIDE = 32 };
+       CR_R1 = 26, CR_E = 27 /*slider index as a real, -1: none*/, CR_F = 28 /*3*/, CR_STRIDE = 32 };
 
 // per-world memory plan.  Offsets are in elements (T for the real arrays, int for the int arrays).
 struct Layout2 {
@@ -670,7 +670,7 @@ struct World2 {
     }
 #pragma unroll
     for (int r = 0; r < 3; r++) cr[CR_NS + r] = ns[r];
-    cr[CR_IWE] = iw_e;
+    cr[CR_IWE] = iw_e; cr[CR_E] = T(e);
     const T imp = impedance2<T>(C.con_si, rc.dist);
     const T R0 = tmax(T(SG_MINVAL), (T(1) - imp) * biw / imp);
     const T R1 = R0 / tmax(T(SG_MINVAL), C.impratio);
@@ -1096,16 +1096,15 @@ struct World2 {
   }
 
   // one elliptic contact block (mj_solPGS inner body, dim 3) on the lane that owns its chain
-  __device__ __forceinline__ T contact_block(int i, T* ag, bool has_chain, const T* mv) {
+  __device__ __forceinline__ T contact_block(T* r, T* ag, bool has_chain, const T* mv) {
     const int nfd = D.nfd;
-    T* r = crec(i);
     T jg[12], w1[4], w2[4], w3[4];
     ld4(r + CR_JG, jg); ld4(r + CR_JG + 4, jg + 4); ld4(r + CR_JG + 8, jg + 8);
     ld4(r + CR_NS, w1);          // ns0 ns1 ns2 iwe
     ld4(r + CR_AREF, w2);        // aref0 aref1 aref2 R0
-    T Aw[8]; ld4(r + CR_A, Aw); ld4(r + CR_A + 4, Aw + 4);   // A00 A01 A02 A11 | A12 A22 R1 -
+    T Aw[8]; ld4(r + CR_A, Aw); ld4(r + CR_A + 4, Aw + 4);   // A00 A01 A02 A11 | A12 A22 R1 e
     ld4(r + CR_F, w3);           // f0 f1 f2 -
-    const int e = (auxi[L.i_con + i] >> 4) - 1;
+    const int e = (int)Aw[7];
     const T A00 = Aw[0], A01 = Aw[1], A02 = Aw[2], A11 = Aw[3], A12 = Aw[4], A22 = Aw[5];
     const T R0 = w2[3], R1 = Aw[6];
     const T old0 = w3[0], old1 = w3[1], old2 = w3[2];
@@ -1208,9 +1207,19 @@ struct World2 {
     for (int jj = 0; jj < MAXCD; jj++) cs.ag[jj] = (cs.chain_lane && jj < D.ncd[sl]) ? a()[D.chain_dof0[sl] + jj] : T(0);
   }
   // one sweep over this lane's limit rows and contact blocks (time slots 1..tmaxw, a warp barrier after each);
-  // returns the lane's cost improvement
+  // returns the lane's cost improvement.  The contact records live in the L2-resident scratch: the lane's schedule
+  // entries are fetched three blocks ahead (registers) and the 128-byte record of the next block is prefetched into
+  // L1 when the current block starts, so that no block waits for two dependent L2 round trips.
   __device__ T chain_phase(ChainState& cs, int tmaxw, bool done) {
     T impr = 0;
+    const int* order = auxi + L.i_order + cs.mystart;
+    const int cnt = done ? 0 : cs.mycnt;
+    int entA = 0, entB = 0, entC = 0;
+    if (cnt > 0) entA = order[0];
+    if (cnt > 1) entB = order[1];
+    if (cnt > 2) entC = order[2];
+    const int ent0 = entA;
+    if (cnt > 1 && !L.aux_in_smem) prefetch_l1(crec(entB & 0xffff));
     if (cs.chain_lane && !done) {
 #pragma unroll
       for (int jl = 0; jl < MAXCD; jl++) {
@@ -1234,15 +1243,18 @@ struct World2 {
     }
     int k = 0;
     for (int t = 1; t <= tmaxw; t++) {
-      if (!done && k < cs.mycnt) {
-        const int ent = auxi[L.i_order + cs.mystart + k];
-        if ((ent >> 16) == t) {
-          if (k + 1 < cs.mycnt && !L.aux_in_smem) prefetch_l1(crec(auxi[L.i_order + cs.mystart + k + 1] & 0xffff));
-          impr -= contact_block(ent & 0xffff, cs.ag, cs.chain_lane, cs.mv); k++;
-        }
+      if (k < cnt && (entA >> 16) == t) {
+        T* r = crec(entA & 0xffff);
+        k++;
+        entA = entB; entB = entC;
+        if (k + 1 < cnt && !L.aux_in_smem) prefetch_l1(crec(entB & 0xffff));
+        if (k + 2 < cnt) entC = order[k + 2];
+        impr -= contact_block(r, cs.ag, cs.chain_lane, cs.mv);
       }
       __syncwarp();
     }
+    // next sweep's first entries and record: towards L1 while the equality block is swept
+    if (cnt > 0 && !L.aux_in_smem) { prefetch_l1(order); prefetch_l1(crec(ent0 & 0xffff)); }
     return impr;
   }
   __device__ void chain_epilogue(const ChainState& cs) {

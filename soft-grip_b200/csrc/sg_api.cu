@@ -225,6 +225,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       if (b->smem2 <= prop.sharedMemPerBlockOptin || b->nwarp == 1) break;
       b->nwarp -= 1;                       // largest CTA that fits
     }
+    if (b->L2.cand_cap < 16) { delete b; return fail("sg_batch_create: the collision scratch (the equality-row pairs of one world) is too small for this model"); }
     b->team = 0;
     if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) != 0 && b->lpw >= 4 && b->nwarp % (b->lpw / 2) == 0) b->team = 1; }
     if (b->smem2 > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: worlds of one warp do not fit in shared memory (use more lanes per world or SOFTGRIP_AUX_SMEM=0)"); }

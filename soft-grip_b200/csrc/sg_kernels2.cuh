@@ -57,8 +57,6 @@ struct Layout2 {
   int q, v, qs, jtf, a0; // nv each (qs: qacc_smooth; a0: qacc_warmstart at step entry, for the re-run after a divergence reset)
   int qv_in_smem, hq, hv; // optionally qpos/qvel live in the hot region (offsets hq, hv) instead of aux
   int act, ctrl, actdot; // nu each
-  int g_axis, g_anchor;  // 3*MAXFD each
-  int g_box;             // 12 per moving box
   int s_jv, s_ab, s_rot; // per sensor: 12, 3, 9
   int sens;              // nsd
   int crec;              // CR_STRIDE * maxcon
@@ -66,10 +64,17 @@ struct Layout2 {
   int i_con;             // maxcon : (chain+1) | (slider+1) << 4
   int i_tl;              // maxcon : time | lane << 16
   int i_order;           // maxcon : contact index | time << 16, segmented by lane
-  int i_cand;            // max(maxcand, ns)
+  int i_cand;            // ns : per-slider latest time slot of the contact schedule
   int i_lmask;           // MAXCHAIN : active-limit masks (bit jl: lower, bit 4+jl: upper)
   int auxI;
   int aux_in_smem;
+  // collision scratch: the (u, n) pairs of the equality rows are dead between the end of the solve and the next
+  // rows_and_smooth(), so gripper() and collide() keep their per-step data there (offsets in T words from row2)
+  int sc_cen;            // 3*ns : capsule centres
+  int sc_gbox;           // 12 per moving box : geom position, rotation
+  int sc_gaxis, sc_ganchor;  // 3*MAXFD each : world-frame joint axes / anchors of the finger chains
+  int sc_cand;           // candidate list (ints): pair type | collider << 3 | second geom << 8
+  int cand_cap;          // capacity of the candidate list (<= 0: the model does not fit the scratch)
   int smem_stride;       // bytes per world in shared memory (multiple of 16, bank-skewed)
   int smem_tables;       // bytes of the CTA-shared level-sweep step tables at the start of shared memory
   int gs_stride;         // bytes per world in the global scratch (0 when aux_in_smem)
@@ -98,14 +103,13 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw
   L.q = take(D.nv); L.v = take(D.nv); L.qs = take(D.nv); L.jtf = take(D.nv); L.a0 = take(D.nv);
   const int nu = D.nu > 0 ? D.nu : 1;
   L.act = take(nu); L.ctrl = take(nu); L.actdot = take(nu);
-  L.g_axis = take(3 * MAXFD); L.g_anchor = take(3 * MAXFD); L.g_box = take(12 * MAXCHAIN * MAXCB);
   L.s_jv = take(12 * MAXSENS); L.s_ab = take(3 * MAXSENS); L.s_rot = take(9 * MAXSENS); L.sens = take(D.nsd > 0 ? D.nsd : 1);
   L.crec = take(CR_STRIDE * D.maxcon);
   L.auxT = o;
   int io = 0;
   auto takei = [&](int n) { int r = io; io += (n + 3) & ~3; return r; };
   L.i_con = takei(D.maxcon); L.i_tl = takei(D.maxcon); L.i_order = takei(D.maxcon);
-  L.i_cand = takei(D.maxcand > D.ns ? D.maxcand : D.ns); L.i_lmask = takei(MAXCHAIN);
+  L.i_cand = takei(D.ns); L.i_lmask = takei(MAXCHAIN);
   L.auxI = io;
   L.aux_in_smem = aux_in_smem;
   size_t hot = sizeof(T) * (size_t)L.hotT + sizeof(int) * (size_t)L.hotI;
@@ -116,7 +120,20 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw
   if (wpw > 1) { const size_t unit = (size_t)(128 / wpw) < 16 ? 16 : (size_t)(128 / wpw); while ((sb / unit) % 2 == 0 || sb % unit) sb += 16; }
   L.smem_stride = (int)sb;
   L.gs_stride = aux_in_smem ? 0 : (int)((aux + 127) & ~(size_t)127);
-  L.smem_tables = (int)(((size_t)(D.nstep + 1) * lpw * (8 + 2 * sizeof(T)) + 3 * (size_t)D.ns * sizeof(T) + 127) & ~(size_t)127);
+  {
+    int so = 0;
+    L.sc_cen = so; so += 3 * D.ns;
+    L.sc_gbox = so; so += 12 * MAXCHAIN * MAXCB;
+    L.sc_gaxis = so; so += 3 * MAXFD;
+    L.sc_ganchor = so; so += 3 * MAXFD;
+    L.sc_cand = so;
+    L.cand_cap = (2 * D.nrow - so) * (int)(sizeof(T) / sizeof(int));
+    if (L.cand_cap > D.maxcand) L.cand_cap = D.maxcand;
+  }
+  // CTA-shared tables: step slots | tendon coefficients, coefficient / mass, 1 / mass (ns each) | slider axes (3 ns) |
+  // collider table | broadphase runs
+  L.smem_tables = (int)(((size_t)(D.nstep + 1) * lpw * (8 + 2 * sizeof(T)) + (6 * (size_t)D.ns + (size_t)MAXCOLL * CO_STRIDE) * sizeof(T) +
+                         4 * (size_t)D.nrun * sizeof(int) + 127) & ~(size_t)127);
   return L;
 }
 
@@ -293,6 +310,9 @@ struct World2 {
   const Slot<T>* slots;  // CTA-shared step tables of the level sweep (shared memory), already offset to this lane
   const T *stc, *stciw;   // CTA-shared copies of the tendon coefficients and coefficient / mass
   const T* stim;          // CTA-shared 1 / slider mass
+  const T* sax;           // CTA-shared slider axes (3 per slider)
+  const T* scoll;         // CTA-shared collider table
+  const int* sruns;       // CTA-shared broadphase runs
   __device__ __forceinline__ T stiw(int e) const { return stim[e]; }
 
   // vwarp / vnwarp: position of this warp's worlds in the CTA in units of WPW worlds (the real warp index, except
@@ -306,6 +326,9 @@ struct World2 {
     stc = reinterpret_cast<const T*>(smem + (size_t)(D.nstep + 1) * LPW * sizeof(Slot<T>));
     stciw = stc + D.ns;
     stim = stciw + D.ns;
+    sax = stim + D.ns;
+    scoll = sax + 3 * D.ns;
+    sruns = reinterpret_cast<const int*>(scoll + MAXCOLL * CO_STRIDE);
     unsigned char* base = smem + L.smem_tables + (size_t)(warp * WPW + grp) * L.smem_stride;
     hot = reinterpret_cast<T*>(base);
     hoti = reinterpret_cast<int*>(hot + L.hotT);
@@ -322,6 +345,8 @@ struct World2 {
   __device__ __forceinline__ T* qs() { return aux + L.qs; }
   __device__ __forceinline__ int& misc(int i) { return hoti[L.h_misc + i]; }
   __device__ __forceinline__ T* crec(int i) { return aux + L.crec + CR_STRIDE * i; }
+  __device__ __forceinline__ T* scr(int o) { return hot + L.row2 + o; }     // collision scratch (see Layout2)
+  __device__ __forceinline__ int* scand() { return reinterpret_cast<int*>(hot + L.row2 + L.sc_cand); }
 
   // phase clock (development aid): charges the cycles since the warp's previous tick to phase `ph`
   __device__ __forceinline__ void tick(int ph) {
@@ -430,7 +455,7 @@ struct World2 {
       Iw[k][4] = Ri[0] * Ri[6] * I0 + Ri[1] * Ri[7] * I1 + Ri[2] * Ri[8] * I2;   // xz
       Iw[k][5] = Ri[3] * Ri[6] * I0 + Ri[4] * Ri[7] * I1 + Ri[5] * Ri[8] * I2;   // yz
       // box geom pose -> aux
-      T* gb = aux + L.g_box + 12 * (c * MAXCB + k);
+      T* gb = scr(L.sc_gbox) + 12 * (c * MAXCB + k);
       matvec3(t, Rc, cb + CB_GPOS);
 #pragma unroll
       for (int i = 0; i < 3; i++) gb[i] = pos[i] + t[i];
@@ -442,7 +467,7 @@ struct World2 {
     for (int jj = 0; jj < MAXCD; jj++) {
       if (jj >= nd) break;
 #pragma unroll
-      for (int i = 0; i < 3; i++) { aux[L.g_axis + 3 * (dof0 + jj) + i] = axis[jj][i]; aux[L.g_anchor + 3 * (dof0 + jj) + i] = anch[jj][i]; }
+      for (int i = 0; i < 3; i++) { scr(L.sc_gaxis)[3 * (dof0 + jj) + i] = axis[jj][i]; scr(L.sc_ganchor)[3 * (dof0 + jj) + i] = anch[jj][i]; }
     }
     // velocity-dependent terms
     T qv[MAXCD], da[MAXCD][3], va[MAXCD][3];
@@ -607,14 +632,13 @@ struct World2 {
   // ------------------------------------------------------------------------------------------
   // collision + contact rows
   // ------------------------------------------------------------------------------------------
-  __device__ __forceinline__ void capsule_center(int e, T* c, const T* __restrict__ qsl) {
-    const T* __restrict__ c0 = tab(D.o_sl_cap0) + 3 * e; const T* __restrict__ ax = tab(D.o_sl_axis) + 3 * e;
-    const T qe = qsl[e];
+  __device__ __forceinline__ void capsule_center(int e, T* c) {
+    const T* ce = scr(L.sc_cen) + 3 * e;
 #pragma unroll
-    for (int k = 0; k < 3; k++) c[k] = off[k] + c0[k] + ax[k] * qe;
+    for (int k = 0; k < 3; k++) c[k] = ce[k];
   }
   __device__ __forceinline__ void collider_pose(int ci, T* pos, T* rot) {
-    const T* co = tab(D.o_coll + ci * CO_STRIDE);
+    const T* co = scoll + ci * CO_STRIDE;
     const int c = (int)co[CO_CHAIN];
     if (c < 0) {
 #pragma unroll
@@ -622,7 +646,7 @@ struct World2 {
 #pragma unroll
       for (int k = 0; k < 9; k++) rot[k] = co[CO_ROT + k];
     } else {
-      const T* gb = aux + L.g_box + 12 * (c * MAXCB + (int)co[CO_BODY]);
+      const T* gb = scr(L.sc_gbox) + 12 * (c * MAXCB + (int)co[CO_BODY]);
 #pragma unroll
       for (int k = 0; k < 3; k++) pos[k] = gb[k];
 #pragma unroll
@@ -633,7 +657,7 @@ struct World2 {
   // builds the three rows of one contact into record `slot` (mj_instantiateContact + mj_makeImpedance +
   // mj_referenceConstraint + the diagonal block of efc_AR)
   __device__ void contact_rows(int slot, const RawCon<T>& rc, int ci, int e, T slider_sign, bool dbg, int dbg_index) {
-    const T* co = tab(D.o_coll + ci * CO_STRIDE);
+    const T* co = scoll + ci * CO_STRIDE;
     const int c = (int)co[CO_CHAIN];
     T fr[9];
 #pragma unroll
@@ -652,7 +676,7 @@ struct World2 {
     for (int jj = 0; jj < MAXCD; jj++) {
       T col[3] = {0, 0, 0};
       if (jj < nsupp) {
-        const T* ax = aux + L.g_axis + 3 * (dof0 + jj); const T* an = aux + L.g_anchor + 3 * (dof0 + jj);
+        const T* ax = scr(L.sc_gaxis) + 3 * (dof0 + jj); const T* an = scr(L.sc_ganchor) + 3 * (dof0 + jj);
         T r[3] = {rc.pos[0] - an[0], rc.pos[1] - an[1], rc.pos[2] - an[2]};
         cross3(col, ax, r);
       }
@@ -661,10 +685,10 @@ struct World2 {
     }
     T ns[3] = {0, 0, 0}, iw_e = 0, biw = co[CO_BIW], ve = 0;
     if (e >= 0) {
-      const T* ax = tab(D.o_sl_axis) + 3 * e;
+      const T* ax = sax + 3 * e;
 #pragma unroll
       for (int r = 0; r < 3; r++) ns[r] = slider_sign * dot3(fr + 3 * r, ax);
-      iw_e = T(1) / tab(D.o_sl_m)[e];
+      iw_e = stiw(e);
       biw += tab(D.o_sl_biw)[e];
       ve = v()[D.nfd + e];
     }
@@ -724,44 +748,63 @@ struct World2 {
 
   __device__ void collide() {
     const bool dbg = valid && (w == K.debug_world);
-    const T* __restrict__ qsl = q() + D.nfd;     // slider positions are read-only during collision
-    // ---- broadphase: bounding spheres, candidates compacted in pair order ----
-    int ncand = 0, flags = 0;
-    for (int base = 0; base < D.npair; base += LPW) {
-      const int p = base + sl;
-      bool pass = false;
-      if (p < D.npair) {
-        const int pt = itab(D.io_pair_t)[p], pa = itab(D.io_pair_a)[p], pb = itab(D.io_pair_b)[p];
-        const T* co = tab(D.o_coll + pa * CO_STRIDE);
-        T c2[3], rb2;
-        if (pt == PAIR_PLANE_CAPSULE || pt == PAIR_BOX_CAPSULE) { capsule_center(pb, c2, qsl); rb2 = C.cap_r + C.cap_hl; }
-        else if (pt == PAIR_SPHERE_BOX) {
+    // ---- capsule centres into the scratch (the sliders only move along their axes) ----
+    {
+      const T* __restrict__ qsl = q() + D.nfd;
+      const T* __restrict__ c0 = tab(D.o_sl_cap0);
+      T* cen = scr(L.sc_cen);
+#pragma unroll 2
+      for (int e = sl; e < D.ns; e += LPW) {
+        const T qe = qsl[e];
 #pragma unroll
-          for (int k = 0; k < 3; k++) c2[k] = off[k] + C.sph_pos[k];
-          rb2 = C.sph_r;
-        } else { T rot[9]; collider_pose(pb, c2, rot); rb2 = tab(D.o_coll + pb * CO_STRIDE)[CO_RBOUND]; }
-        T c1[3], rot1[9];
-        collider_pose(pa, c1, rot1);
-        T dif[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
-        if ((int)co[CO_TYPE] == GEOM_PLANE) { T nrm[3] = {rot1[2], rot1[5], rot1[8]}; pass = !(dot3(dif, nrm) > rb2); }
-        else { T bound = co[CO_RBOUND] + rb2; pass = !(dot3(dif, dif) > bound * bound); }
-        if (pass && pt == PAIR_BOX_CAPSULE) {
-          // mid-phase (prunes only): the capsule's bounding box in the frame of the box must overlap the box
-          T dl[3], al[3];
-          matTvec3(dl, rot1, dif);
-          matTvec3(al, rot1, tab(D.o_sl_axis) + 3 * pb);
-#pragma unroll
-          for (int k = 0; k < 3; k++) if (tabs(dl[k]) > co[CO_SIZE + k] + C.cap_r + C.cap_hl * tabs(al[k])) pass = false;
-        }
+        for (int k = 0; k < 3; k++) cen[3 * e + k] = off[k] + c0[3 * e + k] + sax[3 * e + k] * qe;
       }
-      const unsigned m = gballot(pass);
-      if (pass) {
-        const int slot = ncand + __popc(m & ((1u << sl) - 1));
-        if (slot < D.maxcand) auxi[L.i_cand + slot] = p; else flags |= SG_ST_CON_FULL_BIT;
-      }
-      ncand += __popc(m);
+      __syncwarp();
     }
-    if (ncand > D.maxcand) ncand = D.maxcand;
+    // ---- broadphase: bounding spheres, candidates compacted in pair order.  The pair list is walked by runs
+    // {type, collider a, first b, count}: the collider is fetched once per run, everything else is in shared memory ----
+    int ncand = 0, flags = 0;
+    int* cand = scand();
+    const int cand_cap = L.cand_cap;
+    for (int run = 0; run < D.nrun; run++) {
+      const int pt = sruns[4 * run], pa = sruns[4 * run + 1], b0 = sruns[4 * run + 2], nb = sruns[4 * run + 3];
+      const T* co = scoll + pa * CO_STRIDE;
+      T c1[3], rot1[9];
+      collider_pose(pa, c1, rot1);
+      const bool plane = (int)co[CO_TYPE] == GEOM_PLANE;
+      const T rb1 = co[CO_RBOUND];
+      for (int base = 0; base < nb; base += LPW) {
+        const int pb = b0 + base + sl;
+        bool pass = false;
+        if (base + sl < nb) {
+          T c2[3], rb2;
+          if (pt == PAIR_PLANE_CAPSULE || pt == PAIR_BOX_CAPSULE) { capsule_center(pb, c2); rb2 = C.cap_r + C.cap_hl; }
+          else if (pt == PAIR_SPHERE_BOX) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) c2[k] = off[k] + C.sph_pos[k];
+            rb2 = C.sph_r;
+          } else { T rot[9]; collider_pose(pb, c2, rot); rb2 = scoll[pb * CO_STRIDE + CO_RBOUND]; }
+          T dif[3] = {c2[0] - c1[0], c2[1] - c1[1], c2[2] - c1[2]};
+          if (plane) { T nrm[3] = {rot1[2], rot1[5], rot1[8]}; pass = !(dot3(dif, nrm) > rb2); }
+          else { T bound = rb1 + rb2; pass = !(dot3(dif, dif) > bound * bound); }
+          if (pass && pt == PAIR_BOX_CAPSULE) {
+            // mid-phase (prunes only): the capsule's bounding box in the frame of the box must overlap the box
+            T dl[3], al[3];
+            matTvec3(dl, rot1, dif);
+            matTvec3(al, rot1, sax + 3 * pb);
+#pragma unroll
+            for (int k = 0; k < 3; k++) if (tabs(dl[k]) > co[CO_SIZE + k] + C.cap_r + C.cap_hl * tabs(al[k])) pass = false;
+          }
+        }
+        const unsigned m = gballot(pass);
+        if (pass) {
+          const int slot = ncand + __popc(m & ((1u << sl) - 1));
+          if (slot < cand_cap) cand[slot] = pt | (pa << 3) | (pb << 8); else flags |= SG_ST_CON_FULL_BIT;
+        }
+        ncand += __popc(m);
+      }
+    }
+    if (ncand > cand_cap) ncand = cand_cap;
     const int ncand_w = wmax(ncand);   // also orders the candidate writes before the reads below
     // ---- narrowphase over the candidate list; contacts keep the pair order ----
     int ncon = 0, ncontot = 0, touch = 0;
@@ -770,20 +813,20 @@ struct World2 {
       RawCon<T> rc[2];
       int n = 0, pa = 0, e = -1; T ssign = 0;
       if (ci_ < ncand) {
-        const int p = auxi[L.i_cand + ci_];
-        const int pt = itab(D.io_pair_t)[p]; pa = itab(D.io_pair_a)[p]; const int pb = itab(D.io_pair_b)[p];
-        const T* co = tab(D.o_coll + pa * CO_STRIDE);
+        const int cw = cand[ci_];
+        const int pt = cw & 7; pa = (cw >> 3) & 31; const int pb = cw >> 8;
+        const T* co = scoll + pa * CO_STRIDE;
         T c1[3], rot1[9];
         collider_pose(pa, c1, rot1);
         T size1[3] = {co[CO_SIZE], co[CO_SIZE + 1], co[CO_SIZE + 2]};
         int mask = (int)co[CO_MASK];
         if (pt == PAIR_PLANE_CAPSULE) {
-          T cc[3]; capsule_center(pb, cc, qsl);
-          n = plane_capsule(rc, c1, rot1, cc, tab(D.o_sl_axis) + 3 * pb, C.cap_r, C.cap_hl);
+          T cc[3]; capsule_center(pb, cc);
+          n = plane_capsule(rc, c1, rot1, cc, sax + 3 * pb, C.cap_r, C.cap_hl);
           e = pb; ssign = 1; mask |= C.cap_mask;
         } else if (pt == PAIR_BOX_CAPSULE) {
-          T cc[3]; capsule_center(pb, cc, qsl);
-          n = capsule_box(rc, cc, tab(D.o_sl_axis) + 3 * pb, C.cap_r, C.cap_hl, c1, rot1, size1);
+          T cc[3]; capsule_center(pb, cc);
+          n = capsule_box(rc, cc, sax + 3 * pb, C.cap_r, C.cap_hl, c1, rot1, size1);
           e = pb; ssign = -1; mask |= C.cap_mask;
         } else if (pt == PAIR_SPHERE_BOX) {
           T sc[3];
@@ -792,7 +835,7 @@ struct World2 {
           n = sphere_box(rc[0], sc, C.sph_r, c1, rot1, size1);
           e = -1; mask |= C.sph_mask;
         } else if (pt == PAIR_BOX_BOX) {
-          const T* co2 = tab(D.o_coll + pb * CO_STRIDE);
+          const T* co2 = scoll + pb * CO_STRIDE;
           T c2[3], rot2[9]; collider_pose(pb, c2, rot2);
           T size2[3] = {co2[CO_SIZE], co2[CO_SIZE + 1], co2[CO_SIZE + 2]};
           if (box_box_overlap(c1, rot1, size1, c2, rot2, size2)) flags |= SG_ST_UNSUPPORTED_BIT;
@@ -1580,6 +1623,12 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
     }
     T* tc = reinterpret_cast<T*>(smem_raw + (size_t)nslot * sizeof(Slot<T>));
     for (int i = threadIdx.x; i < D.ns; i += blockDim.x) { tc[i] = K.tab[D.o_sl_tc + i]; tc[D.ns + i] = K.tab[D.o_sl_tciw + i]; tc[2 * D.ns + i] = T(1) / K.tab[D.o_sl_m + i]; }
+    T* ax = tc + 3 * D.ns;
+    for (int i = threadIdx.x; i < 3 * D.ns; i += blockDim.x) ax[i] = K.tab[D.o_sl_axis + i];
+    T* cl = ax + 3 * D.ns;
+    for (int i = threadIdx.x; i < MAXCOLL * CO_STRIDE; i += blockDim.x) cl[i] = K.tab[D.o_coll + i];
+    int* rn = reinterpret_cast<int*>(cl + MAXCOLL * CO_STRIDE);
+    for (int i = threadIdx.x; i < 4 * D.nrun; i += blockDim.x) rn[i] = K.itab[D.io_run + i];
     __syncthreads();
   }
 #if defined(__CUDA_ARCH__)

@@ -767,16 +767,21 @@ struct World2 {
     int* cand = scand();
     const int cand_cap = L.cand_cap;
     for (int run = 0; run < D.nrun; run++) {
-      const int pt = sruns[4 * run], pa = sruns[4 * run + 1], b0 = sruns[4 * run + 2], nb = sruns[4 * run + 3];
+      const int pt = sruns[4 * run], a0 = sruns[4 * run + 1] & 255, na = sruns[4 * run + 1] >> 8, b0 = sruns[4 * run + 2];
+      const int total = na * sruns[4 * run + 3];
+      const bool one = na == 1;                      // one collider against a range of second geoms: fetched once
+      int pa = a0;
       const T* co = scoll + pa * CO_STRIDE;
       T c1[3], rot1[9];
-      collider_pose(pa, c1, rot1);
-      const bool plane = (int)co[CO_TYPE] == GEOM_PLANE;
-      const T rb1 = co[CO_RBOUND];
-      for (int base = 0; base < nb; base += LPW) {
-        const int pb = b0 + base + sl;
+      if (one) collider_pose(pa, c1, rot1);
+      for (int base = 0; base < total; base += LPW) {
+        const int j = base + sl;
+        int pb = b0 + j;
         bool pass = false;
-        if (base + sl < nb) {
+        if (j < total) {
+          if (!one) { const int jb = j / na; pa = a0 + (j - jb * na); pb = b0 + jb; co = scoll + pa * CO_STRIDE; collider_pose(pa, c1, rot1); }
+          const bool plane = (int)co[CO_TYPE] == GEOM_PLANE;
+          const T rb1 = co[CO_RBOUND];
           T c2[3], rb2;
           if (pt == PAIR_PLANE_CAPSULE || pt == PAIR_BOX_CAPSULE) { capsule_center(pb, c2); rb2 = C.cap_r + C.cap_hl; }
           else if (pt == PAIR_SPHERE_BOX) {

@@ -69,7 +69,7 @@ struct PlanDims {
   // offsets into the int table
   int io_kmask, io_row_d1, io_row_d2, io_lev_start, io_dof_rows, io_pair_t, io_pair_a, io_pair_b;
   int io_row_d12;   // nrow: first slider | second slider << 16 (0xffff: none), schedule order
-  int io_run, nrun; // broadphase runs of the pair list: {pair type, collider a, first b, count} (consecutive pairs with b, b+1, ...)
+  int io_run, nrun; // broadphase runs of the pair list: {pair type, first collider | colliders << 8, first second geom, count}
   // per-batch step tables of the level sweep (depend on the lanes per world; appended by sg_api.cu)
   int io_step_d;    // 2*(nstep+1)*lpw ints: {byte offset of d1 | of d2 << 16, byte offset of the row pair | barrier << 31} per slot
   int o_step_iw;    // 2*nstep*lpw reals: {1/m first, 1/m second} per slot
@@ -566,15 +566,26 @@ inline Plan build_plan(const void* blob, size_t nbytes) {
   D.npair = (int)pt.size();
   D.io_pair_t = alloc_i(D.npair); D.io_pair_a = alloc_i(D.npair); D.io_pair_b = alloc_i(D.npair);
   for (int p = 0; p < D.npair; p++) { P.itab[D.io_pair_t + p] = pt[p]; P.itab[D.io_pair_a + p] = pa[p]; P.itab[D.io_pair_b + p] = pb[p]; }
-  // run-length form of the same list (same order): the device broadphase walks runs, so that the collider of a run is
-  // fetched once and the pair tables are not touched at all
+  // run-length form of the same list (same order): a run is a block {type, first collider a0, na, first second geom b0,
+  // nb} standing for the pairs (a0 + i, b0 + j) in the order j-major, i-minor (MuJoCo walks body pairs and, inside a body
+  // pair, geom x geom: a body with two boxes against the shell gives a-minor runs).  The device broadphase walks runs, so
+  // the pair tables are not touched at all.
   {
     std::vector<int> runs;
     for (int p = 0; p < D.npair;) {
-      int n = 1;
-      while (p + n < D.npair && pt[p + n] == pt[p] && pa[p + n] == pa[p] && pb[p + n] == pb[p] + n) n++;
-      runs.push_back(pt[p]); runs.push_back(pa[p]); runs.push_back(pb[p]); runs.push_back(n);
-      p += n;
+      int na = 1;
+      while (p + na < D.npair && pt[p + na] == pt[p] && pb[p + na] == pb[p] && pa[p + na] == pa[p] + na) na++;
+      int nb = 1;
+      for (;;) {
+        const int q = p + nb * na;
+        if (q + na > D.npair) break;
+        bool ok = true;
+        for (int i = 0; i < na && ok; i++) ok = pt[q + i] == pt[p] && pa[q + i] == pa[p] + i && pb[q + i] == pb[p] + nb;
+        if (!ok) break;
+        nb++;
+      }
+      runs.push_back(pt[p]); runs.push_back(pa[p] | (na << 8)); runs.push_back(pb[p]); runs.push_back(nb);
+      p += na * nb;
     }
     D.nrun = (int)runs.size() / 4;
     D.io_run = alloc_i(runs.size());

@@ -230,11 +230,47 @@ template <> __device__ __forceinline__ float tdiv<float>(float a, float b) {
 #endif
 }
 
-// mju_QCQP2 with tdiv (same algorithm as sg_math.cuh qcqp2)
+// square root inside the contact blocks: MUFU.SQRT on the fp32 fast path, IEEE in the verification build
+template <typename T> __device__ __forceinline__ T tfsqrt(T x);
+template <> __device__ __forceinline__ double tfsqrt<double>(double x) { return sqrt(x); }
+template <> __device__ __forceinline__ float tfsqrt<float>(float x) {
+#ifdef __CUDA_ARCH__
+  float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return sqrtf(x);
+#endif
+}
+
+// mju_QCQP2: min 0.5 v'Av + b'v  s.t. |v| <= r  in the friction-scaled variables.
+// Verification build (double): MuJoCo's own iteration (same algorithm as sg_math.cuh qcqp2) -- Newton on
+// |v(la)|^2 - r^2 from la = 0, at most 20 steps, absolute thresholds 1e-10.
+// Fast path (float): the same root of the same secular equation, found by Newton on 1/r - 1/|v(la)| (More-Sorensen:
+// convex and nearly linear in la, so the iterates rise monotonically to the root and 2-3 steps reach float accuracy
+// where MuJoCo's iteration needs 6-20), started from the lower bound |b|/r - trace(A) of the root when that is positive.
+// MuJoCo's thresholds (1e-10 absolute) are below float resolution; the fast path stops at |v| - r <= 2e-6 r.  The
+// caller rescales v onto the cone afterwards, as MuJoCo does.
 template <typename T> __device__ __forceinline__ int qcqp2_fast(T* res, T A11i, T A12i, T A22i, const T* bin, T d0, T d1, T r) {
   T b1 = bin[0] * d0, b2 = bin[1] * d1;
   T A11 = A11i * d0 * d0, A22 = A22i * d1 * d1, A12 = A12i * d0 * d1;
   T la = 0, v1 = 0, v2 = 0;
+  if (sizeof(T) == 4) {
+    const T lb = tdiv(tfsqrt(b1 * b1 + b2 * b2), r) - (A11 + A22);
+    if (lb > T(0)) la = lb;
+    for (int iter = 0; iter < 8; iter++) {
+      T det = (A11 + la) * (A22 + la) - A12 * A12;
+      if (det < T(1e-10)) { res[0] = 0; res[1] = 0; return 0; }
+      T detinv = tdiv(T(1), det), P11 = (A22 + la) * detinv, P22 = (A11 + la) * detinv, P12 = -A12 * detinv;
+      v1 = -P11 * b1 - P12 * b2; v2 = -P12 * b1 - P22 * b2;
+      const T n2 = v1 * v1 + v2 * v2, gap = tfsqrt(n2) - r;
+      if (gap <= T(2e-6) * r) break;
+      const T q = P11 * v1 * v1 + T(2) * P12 * v1 * v2 + P22 * v2 * v2;
+      const T delta = tdiv(n2 * gap, q * r);
+      if (!(delta > T(1e-10))) break;
+      la += delta;
+    }
+    res[0] = v1 * d0; res[1] = v2 * d1;
+    return la != T(0);
+  }
   for (int iter = 0; iter < 20; iter++) {
     T det = (A11 + la) * (A22 + la) - A12 * A12;
     if (det < T(1e-10)) { res[0] = 0; res[1] = 0; return 0; }

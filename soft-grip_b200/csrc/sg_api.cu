@@ -46,6 +46,7 @@ struct sg_batch {
   unsigned char* scratch = nullptr;   // global aux slots of kernel 2 (when aux is not in shared memory)
   std::vector<int> step_d;            // level-sweep step tables of kernel 2 for this batch's lanes per world
   std::vector<double> step_iw;
+  std::vector<int> row_perm;          // plan schedule position -> storage position of the row in this batch's kernel tables
   void* tab = nullptr;        // device table in batch precision
   int* itab = nullptr;
   void *qpos = nullptr, *qvel = nullptr, *warm = nullptr, *act = nullptr, *ctrl = nullptr;
@@ -191,7 +192,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   if (b->lpw != 4 && b->lpw != 8 && b->lpw != 16 && b->lpw != 32) { delete b; return fail("SOFTGRIP_LPW must be 4, 8, 16 or 32"); }
   if (b->kernel == 2) {
     const Plan& P = m->plan;
-    build_step_tables(b->D, P.tab, P.itab, b->lpw, b->esize, b->step_d, b->step_iw);
+    build_step_tables(b->D, P.tab, P.itab, b->lpw, (int)b->esize, b->step_d, b->step_iw, b->row_perm, false);
     b->D.nstep = (int)(b->step_d.size() / (2 * (size_t)b->lpw)) - 1;   // without the trailing dummy step
     b->D.o_step_iw = (int)((P.tab.size() + 3) / 4 * 4);
     b->D.io_step_d = (int)((P.itab.size() + 3) / 4 * 4);

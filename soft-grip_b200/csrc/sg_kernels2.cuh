@@ -1454,7 +1454,9 @@ struct World2 {
       chain_epilogue(cs);
     } else {
       constexpr int TEAMW = LPW / 2 > 0 ? LPW / 2 : 1;       // warps per team (16 worlds)
-      const int warp = threadIdx.x >> 5, team = warp / TEAMW, wit = warp % TEAMW;
+      // the team's chain warp: a different position in every team, so that the chain warps of the CTA's teams sit on
+      // different warp schedulers (warp index modulo 4)
+      const int warp = threadIdx.x >> 5, team = warp / TEAMW, wit = (warp % TEAMW + TEAMW - team % TEAMW) % TEAMW;
       const int bar_id = 1 + team, nthr = 32 * TEAMW;
       World2<T, 2> V(K, smem, 0, false, team, (int)(blockDim.x >> 5) / TEAMW);
       typename World2<T, 2>::ChainState cs;

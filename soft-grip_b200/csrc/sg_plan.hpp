@@ -143,19 +143,25 @@ struct Plan {
 
 #define SG_REQUIRE(cond, msg) do { if (!(cond)) throw std::runtime_error(std::string("unsupported model: ") + msg); } while (0)
 
-// Level sweep tables for `lpw` lanes per world.  The rows (schedule positions p) are list-scheduled onto steps of `lpw`
-// slots: a row is ready once every earlier row (in MuJoCo's sequential order) that shares one of its sliders has run in an
-// earlier step; among the ready rows the ones with the longest chain of dependants go first.  A step carries the
-// "barrier" flag when a row of a later step, up to the next flagged step, depends on one of its rows or of an earlier
-// unflagged step.  The result equals the sequential sweep (rows that share a slider keep their order, rows that do not
-// commute).  Padding slots and the missing second slider of fix rows point at the dummy slider (index ns, inverse
-// mass 0) and the dummy row (index nrow), which the sweep leaves unchanged.
+// Level sweep tables for `lpw` lanes per world.  The rows are list-scheduled onto steps of `lpw` slots: a row is ready
+// once every earlier row (in MuJoCo's sequential order) that shares one of its sliders has run in an earlier step; among
+// the ready rows the ones with the longest chain of dependants go first.  A step carries the "barrier" flag when a row of
+// a later step, up to the next flagged step, depends on one of its rows or of an earlier unflagged step.  The result
+// equals the sequential sweep (rows that share a slider keep their order, rows that do not commute).
+// The sweep is bound by shared-memory wavefronts, so the schedule also avoids bank conflicts: the worlds of a warp sit
+// `lpw` banks apart, hence the accesses of a step are conflict-free when the slider indices (first sliders among each
+// other, second sliders among each other) and the storage positions of the rows are distinct modulo `lpw`.  Rows that
+// are not on the critical path wait for a step where they fit; the storage position of every row (`perm`: schedule
+// position of the plan -> position in the kernel's row arrays) is chosen so that the rows of a step get distinct
+// residues.  Padding slots and the missing second slider of fix rows point at the dummy slider (index ns, inverse mass
+// 0) and the dummy row (position nrow), which the sweep leaves unchanged; their residues are kept free as well.
 // Slot encoding (esize = bytes per real of the kernel precision): {first slider * esize | second slider * esize << 16,
-// row * 2 * esize | barrier << 31}, {1/m first, 1/m second}.
+// row position * 2 * esize | barrier << 31}, {1/m first, 1/m second}.
 inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab, const std::vector<int>& itab, int lpw, int esize,
-                              std::vector<int>& step_d, std::vector<double>& step_iw) {
+                              std::vector<int>& step_d, std::vector<double>& step_iw, std::vector<int>& perm, bool avoid_conflicts = true) {
   step_d.clear(); step_iw.clear();
   const int dummy_d = D.ns, dummy_p = D.nrow, nrow = D.nrow;
+  const int R = lpw < 32 ? lpw : 32;                 // residue modulus: bank distance of the worlds of a warp
   SG_REQUIRE((size_t)(D.ns + 1) * esize <= 0xffff, "too many shell joints for the packed step descriptors");
   // dependency chains per slider, in schedule order (which respects MuJoCo's row order along every slider)
   std::vector<int> last(D.ns, -1), npred(nrow, 0), height(nrow, 1), step_of(nrow, -1);
@@ -179,12 +185,21 @@ inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab,
   while (done < nrow) {
     SG_REQUIRE(!ready.empty(), "cyclic equality schedule");
     std::stable_sort(ready.begin(), ready.end(), [&](int a, int b) { return height[a] != height[b] ? height[a] > height[b] : a < b; });
-    const int take = (int)ready.size() < lpw ? (int)ready.size() : lpw;
-    std::vector<int> cur(ready.begin(), ready.begin() + take);
-    ready.erase(ready.begin(), ready.begin() + take);
+    const int hmax = height[ready[0]];               // rows this tall are on the critical path: they never wait
+    std::vector<int> cur, rest;
+    std::vector<char> use1(R, 0), use2(R, 0);
+    use1[dummy_d % R] = 1; use2[dummy_d % R] = 1;
+    for (int p : ready) {
+      const int d1 = itab[D.io_row_d1 + p], d2 = itab[D.io_row_d2 + p];
+      const bool clash = avoid_conflicts && (use1[d1 % R] || (d2 >= 0 && use2[d2 % R]));
+      if ((int)cur.size() < lpw && (!clash || height[p] == hmax)) {
+        cur.push_back(p); use1[d1 % R] = 1; if (d2 >= 0) use2[d2 % R] = 1;
+      } else rest.push_back(p);
+    }
+    ready.swap(rest);
     for (int p : cur) step_of[p] = (int)steps.size();
     for (int p : cur) for (int s : succ[p]) if (--npred[s] == 0) ready.push_back(s);
-    done += take;
+    done += (int)cur.size();
     steps.push_back(cur);
   }
   const int nstep = (int)steps.size();
@@ -196,12 +211,34 @@ inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab,
     if (need) { flag[s - 1] = 1; synced = s - 1; }
   }
   if (nstep > 0) flag[nstep - 1] = 1;                // the tendon row reads every slider
+  // storage positions: the rows of a step get distinct residues (not the dummy row's), classes filled evenly
+  perm.assign(nrow, -1);
+  {
+    std::vector<int> cap(R, 0), used(R, 0);
+    for (int q = 0; q < nrow; q++) cap[q % R]++;
+    for (int s = 0; s < nstep; s++) {
+      std::vector<char> taken(R, 0);
+      if (avoid_conflicts && (int)steps[s].size() < lpw) taken[dummy_p % R] = 1;
+      for (int p : steps[s]) {
+        int best = -1;
+        for (int pass = 0; pass < 2 && best < 0; pass++)
+          for (int r = 0; r < R; r++) {
+            if (used[r] >= cap[r] || (pass == 0 && taken[r])) continue;
+            if (best < 0 || cap[r] - used[r] > cap[best] - used[best]) best = r;
+          }
+        SG_REQUIRE(best >= 0, "row storage assignment");
+        taken[best] = 1;
+        perm[p] = best + R * used[best]++;
+      }
+    }
+    if (!avoid_conflicts) for (int p = 0; p < nrow; p++) perm[p] = p;
+  }
   for (int s = 0; s < nstep; s++) {
     for (int k = 0; k < lpw; k++) {
       int d1 = dummy_d, d2 = dummy_d, row = dummy_p; double iw1 = 0, iw2 = 0;
       if (k < (int)steps[s].size()) {
         const int p = steps[s][k];
-        d1 = itab[D.io_row_d1 + p]; row = p; iw1 = 1.0 / tab[D.o_sl_m + d1];
+        d1 = itab[D.io_row_d1 + p]; row = perm[p]; iw1 = 1.0 / tab[D.o_sl_m + d1];
         const int dd2 = itab[D.io_row_d2 + p];
         if (dd2 >= 0) { d2 = dd2; iw2 = 1.0 / tab[D.o_sl_m + dd2]; }
       }
@@ -215,6 +252,36 @@ inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab,
     step_d.push_back((int)((unsigned)(dummy_d * esize) | ((unsigned)(dummy_d * esize) << 16))); step_d.push_back(dummy_p * 2 * esize);
     step_iw.push_back(0.0); step_iw.push_back(0.0);
   }
+}
+
+// shared-memory wavefronts of one equality sweep for the tables above (the model the schedule is tuned with; also reported
+// by bench.py): 32-bit accesses to the sliders (2 loads + 2 stores per step), 64-bit loads and 32-bit stores of the rows
+inline long sweep_wavefronts(const std::vector<int>& step_d, int lpw, int esize) {
+  const int wpw = 32 / lpw, nslot = (int)step_d.size() / 2, nstep = nslot / lpw - 1;
+  long total = 0;
+  auto wf32 = [&](const std::vector<long>& word) {   // one address per lane, in 32-bit words
+    int worst = 0;
+    for (int b = 0; b < 32; b++) { std::vector<long> seen; for (long w : word) if (w % 32 == b && std::find(seen.begin(), seen.end(), w) == seen.end()) seen.push_back(w); worst = std::max(worst, (int)seen.size()); }
+    return worst;
+  };
+  for (int s = 0; s < nstep; s++) {
+    std::vector<long> a1, a2, rw;
+    for (int g = 0; g < wpw; g++)
+      for (int k = 0; k < lpw; k++) {
+        const unsigned x = (unsigned)step_d[2 * (s * lpw + k)], y = (unsigned)step_d[2 * (s * lpw + k) + 1] & 0x7fffffffu;
+        const long goff = (long)g * lpw + 4096L * g;   // worlds sit lpw banks apart (plus whole multiples of 32 words)
+        a1.push_back(goff + (x & 0xffff) / esize * (esize / 4)); a2.push_back(goff + (x >> 16) / esize * (esize / 4));
+        rw.push_back(goff + y / 4);
+      }
+    total += 2 * wf32(a1) + 2 * wf32(a2) + wf32(rw);          // loads + stores of the sliders, store of u
+    // 64-bit (float) row load: two half-warps, 16 bank pairs each
+    for (int h = 0; h < 2; h++) {
+      int worst = 0;
+      for (int b = 0; b < 16; b++) { std::vector<long> seen; for (int i = h * 16; i < h * 16 + 16; i++) { const long w = rw[i] / 2; if (w % 16 == b && std::find(seen.begin(), seen.end(), w) == seen.end()) seen.push_back(w); } worst = std::max(worst, (int)seen.size()); }
+      total += worst;
+    }
+  }
+  return total;
 }
 
 inline bool same(const double* a, const double* b, int n) { for (int i = 0; i < n; i++) if (a[i] != b[i]) return false; return true; }

@@ -19,7 +19,9 @@ for cfg in cfgs:
     k, l, a = parts.get("k", 2), parts.get("l", 8), parts.get("a", 0)
     os.environ["SOFTGRIP_KERNEL"] = str(k); os.environ["SOFTGRIP_LPW"] = str(l); os.environ["SOFTGRIP_AUX_SMEM"] = str(a)
     os.environ["SOFTGRIP_QV_SMEM"] = str(parts.get("q", 0))
-    os.environ["SOFTGRIP_TEAM"] = str(parts.get("t", 1))
+    os.environ["SOFTGRIP_TEAM"] = str(parts.get("t", 0))
+    if parts.get("b", 1) == 0: os.environ["SOFTGRIP_NO_BANK_SCHEDULE"] = "1"
+    else: os.environ.pop("SOFTGRIP_NO_BANK_SCHEDULE", None)
     if "n" in parts: os.environ["SOFTGRIP_NW"] = str(parts["n"])
     else: os.environ.pop("SOFTGRIP_NW", None)
     for dt in (torch.float32,):

@@ -121,6 +121,21 @@ extern "C" int sg_model_set_geom_mask(sg_model* m, const int* mask) {
 static void host_tables(const sg_batch* b, std::vector<double>& tab, std::vector<int>& itab) {
   const Plan& P = b->model->plan;
   tab = P.tab; itab = P.itab;
+  if (b->kernel == 2 && !b->row_perm.empty()) {
+    // kernel 2 stores the equality rows at the positions its step schedule chose (bank-conflict-free steps)
+    const PlanDims& D = P.d;
+    const std::vector<int>& perm = b->row_perm;
+    for (int p = 0; p < D.nrow; p++) {
+      const int q = perm[p];
+      itab[D.io_row_d1 + q] = P.itab[D.io_row_d1 + p]; itab[D.io_row_d2 + q] = P.itab[D.io_row_d2 + p];
+      itab[D.io_row_d12 + q] = P.itab[D.io_row_d12 + p];
+      tab[D.o_row_iw + 2 * q] = P.tab[D.o_row_iw + 2 * p]; tab[D.o_row_iw + 2 * q + 1] = P.tab[D.o_row_iw + 2 * p + 1];
+    }
+    for (int i = 0; i < D.ns * MAXDOFROWS; i++) {
+      const int code = P.itab[D.io_dof_rows + i];
+      if (code >= 0) itab[D.io_dof_rows + i] = perm[code >> 1] * 2 + (code & 1);
+    }
+  }
   while (tab.size() % 4) tab.push_back(0.0);
   while (itab.size() % 4) itab.push_back(0);
   tab.insert(tab.end(), b->step_iw.begin(), b->step_iw.end());
@@ -192,7 +207,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   if (b->lpw != 4 && b->lpw != 8 && b->lpw != 16 && b->lpw != 32) { delete b; return fail("SOFTGRIP_LPW must be 4, 8, 16 or 32"); }
   if (b->kernel == 2) {
     const Plan& P = m->plan;
-    build_step_tables(b->D, P.tab, P.itab, b->lpw, (int)b->esize, b->step_d, b->step_iw, b->row_perm, false);
+    build_step_tables(b->D, P.tab, P.itab, b->lpw, (int)b->esize, b->step_d, b->step_iw, b->row_perm, std::getenv("SOFTGRIP_NO_BANK_SCHEDULE") == nullptr);
     b->D.nstep = (int)(b->step_d.size() / (2 * (size_t)b->lpw)) - 1;   // without the trailing dummy step
     b->D.o_step_iw = (int)((P.tab.size() + 3) / 4 * 4);
     b->D.io_step_d = (int)((P.itab.size() + 3) / 4 * 4);
@@ -610,7 +625,7 @@ extern "C" int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int
     const int which = k == "efc_force" ? 0 : (k == "efc_aref" ? 1 : 2);
     std::vector<double> t(nefc);
     const std::vector<int>& sched = b->model->plan.sched_eq;
-    for (int p = 0; p < b->D.nrow; p++) t[sched[p]] = h[eb + which * nefc + p];
+    for (int p = 0; p < b->D.nrow; p++) t[sched[p]] = h[eb + which * nefc + (b->row_perm.empty() ? p : b->row_perm[p])];
     for (int r = b->D.nrow; r < nefc; r++) t[r] = h[eb + which * nefc + r];
     return put(t.data(), nefc);
   }

@@ -365,11 +365,15 @@ struct World2 {
     sax = stim + D.ns;
     scoll = sax + 3 * D.ns;
     sruns = reinterpret_cast<const int*>(scoll + MAXCOLL * CO_STRIDE);
-    unsigned char* base = smem + L.smem_tables + (size_t)(warp * WPW + grp) * L.smem_stride;
+    // storage slot of the group: consecutive slots sit LPW banks apart (Layout2::smem_stride); the two (or more) groups
+    // of a half-warp take slots that are 16 banks apart, so that a 64-bit access of the whole warp to the same row pair
+    // of every world is conflict-free as well
+    const int gslot = WPW > 1 ? (grp % (WPW / 2)) * 2 + grp / (WPW / 2) : 0;
+    unsigned char* base = smem + L.smem_tables + (size_t)(warp * WPW + gslot) * L.smem_stride;
     hot = reinterpret_cast<T*>(base);
     hoti = reinterpret_cast<int*>(hot + L.hotT);
     if (L.aux_in_smem) aux = reinterpret_cast<T*>(hoti + L.hotI);
-    else aux = reinterpret_cast<T*>(K.scratch + (((size_t)blockIdx.x * nwarp + warp) * WPW + grp) * (size_t)L.gs_stride);
+    else aux = reinterpret_cast<T*>(K.scratch + (((size_t)blockIdx.x * nwarp + warp) * WPW + gslot) * (size_t)L.gs_stride);
     auxi = reinterpret_cast<int*>(aux + L.auxT);
   }
 
@@ -1350,8 +1354,8 @@ struct World2 {
 
   // one sweep over the equality block and the volume-tendon row; returns this lane's cost improvement.
   // Step slots (built per lanes-per-world by the host, staged in shared memory by the kernel prologue and shared by all
-  // worlds of the CTA): slot = step * LPW + lane.  Slots that pad a step and rows with a single slider point at the dummy
-  // slider / dummy row, so the loop body has no predication at all.
+  // worlds of the CTA): slot = step * LPW + lane.  Slots that pad a step, and the second slider of fix rows, are
+  // predicated off, so they cost no shared-memory wavefronts (the sweep is bound by those, see sg_plan.hpp).
   // Per row the sweep keeps (u, n) with u = R f - aref and n = -1 / (1/m1 + 1/m2 + R): the residual is a1 - a2 + u, the
   // force change dl = res * n, and since an (unclamped) equality row has zero residual right after its own update, the
   // new u is simply a2' - a1' -- neither R nor f is needed, and there is no division in the sweep.
@@ -1367,12 +1371,15 @@ struct World2 {
 #pragma unroll 2
     for (int st = 0; st < nstep; st++) {
       const Slot<T> sc = sn;
-      sn = ld_slot<T>(slots + (st + 1) * LPW);   // the table carries one dummy step past the end
+      sn = ld_slot<T>(slots + (st + 1) * LPW);   // the table carries one empty step past the end
+      const unsigned o2 = sc.x >> 16;
+      const bool valid = (sc.y & 0x40000000u) != 0u, has2 = o2 != 0xffffu;     // padding slot / fix row: predicated off
       T* pa1 = reinterpret_cast<T*>(avb + (sc.x & 0xffffu));
-      T* pa2 = reinterpret_cast<T*>(avb + (sc.x >> 16));
-      T* pr = reinterpret_cast<T*>(rwb + (sc.y & 0x7fffffffu));
-      T a1 = *pa1, a2 = *pa2;
-      T u, n; ld2(pr, u, n);
+      T* pa2 = reinterpret_cast<T*>(avb + o2);
+      T* pr = reinterpret_cast<T*>(rwb + (sc.y & 0x3fffffffu));
+      T a1 = 0, a2 = 0, u = 0, n = 0;
+      if (valid) { a1 = *pa1; ld2(pr, u, n); }
+      if (has2) a2 = *pa2;
       const T res = (a1 - a2) + u;
       if (GATED) n = done ? T(0) : n;
       const T dl = res * n;
@@ -1380,9 +1387,8 @@ struct World2 {
       a1 += sc.iw1 * dl; a2 -= sc.iw2 * dl;
       T un = a2 - a1;
       if (GATED) un = done ? u : un;
-      *pr = un;
-      *pa1 = a1;
-      *pa2 = a2;
+      if (valid) { *pr = un; *pa1 = a1; }
+      if (has2) *pa2 = a2;
       if ((int)sc.y < 0) __syncwarp();
     }
     return T(-0.5) * acc;

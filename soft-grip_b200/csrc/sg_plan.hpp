@@ -150,19 +150,20 @@ struct Plan {
 // equals the sequential sweep (rows that share a slider keep their order, rows that do not commute).
 // The sweep is bound by shared-memory wavefronts, so the schedule also avoids bank conflicts: the worlds of a warp sit
 // `lpw` banks apart, hence the accesses of a step are conflict-free when the slider indices (first sliders among each
-// other, second sliders among each other) and the storage positions of the rows are distinct modulo `lpw`.  Rows that
-// are not on the critical path wait for a step where they fit; the storage position of every row (`perm`: schedule
-// position of the plan -> position in the kernel's row arrays) is chosen so that the rows of a step get distinct
-// residues.  Padding slots and the missing second slider of fix rows point at the dummy slider (index ns, inverse mass
-// 0) and the dummy row (position nrow), which the sweep leaves unchanged; their residues are kept free as well.
+// other, second sliders among each other) and the storage positions of the rows are distinct modulo `lpw`.  A row with
+// slack waits for a step where it fits (`target` = schedule length the slack is measured against; the caller searches
+// it); the storage position of every row (`perm`: schedule position of the plan -> position in the kernel's row
+// arrays) is chosen so that the rows of a step get distinct residues.  Padding slots and the missing second slider of
+// fix rows are predicated off by the kernel (second-slider offset 0xffff, valid bit clear).
 // Slot encoding (esize = bytes per real of the kernel precision): {first slider * esize | second slider * esize << 16,
-// row position * 2 * esize | barrier << 31}, {1/m first, 1/m second}.
-inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab, const std::vector<int>& itab, int lpw, int esize,
-                              std::vector<int>& step_d, std::vector<double>& step_iw, std::vector<int>& perm, bool avoid_conflicts = true) {
+// row position * 2 * esize | valid << 30 | barrier << 31}, {1/m first, 1/m second}.
+inline int build_step_tables_for(const PlanDims& D, const std::vector<double>& tab, const std::vector<int>& itab, int lpw, int esize,
+                                 int target, std::vector<int>& step_d, std::vector<double>& step_iw, std::vector<int>& perm) {
   step_d.clear(); step_iw.clear();
-  const int dummy_d = D.ns, dummy_p = D.nrow, nrow = D.nrow;
+  const int nrow = D.nrow;
+  const bool avoid = target > 0;
   const int R = lpw < 32 ? lpw : 32;                 // residue modulus: bank distance of the worlds of a warp
-  SG_REQUIRE((size_t)(D.ns + 1) * esize <= 0xffff, "too many shell joints for the packed step descriptors");
+  SG_REQUIRE((size_t)(D.ns + 1) * esize < 0xffff && (size_t)(nrow + 1) * 2 * esize < (1u << 30), "too many shell joints for the packed step descriptors");
   // dependency chains per slider, in schedule order (which respects MuJoCo's row order along every slider)
   std::vector<int> last(D.ns, -1), npred(nrow, 0), height(nrow, 1), step_of(nrow, -1);
   std::vector<std::vector<int>> pred(nrow), succ(nrow);
@@ -185,19 +186,19 @@ inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab,
   while (done < nrow) {
     SG_REQUIRE(!ready.empty(), "cyclic equality schedule");
     std::stable_sort(ready.begin(), ready.end(), [&](int a, int b) { return height[a] != height[b] ? height[a] > height[b] : a < b; });
-    const int hmax = height[ready[0]];               // rows this tall are on the critical path: they never wait
+    const int now = (int)steps.size();
     std::vector<int> cur, rest;
     std::vector<char> use1(R, 0), use2(R, 0);
-    use1[dummy_d % R] = 1; use2[dummy_d % R] = 1;
     for (int p : ready) {
       const int d1 = itab[D.io_row_d1 + p], d2 = itab[D.io_row_d2 + p];
-      const bool clash = avoid_conflicts && (use1[d1 % R] || (d2 >= 0 && use2[d2 % R]));
-      if ((int)cur.size() < lpw && (!clash || height[p] == hmax)) {
+      const bool clash = avoid && (use1[d1 % R] || (d2 >= 0 && use2[d2 % R]));
+      const bool must = now + height[p] >= target;   // no slack left: waiting would lengthen the schedule
+      if ((int)cur.size() < lpw && (!clash || must)) {
         cur.push_back(p); use1[d1 % R] = 1; if (d2 >= 0) use2[d2 % R] = 1;
       } else rest.push_back(p);
     }
     ready.swap(rest);
-    for (int p : cur) step_of[p] = (int)steps.size();
+    for (int p : cur) step_of[p] = now;
     for (int p : cur) for (int s : succ[p]) if (--npred[s] == 0) ready.push_back(s);
     done += (int)cur.size();
     steps.push_back(cur);
@@ -211,14 +212,13 @@ inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab,
     if (need) { flag[s - 1] = 1; synced = s - 1; }
   }
   if (nstep > 0) flag[nstep - 1] = 1;                // the tendon row reads every slider
-  // storage positions: the rows of a step get distinct residues (not the dummy row's), classes filled evenly
+  // storage positions: the rows of a step get distinct residues, classes filled evenly
   perm.assign(nrow, -1);
-  {
+  if (avoid) {
     std::vector<int> cap(R, 0), used(R, 0);
     for (int q = 0; q < nrow; q++) cap[q % R]++;
     for (int s = 0; s < nstep; s++) {
       std::vector<char> taken(R, 0);
-      if (avoid_conflicts && (int)steps[s].size() < lpw) taken[dummy_p % R] = 1;
       for (int p : steps[s]) {
         int best = -1;
         for (int pass = 0; pass < 2 && best < 0; pass++)
@@ -231,57 +231,73 @@ inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab,
         perm[p] = best + R * used[best]++;
       }
     }
-    if (!avoid_conflicts) for (int p = 0; p < nrow; p++) perm[p] = p;
-  }
-  for (int s = 0; s < nstep; s++) {
-    for (int k = 0; k < lpw; k++) {
-      int d1 = dummy_d, d2 = dummy_d, row = dummy_p; double iw1 = 0, iw2 = 0;
-      if (k < (int)steps[s].size()) {
-        const int p = steps[s][k];
-        d1 = itab[D.io_row_d1 + p]; row = perm[p]; iw1 = 1.0 / tab[D.o_sl_m + d1];
-        const int dd2 = itab[D.io_row_d2 + p];
-        if (dd2 >= 0) { d2 = dd2; iw2 = 1.0 / tab[D.o_sl_m + dd2]; }
-      }
-      step_d.push_back((int)((unsigned)(d1 * esize) | ((unsigned)(d2 * esize) << 16)));
-      step_d.push_back((int)((unsigned)(row * 2 * esize) | ((unsigned)flag[s] << 31)));
-      step_iw.push_back(iw1); step_iw.push_back(iw2);
+  } else for (int p = 0; p < nrow; p++) perm[p] = p;
+  auto emit = [&](int p, int fl) {
+    unsigned x = 0xffffffffu, y = (unsigned)fl << 31; double iw1 = 0, iw2 = 0;
+    if (p >= 0) {
+      const int d1 = itab[D.io_row_d1 + p], d2 = itab[D.io_row_d2 + p];
+      iw1 = 1.0 / tab[D.o_sl_m + d1];
+      unsigned o2 = 0xffffu;
+      if (d2 >= 0) { o2 = (unsigned)(d2 * esize); iw2 = 1.0 / tab[D.o_sl_m + d2]; }
+      x = (unsigned)(d1 * esize) | (o2 << 16);
+      y |= (unsigned)(perm[p] * 2 * esize) | (1u << 30);
     }
-  }
-  // one dummy step past the end: the sweep prefetches the next step's descriptors unconditionally
-  for (int k = 0; k < lpw; k++) {
-    step_d.push_back((int)((unsigned)(dummy_d * esize) | ((unsigned)(dummy_d * esize) << 16))); step_d.push_back(dummy_p * 2 * esize);
-    step_iw.push_back(0.0); step_iw.push_back(0.0);
-  }
+    step_d.push_back((int)x); step_d.push_back((int)y); step_iw.push_back(iw1); step_iw.push_back(iw2);
+  };
+  for (int s = 0; s < nstep; s++) for (int k = 0; k < lpw; k++) emit(k < (int)steps[s].size() ? steps[s][k] : -1, flag[s]);
+  // one empty step past the end: the sweep prefetches the next step's descriptors unconditionally
+  for (int k = 0; k < lpw; k++) emit(-1, 0);
+  return nstep;
 }
 
-// shared-memory wavefronts of one equality sweep for the tables above (the model the schedule is tuned with; also reported
-// by bench.py): 32-bit accesses to the sliders (2 loads + 2 stores per step), 64-bit loads and 32-bit stores of the rows
+// shared-memory wavefronts of one equality sweep for the tables above (the model the schedule is tuned with): 32-bit
+// accesses to the sliders (load + store each), 64-bit load and 32-bit store of the row pair.  The two worlds of a
+// half-warp sit 16 banks apart (World2's slot permutation), all worlds of a warp `lpw` banks apart.
 inline long sweep_wavefronts(const std::vector<int>& step_d, int lpw, int esize) {
   const int wpw = 32 / lpw, nslot = (int)step_d.size() / 2, nstep = nslot / lpw - 1;
   long total = 0;
-  auto wf32 = [&](const std::vector<long>& word) {   // one address per lane, in 32-bit words
+  auto worst_bank = [&](const std::vector<long>& word, int lo, int hi, int nbank, int unit) {
     int worst = 0;
-    for (int b = 0; b < 32; b++) { std::vector<long> seen; for (long w : word) if (w % 32 == b && std::find(seen.begin(), seen.end(), w) == seen.end()) seen.push_back(w); worst = std::max(worst, (int)seen.size()); }
+    for (int b = 0; b < nbank; b++) {
+      std::vector<long> seen;
+      for (int i = lo; i < hi; i++) { if (word[i] < 0) continue; const long w = word[i] / unit; if (w % nbank == b && std::find(seen.begin(), seen.end(), w) == seen.end()) seen.push_back(w); }
+      worst = std::max(worst, (int)seen.size());
+    }
     return worst;
   };
   for (int s = 0; s < nstep; s++) {
     std::vector<long> a1, a2, rw;
-    for (int g = 0; g < wpw; g++)
+    for (int g = 0; g < wpw; g++) {
+      const int slot = wpw > 1 ? (g % (wpw / 2)) * 2 + g / (wpw / 2) : 0;
       for (int k = 0; k < lpw; k++) {
-        const unsigned x = (unsigned)step_d[2 * (s * lpw + k)], y = (unsigned)step_d[2 * (s * lpw + k) + 1] & 0x7fffffffu;
-        const long goff = (long)g * lpw + 4096L * g;   // worlds sit lpw banks apart (plus whole multiples of 32 words)
-        a1.push_back(goff + (x & 0xffff) / esize * (esize / 4)); a2.push_back(goff + (x >> 16) / esize * (esize / 4));
-        rw.push_back(goff + y / 4);
+        const unsigned x = (unsigned)step_d[2 * (s * lpw + k)], y = (unsigned)step_d[2 * (s * lpw + k) + 1];
+        const long goff = (long)slot * lpw + 4096L * slot;   // worlds sit lpw banks apart (plus whole multiples of 32 words)
+        const bool valid = (y >> 30) & 1, has2 = (x >> 16) != 0xffffu;
+        a1.push_back(valid ? goff + (x & 0xffff) / 4 : -1); a2.push_back(valid && has2 ? goff + (x >> 16) / 4 : -1);
+        rw.push_back(valid ? goff + (y & 0x3fffffffu) / 4 : -1);
       }
-    total += 2 * wf32(a1) + 2 * wf32(a2) + wf32(rw);          // loads + stores of the sliders, store of u
-    // 64-bit (float) row load: two half-warps, 16 bank pairs each
-    for (int h = 0; h < 2; h++) {
-      int worst = 0;
-      for (int b = 0; b < 16; b++) { std::vector<long> seen; for (int i = h * 16; i < h * 16 + 16; i++) { const long w = rw[i] / 2; if (w % 16 == b && std::find(seen.begin(), seen.end(), w) == seen.end()) seen.push_back(w); } worst = std::max(worst, (int)seen.size()); }
-      total += worst;
     }
+    total += 2 * worst_bank(a1, 0, 32, 32, 1) + 2 * worst_bank(a2, 0, 32, 32, 1) + worst_bank(rw, 0, 32, 32, 1);
+    if (esize == 4) total += worst_bank(rw, 0, 16, 16, 2) + worst_bank(rw, 16, 32, 16, 2);      // 64-bit load: two half-warps
+    else total += worst_bank(rw, 0, 32, 32, 1);
   }
   return total;
+}
+
+// the schedule the kernel runs: the target length (critical path + slack) with the least estimated cost
+inline void build_step_tables(const PlanDims& D, const std::vector<double>& tab, const std::vector<int>& itab, int lpw, int esize,
+                              std::vector<int>& step_d, std::vector<double>& step_iw, std::vector<int>& perm, bool avoid_conflicts = true) {
+  const int base = build_step_tables_for(D, tab, itab, lpw, esize, 0, step_d, step_iw, perm);
+  if (!avoid_conflicts) return;
+  const double per_step = 6.0;                       // fixed cost of a step (issue, barrier) in wavefront units
+  double best_cost = 1e300; int best_target = 0;
+  for (int target = base; target <= base + base / 4 + 4; target++) {
+    std::vector<int> sd, pm; std::vector<double> si;
+    const int n = build_step_tables_for(D, tab, itab, lpw, esize, target, sd, si, pm);
+    const double cost = (double)sweep_wavefronts(sd, lpw, esize) + per_step * n;
+    if (cost < best_cost) { best_cost = cost; best_target = target; }
+  }
+  build_step_tables_for(D, tab, itab, lpw, esize, best_target, step_d, step_iw, perm);
 }
 
 inline bool same(const double* a, const double* b, int n) { for (int i = 0; i < n; i++) if (a[i] != b[i]) return false; return true; }

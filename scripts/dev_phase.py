@@ -1,5 +1,5 @@
 """Dev tool: SM cycles per phase of the step kernel (SOFTGRIP_PROF=1), split into the contact-free settle part and the
-whole episode.  usage: dev_phase.py [model] [W] [configs...]   config = l<lpw>:n<warps>:t<team>"""
+whole episode.  usage: dev_phase.py [model] [W] [configs...]   config = l<lpw>:n<warps>:t<team>:a<aux in shared memory>"""
 import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -13,6 +13,7 @@ dm = batched.DeviceModel(os.path.join(ROOT, "tests", "golden", name + ".sgm"))
 for cfg in cfgs:
     parts = {x[0]: int(x[1:]) for x in cfg.split(":")}
     os.environ["SOFTGRIP_LPW"] = str(parts.get("l", 8)); os.environ["SOFTGRIP_TEAM"] = str(parts.get("t", 0))
+    os.environ["SOFTGRIP_AUX_SMEM"] = str(parts.get("a", 0))
     if "n" in parts: os.environ["SOFTGRIP_NW"] = str(parts["n"])
     else: os.environ.pop("SOFTGRIP_NW", None)
     env = batched.BatchedManEnv(dm, W, dtype=torch.float32, seed=0)

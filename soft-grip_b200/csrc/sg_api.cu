@@ -75,6 +75,8 @@ extern "C" int sg_model_load(const void* blob, size_t nbytes, sg_model** out) {
     if (mc < 32) mc = 32;
     if (mc > 128) mc = 128;
     if (const char* e = std::getenv("SOFTGRIP_MAXCON")) mc = std::atoi(e);
+    if (mc > 255) mc = 255;             // contact index and time slot are 8-bit fields of the schedule entries
+    if (mc < 1) mc = 1;
     m->maxcon_default = mc;
     m->maxcand_default = 256;
     if (const char* e = std::getenv("SOFTGRIP_MAXCAND")) m->maxcand_default = std::atoi(e);

@@ -63,7 +63,7 @@ struct Layout2 {
   int auxT;
   int i_con;             // maxcon : (chain+1) | (slider+1) << 4
   int i_tl;              // maxcon : time | lane << 16
-  int i_order;           // maxcon : contact index | time << 16, segmented by lane
+  int i_order;           // maxcon : contact index | time << 8 | (slider + 1) << 16, segmented by lane
   int i_cand;            // ns : per-slider latest time slot of the contact schedule
   int i_lmask;           // MAXCHAIN : active-limit masks (bit jl: lower, bit 4+jl: upper)
   int auxI;
@@ -285,6 +285,47 @@ template <typename T> __device__ __forceinline__ int qcqp2_fast(T* res, T A11i, 
   }
   res[0] = v1 * d0; res[1] = v2 * d1;
   return la != T(0);
+}
+
+// reciprocal square root for the fast friction update
+__device__ __forceinline__ float trsqrt(float x) {
+#ifdef __CUDA_ARCH__
+  float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+
+// Friction forces of one elliptic contact with the normal force f0 fixed (the QCQP of mj_solPGS followed by the
+// rescaling onto the cone), fp32 fast path.  Same problem as qcqp2_fast + rescale, arranged for latency: the problem is
+// normalised by trace(A); with w = adj(A + la) b, v = -w / det, every step needs |w|^2, det and w' adj w only, so its
+// three special-function ops (1/det, sqrt |w|^2, 1/(Q r)) are independent of each other, and the final rescaling is one
+// more reciprocal square root:  f = -w r / |w|  when the cone is active.
+__device__ __forceinline__ void friction_fast(float& f1, float& f2, float A11i, float A12i, float A22i, float bc0, float bc1, float frc, float f0) {
+  const float d2 = frc * frc;
+  float a11 = A11i * d2, a12 = A12i * d2, a22 = A22i * d2, b1 = bc0 * frc, b2 = bc1 * frc;
+  if (a11 * a22 - a12 * a12 < 1e-10f) { f1 = 0; f2 = 0; return; }       // mju_QCQP2: singular -> zero, inactive
+  const float sc = trcp<float>(a11 + a22), rr = trcp<float>(f0);
+  a11 *= sc; a12 *= sc; a22 *= sc; b1 *= sc; b2 *= sc;
+  float la = tfsqrt<float>(b1 * b1 + b2 * b2) * rr - 1.0f;               // lower bound |b|/r - trace of the root
+  if (!(la > 0.0f)) la = 0.0f;
+  float w1 = 0, w2 = 0, rdet = 0, N2 = 0;
+#pragma unroll 1
+  for (int iter = 0; iter < 8; iter++) {
+    const float c11 = a22 + la, c22 = a11 + la;
+    const float det = c11 * c22 - a12 * a12;
+    w1 = c11 * b1 - a12 * b2; w2 = c22 * b2 - a12 * b1;
+    N2 = w1 * w1 + w2 * w2;
+    const float Q = c11 * w1 * w1 - 2.0f * a12 * w1 * w2 + c22 * w2 * w2;
+    rdet = trcp<float>(det);
+    const float gap = tfsqrt<float>(N2) * rdet - f0;
+    if (gap <= 2e-6f * f0) break;
+    const float delta = N2 * det * trcp<float>(Q * f0) * gap;
+    if (!(delta > 0.0f)) break;
+    la += delta;
+  }
+  const float s = la != 0.0f ? f0 * trsqrt(fmaxf(N2, 1e-30f)) : rdet;   // active: onto the cone; inactive: the free minimiser
+  f1 = -w1 * s * frc; f2 = -w2 * s * frc;
 }
 
 template <typename T> __device__ __forceinline__ T powp(T x, T pw) { return pw == T(2) ? x * x : tpow(x, pw); }
@@ -1183,32 +1224,45 @@ struct World2 {
     __syncwarp();
   }
 
+  // friction forces with the normal force fixed: mju_QCQP2 + rescaling onto the cone (mj_solPGS); the fp32 fast path
+  // solves the same problem with friction_fast
+  __device__ __forceinline__ void friction(T& f1, T& f2, T A11, T A12, T A22, const T* bc, T frc, T f0) {
+    if (sizeof(T) == 4) { float g1, g2; friction_fast(g1, g2, (float)A11, (float)A12, (float)A22, (float)bc[0], (float)bc[1], (float)frc, (float)f0); f1 = T(g1); f2 = T(g2); return; }
+    T vv[2];
+    const int active = qcqp2_fast<T>(vv, A11, A12, A22, bc, frc, frc, f0);
+    if (active) {
+      const T ifr2 = tdiv(T(1), frc * frc);
+      T s = vv[0] * vv[0] * ifr2 + vv[1] * vv[1] * ifr2;
+      s = tsqrt(tdiv(f0 * f0, tmax(T(SG_MINVAL), s)));
+      vv[0] *= s; vv[1] *= s;
+    }
+    f1 = vv[0]; f2 = vv[1];
+  }
   // one elliptic contact block (mj_solPGS inner body, dim 3) on the lane that owns its chain
-  __device__ __forceinline__ T contact_block(T* r, T* ag, bool has_chain, const T* mv) {
+  __device__ __forceinline__ T contact_block(T* r, int e, T* ag, bool has_chain, const T* mv) {
     const int nfd = D.nfd;
+    T ae = 0;
+    if (e >= 0) ae = a()[nfd + e];
     T jg[12], w1[4], w2[4], w3[4];
     ld4(r + CR_JG, jg); ld4(r + CR_JG + 4, jg + 4); ld4(r + CR_JG + 8, jg + 8);
     ld4(r + CR_NS, w1);          // ns0 ns1 ns2 iwe
     ld4(r + CR_AREF, w2);        // aref0 aref1 aref2 R0
     T Aw[8]; ld4(r + CR_A, Aw); ld4(r + CR_A + 4, Aw + 4);   // A00 A01 A02 A11 | A12 A22 R1 e
     ld4(r + CR_F, w3);           // f0 f1 f2 -
-    const int e = (int)Aw[7];
     const T A00 = Aw[0], A01 = Aw[1], A02 = Aw[2], A11 = Aw[3], A12 = Aw[4], A22 = Aw[5];
     const T R0 = w2[3], R1 = Aw[6];
     const T old0 = w3[0], old1 = w3[1], old2 = w3[2];
-    T ae = 0;
-    if (e >= 0) ae = a()[nfd + e];
     T res[3];
     const T Rr[3] = {R0, R1, R1};
     const T fo[3] = {old0, old1, old2};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      T s = w1[k] * ae;
+      T s = Rr[k] * fo[k] - w2[k];
       if (has_chain) {
 #pragma unroll
         for (int jj = 0; jj < MAXCD; jj++) s += jg[4 * k + jj] * ag[jj];
       }
-      res[k] = s - w2[k] + Rr[k] * fo[k];
+      res[k] = s + w1[k] * ae;      // the slider's acceleration arrives last (shared memory)
     }
     T f0 = old0, f1 = old1, f2 = old2;
     if (f0 < T(SG_MINVAL)) {
@@ -1231,18 +1285,7 @@ struct World2 {
       bc[0] = res[1] - (A11 * old1 + A12 * old2) + A01 * (f0 - old0);
       bc[1] = res[2] - (A12 * old1 + A22 * old2) + A02 * (f0 - old0);
       if (f0 < T(SG_MINVAL)) { f1 = 0; f2 = 0; }
-      else {
-        const T frc = C.con_fr;
-        T vv[2];
-        const int active = qcqp2_fast<T>(vv, A11, A12, A22, bc, frc, frc, f0);
-        if (active) {
-          const T ifr2 = tdiv(T(1), frc * frc);
-          T s = vv[0] * vv[0] * ifr2 + vv[1] * vv[1] * ifr2;
-          s = tsqrt(tdiv(f0 * f0, tmax(T(SG_MINVAL), s)));
-          vv[0] *= s; vv[1] *= s;
-        }
-        f1 = vv[0]; f2 = vv[1];
-      }
+      else friction(f1, f2, A11, A12, A22, bc, C.con_fr, f0);
     }
     // cost change, revert if positive
     T d0f = f0 - old0, d1f = f1 - old1, d2f = f2 - old2;
@@ -1289,7 +1332,7 @@ struct World2 {
     int k = 0;
     for (int i = 0; i < ncon; i++) {
       const int tl = auxi[L.i_tl + i];
-      if ((tl >> 16) == sl) { auxi[L.i_order + cs.mystart + k] = i | ((tl & 0xffff) << 16); k++; }
+      if ((tl >> 16) == sl) { auxi[L.i_order + cs.mystart + k] = i | ((tl & 0xff) << 8) | ((auxi[L.i_con + i] >> 4) << 16); k++; }
     }
 #pragma unroll
     for (int jj = 0; jj < MAXCD; jj++) cs.ag[jj] = (cs.chain_lane && jj < D.ncd[sl]) ? a()[D.chain_dof0[sl] + jj] : T(0);
@@ -1307,7 +1350,7 @@ struct World2 {
     if (cnt > 1) entB = order[1];
     if (cnt > 2) entC = order[2];
     const int ent0 = entA;
-    if (cnt > 1 && !L.aux_in_smem) prefetch_l1(crec(entB & 0xffff));
+    if (cnt > 1 && !L.aux_in_smem) prefetch_l1(crec(entB & 0xff));
     if (cs.chain_lane && !done) {
 #pragma unroll
       for (int jl = 0; jl < MAXCD; jl++) {
@@ -1331,18 +1374,19 @@ struct World2 {
     }
     int k = 0;
     for (int t = 1; t <= tmaxw; t++) {
-      if (k < cnt && (entA >> 16) == t) {
-        T* r = crec(entA & 0xffff);
+      if (k < cnt && ((entA >> 8) & 0xff) == t) {
+        T* r = crec(entA & 0xff);
+        const int e = (entA >> 16) - 1;
         k++;
         entA = entB; entB = entC;
-        if (k + 1 < cnt && !L.aux_in_smem) prefetch_l1(crec(entB & 0xffff));
+        if (k + 1 < cnt && !L.aux_in_smem) prefetch_l1(crec(entB & 0xff));
         if (k + 2 < cnt) entC = order[k + 2];
-        impr -= contact_block(r, cs.ag, cs.chain_lane, cs.mv);
+        impr -= contact_block(r, e, cs.ag, cs.chain_lane, cs.mv);
       }
       __syncwarp();
     }
     // next sweep's first entries and record: towards L1 while the equality block is swept
-    if (cnt > 0 && !L.aux_in_smem) { prefetch_l1(order); prefetch_l1(crec(ent0 & 0xffff)); }
+    if (cnt > 0 && !L.aux_in_smem) { prefetch_l1(order); prefetch_l1(crec(ent0 & 0xff)); }
     return impr;
   }
   __device__ void chain_epilogue(const ChainState& cs) {

@@ -10,7 +10,8 @@ W = int(sys.argv[2]) if len(sys.argv) > 2 else 1776
 rows = int(sys.argv[3]) if len(sys.argv) > 3 else 60
 blob = os.path.join(ROOT, "tests", "golden", name + ".sgm")
 env = batched.BatchedManEnv(blob, W, dtype=torch.float32, seed=0)
-ev, val = batched.default_schedule(2) if rows == 200 else batched.default_schedule(2, n_settle=10, n_iter=rows - 10, open_close_div=80)
+nset = int(os.environ.get('PROF_SETTLE', '10'))
+ev, val = batched.default_schedule(2) if rows == 200 else batched.default_schedule(2, n_settle=nset, n_iter=rows - nset, open_close_div=80)
 for rep in range(int(os.environ.get('PROF_REPS', '2'))):
     torch.cuda.synchronize(); t = time.time()
     traj, k, st = env.rollout(schedule=(ev, val))

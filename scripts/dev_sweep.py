@@ -12,7 +12,6 @@ rows = int(sys.argv[3]) if len(sys.argv) > 3 else 60
 cfgs = sys.argv[4:] or ["k1:l32:a1", "k2:l8:a0", "k2:l4:a0", "k2:l16:a0", "k2:l32:a0", "k2:l32:a1", "k2:l16:a1"]
 blob = os.path.join(ROOT, "tests", "golden", name + ".sgm")
 ev, val = batched.default_schedule(2) if rows == 200 else batched.default_schedule(2, n_settle=10, n_iter=rows - 10, open_close_div=(rows - 10) // 2)
-dm = batched.DeviceModel(blob)
 ref = None
 for cfg in cfgs:
     parts = {x[0]: int(x[1:]) for x in cfg.split(":")}
@@ -22,8 +21,13 @@ for cfg in cfgs:
     os.environ["SOFTGRIP_TEAM"] = str(parts.get("t", 0))
     if parts.get("b", 1) == 0: os.environ["SOFTGRIP_NO_BANK_SCHEDULE"] = "1"
     else: os.environ.pop("SOFTGRIP_NO_BANK_SCHEDULE", None)
+    if parts.get("p", 0): os.environ["SOFTGRIP_L2_PERSIST"] = "1"
+    else: os.environ.pop("SOFTGRIP_L2_PERSIST", None)
+    if "m" in parts: os.environ["SOFTGRIP_MAXCON"] = str(parts["m"])
+    else: os.environ.pop("SOFTGRIP_MAXCON", None)
     if "n" in parts: os.environ["SOFTGRIP_NW"] = str(parts["n"])
     else: os.environ.pop("SOFTGRIP_NW", None)
+    dm = batched.DeviceModel(blob)
     for dt in (torch.float32,):
         try:
             env = batched.BatchedManEnv(dm, W, dtype=dt, seed=0)

@@ -606,6 +606,16 @@ extern "C" int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int
   const int ncontot = (int)h[0], nefc = (int)h[1], ncon = (int)h[3], nlim = (int)h[4];
   const std::string k(key);
   auto put = [&](const double* src, int n) { if (out) for (int i = 0; i < n && i < cap; i++) out[i] = src[i]; return n; };
+  if (k == "sweep_schedule") {
+    // host-side tables of the equality sweep (no device data): [nstep, lanes per world, bytes per real, nrow, estimated
+    // shared-memory wavefronts per sweep], the slot descriptors (2 ints per slot, nstep + 1 steps), then the storage
+    // position of every row (plan schedule order)
+    std::vector<double> t = {(double)b->D.nstep, (double)b->lpw, (double)b->esize, (double)b->D.nrow,
+                             (double)sweep_wavefronts(b->step_d, b->lpw, (int)b->esize)};
+    for (int v : b->step_d) t.push_back((double)(unsigned)v);
+    for (int v : b->row_perm) t.push_back((double)v);
+    return put(t.data(), (int)t.size());
+  }
   auto scalar = [&](double v) { if (out && cap > 0) out[0] = v; return 1; };
   if (k == "ncon") return scalar(ncontot);
   if (k == "nefc") return scalar(nefc);

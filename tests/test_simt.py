@@ -203,3 +203,74 @@ def test_emulated_other_models_first_steps(emu, make_world, name):
         assert rel(q1[0], oq) < 1e-8 and rel(v1[0], ov) < 1e-8 and rel(qacc[0], oacc) < 1e-8, step
     assert step >= 5
     env.close()
+
+
+def _decode_schedule(env):
+    t = env.debug("sweep_schedule")
+    nstep, lpw, esize, nrow = (int(x) for x in t[:4])
+    wavefronts = int(t[4])
+    sd = t[5:5 + 2 * (nstep + 1) * lpw].astype(np.uint64).reshape(nstep + 1, lpw, 2)
+    perm = t[5 + 2 * (nstep + 1) * lpw:].astype(int)
+    return nstep, lpw, esize, nrow, wavefronts, sd, perm
+
+
+@pytest.mark.parametrize("model,lpw,prec", [("softbox", 8, 32), ("softbox", 4, 32), ("softbox", 16, 64), ("softball", 8, 32), ("softcylinder", 8, 64)])
+def test_equality_sweep_schedule_is_a_valid_gauss_seidel_order(emu, model, lpw, prec):
+    """Host logic of the equality sweep (sg_plan.hpp build_step_tables): every row is swept exactly once, rows of one step
+    share no slider, rows that share a slider keep MuJoCo's order with a barrier in between, the storage positions are a
+    permutation, and the conflict-aware schedule costs no more shared-memory wavefronts than the plain list schedule."""
+    import importlib
+    mjcf = importlib.import_module("soft-grip_b200.mjcf")
+    A = mjcf.load_blob(blob_path(model)).arrays
+    env = emu.EmuBatch(blob_path(model), 2, prec=prec, lpw=lpw, team=0)
+    nstep, lpw_, esize, nrow, wavefronts, sd, perm = _decode_schedule(env)
+    assert lpw_ == lpw and esize == prec // 8 and nrow == len(A["eq_obj1id"]) - 1
+    assert sorted(perm.tolist()) == list(range(nrow))
+    nfd = int((A["jnt_type"] == 3).sum())                      # hinge joints of the fingers come first
+    key_to_eq = {}
+    for r in range(nrow):
+        d1, d2 = int(A["eq_obj1id"][r]) - nfd, int(A["eq_obj2id"][r])
+        key_to_eq[(d1, d2 - nfd if d2 >= 0 else -1)] = r
+    assert len(key_to_eq) == nrow
+    step_of, seen_pos, flags = {}, set(), []
+    for s in range(nstep):
+        used = set()
+        flags.append(int(sd[s, 0, 1]) >> 31)
+        for k in range(lpw):
+            x, y = int(sd[s, k, 0]), int(sd[s, k, 1])
+            assert (y >> 31) == flags[-1]                      # the barrier flag is uniform over the step
+            if not (y >> 30) & 1:
+                continue
+            d1 = (x & 0xffff) // esize
+            d2 = (x >> 16) // esize if (x >> 16) != 0xffff else -1
+            pos = (y & 0x3fffffff) // (2 * esize)
+            assert pos not in seen_pos and 0 <= pos < nrow
+            seen_pos.add(pos)
+            assert d1 not in used and d2 not in used           # rows of a step touch disjoint sliders
+            used.add(d1)
+            if d2 >= 0:
+                used.add(d2)
+            r = key_to_eq[(d1, d2)]
+            assert r not in step_of
+            step_of[r] = s
+    assert len(step_of) == nrow and flags[-1] == 1
+    # the empty step past the end only pads the descriptor prefetch
+    assert all(not (int(sd[nstep, k, 1]) >> 30) & 1 for k in range(lpw))
+    last = {}
+    for r in range(nrow):                                      # MuJoCo's sequential order
+        for d in (int(A["eq_obj1id"][r]) - nfd, int(A["eq_obj2id"][r]) - nfd if A["eq_obj2id"][r] >= 0 else None):
+            if d is None:
+                continue
+            if d in last:
+                q = last[d]
+                assert step_of[q] < step_of[r]
+                assert any(flags[s] for s in range(step_of[q], step_of[r]))
+            last[d] = r
+    os.environ["SOFTGRIP_NO_BANK_SCHEDULE"] = "1"
+    try:
+        plain = emu.EmuBatch(blob_path(model), 2, prec=prec, lpw=lpw, team=0)
+        nstep0, _, _, _, wavefronts0, _, perm0 = _decode_schedule(plain)
+    finally:
+        del os.environ["SOFTGRIP_NO_BANK_SCHEDULE"]
+    assert perm0.tolist() == list(range(nrow))
+    assert wavefronts + 6 * nstep <= wavefronts0 + 6 * nstep0

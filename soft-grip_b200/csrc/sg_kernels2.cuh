@@ -90,8 +90,9 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };   // keep every array 16-byte aligned (float4 loads)
   auto pack = [&](int n) { int r = o; o += n; return r; };               // scalar-access arrays: no padding (shared memory is the
                                                                          // occupancy limit, every 16 bytes per world count)
+  L.row2 = pack(2 * (D.nrow + 1));       // 2-vector loads; at offset 0 so that the sweep addresses the pairs off the world's base register
+  o = (o + 3) & ~3;
   L.minv = take(16 * MAXCHAIN);          // 4-vector loads
-  L.row2 = pack(2 * (D.nrow + 1));       // 2-vector loads (even offset)
   L.a = pack(D.nv + 1); L.hlim = pack(4 * MAXFD); L.h_impr = pack(1);
   L.qv_in_smem = qv_in_smem;
   if (qv_in_smem) { L.hq = pack(D.nv); L.hv = pack(D.nv); }
@@ -1407,7 +1408,7 @@ struct World2 {
   __device__ __forceinline__ T equality_rows(bool done) {
     const int nstep = D.nstep;
     char* avb = reinterpret_cast<char*>(a() + D.nfd);
-    char* rwb = reinterpret_cast<char*>(hot + L.row2);
+    char* rwb = reinterpret_cast<char*>(hot);     // Layout2::row2 == 0 (make_layout2)
     T acc = 0;                                   // sum of res * dl = -2 * cost improvement
     // one row per lane per step, a warp barrier where the schedule asks for one.  The next step's slot is fetched
     // before the barrier so that its latency overlaps this step's arithmetic.
@@ -1433,7 +1434,9 @@ struct World2 {
       if (GATED) un = done ? u : un;
       if (valid) { *pr = un; *pa1 = a1; }
       if (has2) *pa2 = a2;
-      if ((int)sc.y < 0) __syncwarp();
+      // nearly every step of the 8-lane schedules ends a dependency level: an unconditional barrier is cheaper than
+      // testing the flag; narrower worlds have runs of independent steps that are allowed to overlap
+      if (LPW >= 8 || (int)sc.y < 0) __syncwarp();
     }
     return T(-0.5) * acc;
   }

@@ -225,7 +225,8 @@ template <typename T> __device__ __forceinline__ T tdiv(T a, T b);
 template <> __device__ __forceinline__ double tdiv<double>(double a, double b) { return a / b; }
 template <> __device__ __forceinline__ float tdiv<float>(float a, float b) {
 #ifdef __CUDA_ARCH__
-  return __fdividef(a, b);
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b)); return a * r;   // one MUFU + one FMUL (no range scaling:
+                                                                                  // every divisor here is guarded against tiny values)
 #else
   return a / b;
 #endif

@@ -133,9 +133,14 @@ static void host_tables(const sg_batch* b, std::vector<double>& tab, std::vector
       itab[D.io_row_d12 + q] = P.itab[D.io_row_d12 + p];
       tab[D.o_row_iw + 2 * q] = P.tab[D.o_row_iw + 2 * p]; tab[D.o_row_iw + 2 * q + 1] = P.tab[D.o_row_iw + 2 * p + 1];
     }
+    // rows of each slider for the warm start: row position | other slider << 12 (0xfff: none) | "second slider" << 24
     for (int i = 0; i < D.ns * MAXDOFROWS; i++) {
       const int code = P.itab[D.io_dof_rows + i];
-      if (code >= 0) itab[D.io_dof_rows + i] = perm[code >> 1] * 2 + (code & 1);
+      if (code < 0) continue;
+      const int p = code >> 1, second = code & 1;
+      const int d1 = P.itab[D.io_row_d1 + p], d2 = P.itab[D.io_row_d2 + p];
+      const int other = second ? d1 : (d2 >= 0 ? d2 : 0xfff);
+      itab[D.io_dof_rows + i] = perm[p] | (other << 12) | (second << 24);
     }
   }
   while (tab.size() % 4) tab.push_back(0.0);
@@ -243,6 +248,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       if (b->smem2 <= prop.sharedMemPerBlockOptin || b->nwarp == 1) break;
       b->nwarp -= 1;                       // largest CTA that fits
     }
+    if (b->D.nrow >= 0xfff || b->D.ns >= 0xfff) { delete b; return fail("sg_batch_create: too many equality rows or shell joints for the packed warm-start table"); }
     if (b->L2.cand_cap < 16) { delete b; return fail("sg_batch_create: the collision scratch (the equality-row pairs of one world) is too small for this model"); }
     b->team = 0;
     if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) != 0 && b->lpw >= 4 && b->nwarp % (b->lpw / 2) == 0) b->team = 1; }

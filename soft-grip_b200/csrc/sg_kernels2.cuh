@@ -132,9 +132,9 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw
     if (L.cand_cap > D.maxcand) L.cand_cap = D.maxcand;
   }
   // CTA-shared tables: step slots | tendon coefficients, coefficient / mass, 1 / mass (ns each) | slider axes (3 ns) |
-  // collider table | broadphase runs
+  // collider table | broadphase runs | row -> sliders
   L.smem_tables = (int)(((size_t)(D.nstep + 1) * lpw * (8 + 2 * sizeof(T)) + (6 * (size_t)D.ns + (size_t)MAXCOLL * CO_STRIDE) * sizeof(T) +
-                         4 * (size_t)D.nrun * sizeof(int) + 127) & ~(size_t)127);
+                         (4 * (size_t)D.nrun + (size_t)D.nrow) * sizeof(int) + 127) & ~(size_t)127);
   return L;
 }
 
@@ -392,6 +392,7 @@ struct World2 {
   const T* sax;           // CTA-shared slider axes (3 per slider)
   const T* scoll;         // CTA-shared collider table
   const int* sruns;       // CTA-shared broadphase runs
+  const int* srd;         // CTA-shared row -> (first slider | second slider << 16, 0xffff: none), storage order
   __device__ __forceinline__ T stiw(int e) const { return stim[e]; }
 
   // vwarp / vnwarp: position of this warp's worlds in the CTA in units of WPW worlds (the real warp index, except
@@ -408,6 +409,7 @@ struct World2 {
     sax = stim + D.ns;
     scoll = sax + 3 * D.ns;
     sruns = reinterpret_cast<const int*>(scoll + MAXCOLL * CO_STRIDE);
+    srd = sruns + 4 * D.nrun;
     // storage slot of the group: consecutive slots sit LPW banks apart (Layout2::smem_stride); the two (or more) groups
     // of a half-warp take slots that are 16 banks apart, so that a 64-bit access of the whole warp to the same row pair
     // of every world is conflict-free as well
@@ -1026,7 +1028,7 @@ struct World2 {
       qsp[e] = f * stiw(e);
     }
     // joint-equality rows in schedule order: row2 = (aref, R) until the warm start turns aref into u
-    const int* __restrict__ rd = itab(D.io_row_d12);
+    const int* __restrict__ rd = srd;
     const T* __restrict__ siwt = tab(D.o_sl_iw);
     T* __restrict__ row2 = hot + L.row2;
 #pragma unroll 4
@@ -1103,7 +1105,7 @@ struct World2 {
   __device__ void warmstart(Tendon& tn, ChainRows& cr) {
     const int nfd = D.nfd, ns = D.ns;
     const int ncon = misc(M2_NCON);
-    const int* rd = itab(D.io_row_d12);
+    const int* rd = srd;
     T* row2 = hot + L.row2;
     T* jtf = aux + L.jtf;
     // dual cost = sum_rows (0.5 R f^2 - f aref) + (J^T f).qacc_smooth + 0.5 (J^T f)' M^-1 (J^T f): the middle term is
@@ -1115,16 +1117,18 @@ struct World2 {
       const int* dr = itab(D.io_dof_rows) + e * MAXDOFROWS;
       T s = 0;
 #pragma unroll
+      const T ae = a()[nfd + e];
       for (int k = 0; k < MAXDOFROWS; k++) {
+        // entry (sg_api.cu host_tables): row position | other slider << 12 (0xfff: none) | "e is the second slider" << 24
         const int code = dr[k];
         if (code >= 0) {
-          const int p = code >> 1;
-          const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
-          T ja = a()[nfd + d1];
-          if (d2 != 0xffff) ja -= a()[nfd + d2];
+          const int p = code & 0xfff, other = (code >> 12) & 0xfff;
+          const bool second = (code >> 24) & 1;
+          const T ao = other != 0xfff ? a()[nfd + other] : T(0);
+          const T ja = second ? ao - ae : ae - ao;
           T ar, R; ld2(row2 + 2 * p, ar, R);
           const T f = -(T(1) / R) * (ja - ar);
-          if (code & 1) s -= f;
+          if (second) s -= f;
           else { s += f; cost += f * (T(0.5) * R * f - ar); }   // the row's own cost: counted once, by its first dof
         }
       }
@@ -1726,6 +1730,7 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
     for (int i = threadIdx.x; i < MAXCOLL * CO_STRIDE; i += blockDim.x) cl[i] = K.tab[D.o_coll + i];
     int* rn = reinterpret_cast<int*>(cl + MAXCOLL * CO_STRIDE);
     for (int i = threadIdx.x; i < 4 * D.nrun; i += blockDim.x) rn[i] = K.itab[D.io_run + i];
+    for (int i = threadIdx.x; i < D.nrow; i += blockDim.x) rn[4 * D.nrun + i] = K.itab[D.io_row_d12 + i];
     __syncthreads();
   }
 #if defined(__CUDA_ARCH__)

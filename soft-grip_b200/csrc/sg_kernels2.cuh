@@ -64,7 +64,7 @@ struct Layout2 {
   int i_con;             // maxcon : (chain+1) | (slider+1) << 4
   int i_tl;              // maxcon : time | lane << 16
   int i_order;           // maxcon : contact index | time << 8 | (slider + 1) << 16, segmented by lane
-  int i_cand;            // ns : per-slider latest time slot of the contact schedule
+  int i_cand;            // (unused since the schedule's time slots moved to the shared-memory scratch)
   int i_lmask;           // MAXCHAIN : active-limit masks (bit jl: lower, bit 4+jl: upper)
   int auxI;
   int aux_in_smem;
@@ -123,7 +123,7 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw
   L.gs_stride = aux_in_smem ? 0 : (int)((aux + 127) & ~(size_t)127);
   {
     int so = 0;
-    L.sc_cen = so; so += 3 * D.ns;
+    L.sc_cen = so; so += 3 * D.ns > D.ns + 32 ? 3 * D.ns : D.ns + 32;   // later reused for the contact schedule's time slots
     L.sc_gbox = so; so += 12 * MAXCHAIN * MAXCB;
     L.sc_gaxis = so; so += 3 * MAXFD;
     L.sc_ganchor = so; so += 3 * MAXFD;
@@ -958,18 +958,20 @@ struct World2 {
     // (blocks against static colliders: the remaining lanes, round robin); its time slot is one more than the
     // latest earlier block on the same lane or on the same slider -- exactly the dependencies of the
     // sequential sweep of mj_solPGS, so the result equals the sequential one. ----
-    int* lastt = auxi + L.i_cand;     // per-slider latest time slot (the candidate list is dead by now)
+    // per-slider and per-lane latest time slots: in the scratch of the capsule centres, which are dead by now
+    int* lastt = reinterpret_cast<int*>(scr(L.sc_cen));
+    int* lanet = lastt + D.ns;
     const int clpw = K.team ? 2 : LPW;                            // lanes that sweep this world's limit/contact rows
     const int nfree = clpw > MAXCHAIN ? clpw - MAXCHAIN : 0;
-    for (int i = sl; i < ncon; i += LPW) { const int e = (auxi[L.i_con + i] >> 4) - 1; if (e >= 0) lastt[e] = 0; }
-    __syncwarp();
-    int* lanet = auxi + L.i_order;    // per-lane latest time slot (the order list is built later, in pgs())
+    for (int e = sl; e < D.ns; e += LPW) lastt[e] = 0;
     lanet[sl] = 0;
     __syncwarp();
     if (sl == 0) {
       int tmax_ = 0, nstat = 0;
+      int ce_next = ncon > 0 ? auxi[L.i_con] : 0;
       for (int i = 0; i < ncon; i++) {
-        const int ce = auxi[L.i_con + i];
+        const int ce = ce_next;
+        if (i + 1 < ncon) ce_next = auxi[L.i_con + i + 1];       // the record index list lives in the global scratch
         const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
         int ln;
         if (c >= 0) ln = c % clpw;
@@ -1175,19 +1177,40 @@ struct World2 {
       for (int k = 0; k < 3; k++) { r[CR_F + k] = f[k]; cost += f[k] * (T(0.5) * Rr[k] * f[k] - r[CR_AREF + k]); }
     }
     __syncwarp();
-    // J^T f of the contacts, added after the limits: serial in row order on one lane (deterministic)
-    if (sl == 0) {
+    // J^T f of the contacts, added after the limits.  Deterministic without atomics: the contacts of slider e are
+    // summed, in contact order, by lane e % LPW (sliders are private to that lane); the finger-dof parts are kept in
+    // registers per lane and then reduced over the lanes in a fixed order.
+    {
+      T gd[MAXCHAIN][MAXCD];
+#pragma unroll
+      for (int c = 0; c < MAXCHAIN; c++)
+#pragma unroll
+        for (int jj = 0; jj < MAXCD; jj++) gd[c][jj] = 0;
       for (int i = 0; i < ncon; i++) {
         const int ce = auxi[L.i_con + i];
         const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
+        if ((e >= 0 ? e : i) % LPW != sl) continue;
         const T* r = crec(i);
-        const T* f = r + CR_F;
-        if (e >= 0) jtf[nfd + e] += r[CR_NS] * f[0] + r[CR_NS + 1] * f[1] + r[CR_NS + 2] * f[2];
+        T jg[12], w1[4], f[4];
+        ld4(r + CR_NS, w1); ld4(r + CR_F, f);
+        if (e >= 0) jtf[nfd + e] += w1[0] * f[0] + w1[1] * f[1] + w1[2] * f[2];
         if (c >= 0) {
-          const int d0 = D.chain_dof0[c];
-          for (int jj = 0; jj < D.ncd[c]; jj++) jtf[d0 + jj] += r[CR_JG + jj] * f[0] + r[CR_JG + 4 + jj] * f[1] + r[CR_JG + 8 + jj] * f[2];
+          ld4(r + CR_JG, jg); ld4(r + CR_JG + 4, jg + 4); ld4(r + CR_JG + 8, jg + 8);
+#pragma unroll
+          for (int cc = 0; cc < MAXCHAIN; cc++)
+            if (cc == c) {
+#pragma unroll
+              for (int jj = 0; jj < MAXCD; jj++) gd[cc][jj] += jg[jj] * f[0] + jg[4 + jj] * f[1] + jg[8 + jj] * f[2];
+            }
         }
       }
+#pragma unroll
+      for (int c = 0; c < MAXCHAIN; c++)
+#pragma unroll
+        for (int jj = 0; jj < MAXCD; jj++) {
+          const T tot = gsum(gd[c][jj]);
+          if (sl == 0 && c < D.nchain && jj < D.ncd[c]) jtf[D.chain_dof0[c] + jj] += tot;
+        }
     }
     __syncwarp();
     // (J^T f).qacc_smooth + 0.5 (J^T f)' M^-1 (J^T f)

@@ -40,7 +40,7 @@ namespace sg {
 
 // contact record: 32 words of T, 16-byte aligned groups
 enum { CR_JG = 0 /*12*/, CR_NS = 12 /*3*/, CR_IWE = 15, CR_AREF = 16 /*3*/, CR_R0 = 19, CR_A = 20 /*6: 00 01 02 11 12 22*/,
-       CR_R1 = 26, CR_E = 27 /*slider index as a real, -1: none*/, CR_F = 28 /*3*/, CR_STRIDE = 32 };
+       CR_R1 = 26, CR_E = 27 /*slider index as a real, -1: none*/, CR_F = 28 /*3, then the friction multiplier*/, CR_STRIDE = 32 };
 
 // per-world memory plan.  Offsets are in elements (T for the real arrays, int for the int arrays).
 struct Layout2 {
@@ -303,14 +303,18 @@ __device__ __forceinline__ float trsqrt(float x) {
 // normalised by trace(A); with w = adj(A + la) b, v = -w / det, every step needs |w|^2, det and w' adj w only, so its
 // three special-function ops (1/det, sqrt |w|^2, 1/(Q r)) are independent of each other, and the final rescaling is one
 // more reciprocal square root:  f = -w r / |w|  when the cone is active.
-__device__ __forceinline__ void friction_fast(float& f1, float& f2, float A11i, float A12i, float A22i, float bc0, float bc1, float frc, float f0) {
+__device__ __forceinline__ void friction_fast(float& f1, float& f2, float& la_io, float A11i, float A12i, float A22i, float bc0, float bc1, float frc, float f0) {
   const float d2 = frc * frc;
   float a11 = A11i * d2, a12 = A12i * d2, a22 = A22i * d2, b1 = bc0 * frc, b2 = bc1 * frc;
-  if (a11 * a22 - a12 * a12 < 1e-10f) { f1 = 0; f2 = 0; return; }       // mju_QCQP2: singular -> zero, inactive
+  if (a11 * a22 - a12 * a12 < 1e-10f) { f1 = 0; f2 = 0; la_io = 0; return; }       // mju_QCQP2: singular -> zero, inactive
   const float sc = trcp<float>(a11 + a22), rr = trcp<float>(f0);
   a11 *= sc; a12 *= sc; a22 *= sc; b1 *= sc; b2 *= sc;
-  float la = tfsqrt<float>(b1 * b1 + b2 * b2) * rr - 1.0f;               // lower bound |b|/r - trace of the root
-  if (!(la > 0.0f)) la = 0.0f;
+  float lo = tfsqrt<float>(b1 * b1 + b2 * b2) * rr - 1.0f;               // lower bound |b|/r - trace of the root
+  if (!(lo > 0.0f)) lo = 0.0f;
+  // start from the root of the previous sweep (la_io, in the same normalised units; 0 on the first sweep) when it lies
+  // above the bound: the problem changes little between sweeps, and a start to the right of the root costs one extra step
+  // (the tangent of the convex function lands left of the root, from where the iterates rise monotonically)
+  float la = fmaxf(lo, la_io);
   float w1 = 0, w2 = 0, rdet = 0, N2 = 0;
 #pragma unroll 1
   for (int iter = 0; iter < 8; iter++) {
@@ -321,13 +325,16 @@ __device__ __forceinline__ void friction_fast(float& f1, float& f2, float A11i, 
     const float Q = c11 * w1 * w1 - 2.0f * a12 * w1 * w2 + c22 * w2 * w2;
     rdet = trcp<float>(det);
     const float gap = tfsqrt<float>(N2) * rdet - f0;
-    if (gap <= 2e-6f * f0) break;
-    const float delta = N2 * det * trcp<float>(Q * f0) * gap;
-    if (!(delta > 0.0f)) break;
-    la += delta;
+    if (fabsf(gap) <= 2e-6f * f0) break;                 // on the cone
+    if (gap < 0.0f && la <= lo) break;                   // inside the cone at the lowest admissible la (inactive when lo = 0)
+    float nl = la + N2 * det * trcp<float>(Q * f0) * gap;
+    if (!(nl > lo)) nl = lo;
+    if (nl == la) break;
+    la = nl;
   }
   const float s = la != 0.0f ? f0 * trsqrt(fmaxf(N2, 1e-30f)) : rdet;   // active: onto the cone; inactive: the free minimiser
   f1 = -w1 * s * frc; f2 = -w2 * s * frc;
+  la_io = la;
 }
 
 template <typename T> __device__ __forceinline__ T powp(T x, T pw) { return pw == T(2) ? x * x : tpow(x, pw); }
@@ -352,6 +359,13 @@ template <> __device__ __forceinline__ void ld4<float>(const float* p, float* o)
 template <> __device__ __forceinline__ void ld4<double>(const double* p, double* o) {
   const double2 v0 = *reinterpret_cast<const double2*>(p), v1 = *reinterpret_cast<const double2*>(p + 2);
   o[0] = v0.x; o[1] = v0.y; o[2] = v1.x; o[3] = v1.y;
+}
+template <typename T> __device__ __forceinline__ void st4(T* p, T a, T b, T c, T d);
+template <> __device__ __forceinline__ void st4<float>(float* p, float a, float b, float c, float d) {
+  float4 v; v.x = a; v.y = b; v.z = c; v.w = d; *reinterpret_cast<float4*>(p) = v;
+}
+template <> __device__ __forceinline__ void st4<double>(double* p, double a, double b, double c, double d) {
+  double2 v0, v1; v0.x = a; v0.y = b; v1.x = c; v1.y = d; *reinterpret_cast<double2*>(p) = v0; *reinterpret_cast<double2*>(p + 2) = v1;
 }
 template <typename T> __device__ __forceinline__ void ld2(const T* p, T& x, T& y);
 template <> __device__ __forceinline__ void ld2<float>(const float* p, float& x, float& y) { const float2 v = *reinterpret_cast<const float2*>(p); x = v.x; y = v.y; }
@@ -779,7 +793,7 @@ struct World2 {
     }
 #pragma unroll
     for (int r = 0; r < 3; r++) cr[CR_NS + r] = ns[r];
-    cr[CR_IWE] = iw_e; cr[CR_E] = T(e);
+    cr[CR_IWE] = iw_e; cr[CR_E] = T(e); cr[CR_F + 3] = 0;     // word 31: friction multiplier of the previous sweep
     const T imp = impedance2<T>(C.con_si, rc.dist);
     const T R0 = tmax(T(SG_MINVAL), (T(1) - imp) * biw / imp);
     const T R1 = R0 / tmax(T(SG_MINVAL), C.impratio);
@@ -1255,8 +1269,12 @@ struct World2 {
 
   // friction forces with the normal force fixed: mju_QCQP2 + rescaling onto the cone (mj_solPGS); the fp32 fast path
   // solves the same problem with friction_fast
-  __device__ __forceinline__ void friction(T& f1, T& f2, T A11, T A12, T A22, const T* bc, T frc, T f0) {
-    if (sizeof(T) == 4) { float g1, g2; friction_fast(g1, g2, (float)A11, (float)A12, (float)A22, (float)bc[0], (float)bc[1], (float)frc, (float)f0); f1 = T(g1); f2 = T(g2); return; }
+  __device__ __forceinline__ void friction(T& f1, T& f2, T& la, T A11, T A12, T A22, const T* bc, T frc, T f0) {
+    if (sizeof(T) == 4) {
+      float g1, g2, gl = (float)la;
+      friction_fast(g1, g2, gl, (float)A11, (float)A12, (float)A22, (float)bc[0], (float)bc[1], (float)frc, (float)f0);
+      f1 = T(g1); f2 = T(g2); la = T(gl); return;
+    }
     T vv[2];
     const int active = qcqp2_fast<T>(vv, A11, A12, A22, bc, frc, frc, f0);
     if (active) {
@@ -1281,6 +1299,7 @@ struct World2 {
     const T A00 = Aw[0], A01 = Aw[1], A02 = Aw[2], A11 = Aw[3], A12 = Aw[4], A22 = Aw[5];
     const T R0 = w2[3], R1 = Aw[6];
     const T old0 = w3[0], old1 = w3[1], old2 = w3[2];
+    T la = w3[3];                // friction multiplier of the previous sweep (fp32 fast path's warm start)
     T res[3];
     const T Rr[3] = {R0, R1, R1};
     const T fo[3] = {old0, old1, old2};
@@ -1313,15 +1332,15 @@ struct World2 {
       T bc[2];
       bc[0] = res[1] - (A11 * old1 + A12 * old2) + A01 * (f0 - old0);
       bc[1] = res[2] - (A12 * old1 + A22 * old2) + A02 * (f0 - old0);
-      if (f0 < T(SG_MINVAL)) { f1 = 0; f2 = 0; }
-      else friction(f1, f2, A11, A12, A22, bc, C.con_fr, f0);
+      if (f0 < T(SG_MINVAL)) { f1 = 0; f2 = 0; la = 0; }
+      else friction(f1, f2, la, A11, A12, A22, bc, C.con_fr, f0);
     }
     // cost change, revert if positive
     T d0f = f0 - old0, d1f = f1 - old1, d2f = f2 - old2;
     T change = T(0.5) * (d0f * (A00 * d0f + A01 * d1f + A02 * d2f) + d1f * (A01 * d0f + A11 * d1f + A12 * d2f) + d2f * (A02 * d0f + A12 * d1f + A22 * d2f))
              + d0f * res[0] + d1f * res[1] + d2f * res[2];
     if (change > T(1e-10)) { f0 = old0; f1 = old1; f2 = old2; d0f = d1f = d2f = 0; change = 0; }
-    r[CR_F] = f0; r[CR_F + 1] = f1; r[CR_F + 2] = f2;
+    st4(r + CR_F, f0, f1, f2, la);
     // qacc += M^-1 J^T delta
     if (d0f != T(0) || d1f != T(0) || d2f != T(0)) {
       if (e >= 0) a()[nfd + e] = ae + (w1[0] * d0f + w1[1] * d1f + w1[2] * d2f) * w1[3];

@@ -21,8 +21,7 @@ for cfg in cfgs:
     os.environ["SOFTGRIP_TEAM"] = str(parts.get("t", 0))
     if parts.get("b", 1) == 0: os.environ["SOFTGRIP_NO_BANK_SCHEDULE"] = "1"
     else: os.environ.pop("SOFTGRIP_NO_BANK_SCHEDULE", None)
-    if parts.get("p", 0): os.environ["SOFTGRIP_L2_PERSIST"] = "1"
-    else: os.environ.pop("SOFTGRIP_L2_PERSIST", None)
+    os.environ["SOFTGRIP_STEP_BARRIER"] = str(parts.get("s", 1))
     if "m" in parts: os.environ["SOFTGRIP_MAXCON"] = str(parts["m"])
     else: os.environ.pop("SOFTGRIP_MAXCON", None)
     if "n" in parts: os.environ["SOFTGRIP_NW"] = str(parts["n"])

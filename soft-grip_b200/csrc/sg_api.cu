@@ -448,6 +448,9 @@ static int launch_v2(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
   K.C = make_cst<T>(K.D);
   K.tab = (const T*)b->tab; K.itab = b->itab; K.nworlds = b->W;
   K.team = b->team;
+  K.step_barrier = 1;
+  if (const char* sb = std::getenv("SOFTGRIP_STEP_BARRIER")) K.step_barrier = std::atoi(sb) != 0;
+  if (b->team) K.step_barrier = 1;
   K.scratch = b->scratch;
   K.qpos = (T*)b->qpos; K.qvel = (T*)b->qvel; K.warm = (T*)b->warm; K.act = (T*)b->act; K.ctrl = (T*)b->ctrl;
   K.p_stiff = b->has_stiff ? b->p_stiff : nullptr; K.p_damp = b->has_damp ? b->p_damp : nullptr;

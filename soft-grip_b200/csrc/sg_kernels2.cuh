@@ -180,6 +180,7 @@ struct KArgs2 {
   const int* itab;
   int nworlds;
   int team;                    // 1: the limit/contact rows of 16 worlds are swept by one warp (see World2::pgs)
+  int step_barrier;            // 1: the warps of a CTA start every physics step together (CTA barrier per step)
   unsigned char* scratch;      // global aux slots [gridDim.x * WPW][L.gs_stride] (null when aux_in_smem)
   // state, world-major
   T *qpos, *qvel, *warm, *act, *ctrl;
@@ -1680,7 +1681,9 @@ struct World2 {
     if (integrate) { tick(PH_OTHER); euler(); tick(PH_EULER); }
   }
   __device__ __forceinline__ bool cta_any(bool p) const {
-    if (blockDim.x > 32) return __syncthreads_or(p ? 1 : 0) != 0;
+    // without team mode and without the per-step barrier the warps of a CTA never wait for each other: the decision
+    // only has to be uniform over the warp (forward() is full of warp collectives)
+    if (blockDim.x > 32 && (K.team || K.step_barrier)) return __syncthreads_or(p ? 1 : 0) != 0;
     return __any_sync(FULLMASK, p) != 0;
   }
   __device__ void reset_if(bool doit) {
@@ -1795,7 +1798,7 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
     } else W.reset_if(true);     // whole episode on-chip (create_dataset.log_into_file, ref: create_dataset.py:33-60)
     const int total = K.rollout ? K.sim_start + K.nrows * K.sim_step : (K.integrate ? K.nsub : 1);
     for (int s = 0; s < total; s++) {
-      if (nwarp > 1) __syncthreads();     // warps start each step together (instruction-cache locality, see above)
+      if (nwarp > 1 && K.step_barrier) __syncthreads();     // warps start each step together (instruction-cache locality, see above)
       int t = -1, phase = 0;
       if (K.rollout && s >= K.sim_start) {
         const int r = s - K.sim_start;

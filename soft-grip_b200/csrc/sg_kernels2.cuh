@@ -976,7 +976,7 @@ struct World2 {
     // per-slider and per-lane latest time slots: in the scratch of the capsule centres, which are dead by now
     int* lastt = reinterpret_cast<int*>(scr(L.sc_cen));
     int* lanet = lastt + D.ns;
-    const int clpw = (K.team || use_helpers()) ? MAXCHAIN : LPW;  // lanes that sweep this world's limit/contact rows
+    const int clpw = K.team ? 2 : LPW;                            // lanes that sweep this world's limit/contact rows
     const int nfree = clpw > MAXCHAIN ? clpw - MAXCHAIN : 0;
     for (int e = sl; e < D.ns; e += LPW) lastt[e] = 0;
     lanet[sl] = 0;
@@ -1288,23 +1288,15 @@ struct World2 {
   }
   // one elliptic contact block (mj_solPGS inner body, dim 3) on the lane that owns its chain
   __device__ __forceinline__ T contact_block(T* r, int e, T* ag, bool has_chain, const T* mv) {
-    T rec[CR_STRIDE];
-#pragma unroll
-    for (int i = 0; i < CR_STRIDE; i += 4) ld4(r + i, rec + i);
-    return contact_block_core(r, e, rec, ag, has_chain, mv);
-  }
-  // the block proper, with the 32 words of the record in registers (CR_* order)
-  __device__ __forceinline__ T contact_block_core(T* r, int e, const T* rec, T* ag, bool has_chain, const T* mv) {
     const int nfd = D.nfd;
     T ae = 0;
     if (e >= 0) ae = a()[nfd + e];
-    T jg[12], w1[4], w2[4], w3[4], Aw[8];
-#pragma unroll
-    for (int i = 0; i < 12; i++) jg[i] = rec[CR_JG + i];
-#pragma unroll
-    for (int i = 0; i < 4; i++) { w1[i] = rec[CR_NS + i]; w2[i] = rec[CR_AREF + i]; w3[i] = rec[CR_F + i]; }   // ns iwe | aref R0 | f la
-#pragma unroll
-    for (int i = 0; i < 8; i++) Aw[i] = rec[CR_A + i];                                                         // A00 A01 A02 A11 A12 A22 R1 e
+    T jg[12], w1[4], w2[4], w3[4];
+    ld4(r + CR_JG, jg); ld4(r + CR_JG + 4, jg + 4); ld4(r + CR_JG + 8, jg + 8);
+    ld4(r + CR_NS, w1);          // ns0 ns1 ns2 iwe
+    ld4(r + CR_AREF, w2);        // aref0 aref1 aref2 R0
+    T Aw[8]; ld4(r + CR_A, Aw); ld4(r + CR_A + 4, Aw + 4);   // A00 A01 A02 A11 | A12 A22 R1 e
+    ld4(r + CR_F, w3);           // f0 f1 f2 -
     const T A00 = Aw[0], A01 = Aw[1], A02 = Aw[2], A11 = Aw[3], A12 = Aw[4], A22 = Aw[5];
     const T R0 = w2[3], R1 = Aw[6];
     const T old0 = w3[0], old1 = w3[1], old2 = w3[2];
@@ -1398,90 +1390,7 @@ struct World2 {
   // returns the lane's cost improvement.  The contact records live in the L2-resident scratch: the lane's schedule
   // entries are fetched three blocks ahead (registers) and the 128-byte record of the next block is prefetched into
   // L1 when the current block starts, so that no block waits for two dependent L2 round trips.
-  // Helper lanes.  Only MAXCHAIN lanes of a world sweep limit/contact rows; with LPW >= 4 the other lanes stage the
-  // contact records for them: helper m of chain lane c holds, in registers, the record of the chain's contact k with
-  // k % NHELP == m (loaded NHELP blocks ahead, straight from the L2-resident scratch) and hands it over by 32 warp
-  // shuffles when its time slot comes.  The chain lane therefore never waits for global memory, and no register is
-  // spent on it: sender and receiver use the same 32 registers.
-  static constexpr int NHELP = (LPW - MAXCHAIN) / MAXCHAIN > 3 ? 3 : (LPW - MAXCHAIN) / MAXCHAIN;
-  __device__ __forceinline__ bool use_helpers() const { return NHELP > 0 && !L.aux_in_smem && !K.team; }
-
-  __device__ T chain_phase_helped(ChainState& cs, int tmaxw, bool done) {
-    constexpr int H = NHELP > 0 ? NHELP : 1;
-    T impr = 0;
-    const int cnt = done ? 0 : cs.mycnt;
-    const bool is_chain = sl < MAXCHAIN;
-    const int hidx = sl - MAXCHAIN;
-    const bool is_helper = hidx >= 0 && hidx < MAXCHAIN * H;
-    const int hc = is_helper ? hidx / H : 0, hm = is_helper ? hidx % H : 0;
-    const int my_chain_lane = gshift + (is_helper ? hc : (is_chain ? sl : 0));
-    const int start_c = __shfl_sync(FULLMASK, cs.mystart, my_chain_lane);
-    const int cnt_c = __shfl_sync(FULLMASK, cnt, my_chain_lane);
-    const int* order_c = auxi + L.i_order + start_c;
-    int hk = hm, hent = 0;
-    T buf[CR_STRIDE];
-#pragma unroll
-    for (int i = 0; i < CR_STRIDE; i++) buf[i] = 0;
-    if (is_helper && hk < cnt_c) {
-      hent = order_c[hk];
-      const T* r = crec(hent & 0xff);
-#pragma unroll
-      for (int i = 0; i < CR_STRIDE; i += 4) ld4(r + i, buf + i);
-    }
-    if (cs.chain_lane && !done) impr += limit_rows(cs);
-    int k = 0;
-    for (int t = 1; t <= tmaxw; t++) {
-      const int src = is_chain ? gshift + MAXCHAIN + sl * H + k % H : lane;
-      const int ent = __shfl_sync(FULLMASK, hent, src);
-      const bool go = is_chain && k < cnt && ((ent >> 8) & 0xff) == t;
-      if (__any_sync(FULLMASK, go)) {
-        const int from = go ? src : lane;
-#pragma unroll
-        for (int i = 0; i < CR_STRIDE; i++) buf[i] = __shfl_sync(FULLMASK, buf[i], from);
-        const int ck = __shfl_sync(FULLMASK, go ? k : -1, my_chain_lane);     // the contact this chain consumed, if any
-        if (is_helper && ck >= 0 && ck % H == hm) {
-          hk += H;
-          if (hk < cnt_c) {
-            hent = order_c[hk];
-            const T* r = crec(hent & 0xff);
-#pragma unroll
-            for (int i = 0; i < CR_STRIDE; i += 4) ld4(r + i, buf + i);
-          }
-        }
-        if (go) { impr -= contact_block_core(crec(ent & 0xff), (ent >> 16) - 1, buf, cs.ag, cs.chain_lane, cs.mv); k++; }
-      }
-      __syncwarp();
-    }
-    return impr;
-  }
-
-  // the joint-limit rows of this lane's chain (one sweep); returns the cost improvement
-  __device__ __forceinline__ T limit_rows(ChainState& cs) {
-    T impr = 0;
-#pragma unroll
-    for (int jl = 0; jl < MAXCD; jl++) {
-      if (!(cs.lmask & (1 << jl))) continue;
-      const int dof = D.chain_dof0[sl] + jl;
-      const T sgn = lsgn(dof), f = lf(dof), R = lR(dof);
-      const T A = cs.mv[4 * jl + jl] + R;
-      const T res = sgn * cs.ag[jl] - laref(dof) + R * f;
-      T fn = f - tdiv(res, A);
-      if (fn < T(0)) fn = 0;
-      T dl = fn - f;
-      T change = T(0.5) * dl * dl * A + dl * res;
-      if (change > T(1e-10)) { fn = f; dl = 0; change = 0; }
-      impr -= change;
-      lf(dof) = fn;
-      if (dl != T(0)) {
-#pragma unroll
-        for (int ii = 0; ii < MAXCD; ii++) cs.ag[ii] += cs.mv[4 * ii + jl] * sgn * dl;
-      }
-    }
-    return impr;
-  }
-
   __device__ T chain_phase(ChainState& cs, int tmaxw, bool done) {
-    if (use_helpers()) return chain_phase_helped(cs, tmaxw, done);
     T impr = 0;
     const int* order = auxi + L.i_order + cs.mystart;
     const int cnt = done ? 0 : cs.mycnt;
@@ -1491,7 +1400,27 @@ struct World2 {
     if (cnt > 2) entC = order[2];
     const int ent0 = entA;
     if (cnt > 1 && !L.aux_in_smem) prefetch_l1(crec(entB & 0xff));
-    if (cs.chain_lane && !done) impr += limit_rows(cs);
+    if (cs.chain_lane && !done) {
+#pragma unroll
+      for (int jl = 0; jl < MAXCD; jl++) {
+        if (!(cs.lmask & (1 << jl))) continue;
+        const int dof = D.chain_dof0[sl] + jl;
+        const T sgn = lsgn(dof), f = lf(dof), R = lR(dof);
+        const T A = cs.mv[4 * jl + jl] + R;
+        const T res = sgn * cs.ag[jl] - laref(dof) + R * f;
+        T fn = f - tdiv(res, A);
+        if (fn < T(0)) fn = 0;
+        T dl = fn - f;
+        T change = T(0.5) * dl * dl * A + dl * res;
+        if (change > T(1e-10)) { fn = f; dl = 0; change = 0; }
+        impr -= change;
+        lf(dof) = fn;
+        if (dl != T(0)) {
+#pragma unroll
+          for (int ii = 0; ii < MAXCD; ii++) cs.ag[ii] += cs.mv[4 * ii + jl] * sgn * dl;
+        }
+      }
+    }
     int k = 0;
     for (int t = 1; t <= tmaxw; t++) {
       if (k < cnt && ((entA >> 8) & 0xff) == t) {

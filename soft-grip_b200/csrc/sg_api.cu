@@ -206,6 +206,10 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   int qv_in_smem = 0;
   if (const char* e = std::getenv("SOFTGRIP_QV_SMEM")) qv_in_smem = std::atoi(e);
   if (const char* e = std::getenv("SOFTGRIP_AUX_SMEM")) aux_in_smem = std::atoi(e);
+  if (b->kernel == 2 && (aux_in_smem || qv_in_smem)) {
+    delete b;
+    return fail("SOFTGRIP_AUX_SMEM / SOFTGRIP_QV_SMEM: the shared-memory placement of the once-per-step data was removed from kernel 2 (measured slower; a single address space lets the compiler emit global loads)");
+  }
 #ifdef SG_SIMT_EMU
   b->kernel = 2;
 #endif

@@ -432,15 +432,16 @@ struct World2 {
     unsigned char* base = smem + L.smem_tables + (size_t)(warp * WPW + gslot) * L.smem_stride;
     hot = reinterpret_cast<T*>(base);
     hoti = reinterpret_cast<int*>(hot + L.hotT);
-    if (L.aux_in_smem) aux = reinterpret_cast<T*>(hoti + L.hotI);
-    else aux = reinterpret_cast<T*>(K.scratch + (((size_t)blockIdx.x * nwarp + warp) * WPW + gslot) * (size_t)L.gs_stride);
+    // the once-per-step data always lives in the global scratch (a shared-memory variant was measured slower and is gone:
+    // with one possible address space the compiler emits global loads instead of generic ones)
+    aux = reinterpret_cast<T*>(K.scratch + (((size_t)blockIdx.x * nwarp + warp) * WPW + gslot) * (size_t)L.gs_stride);
     auxi = reinterpret_cast<int*>(aux + L.auxT);
   }
 
   __device__ __forceinline__ const T* tab(int o) const { return K.tab + o; }
   __device__ __forceinline__ const int* itab(int o) const { return K.itab + o; }
-  __device__ __forceinline__ T* q() { return L.qv_in_smem ? hot + L.hq : aux + L.q; }
-  __device__ __forceinline__ T* v() { return L.qv_in_smem ? hot + L.hv : aux + L.v; }
+  __device__ __forceinline__ T* q() { return aux + L.q; }
+  __device__ __forceinline__ T* v() { return aux + L.v; }
   __device__ __forceinline__ T* a() { return hot + L.a; }
   __device__ __forceinline__ T* qs() { return aux + L.qs; }
   __device__ __forceinline__ int& misc(int i) { return hoti[L.h_misc + i]; }

@@ -32,7 +32,7 @@ def states():
     return np.load(os.path.join(GOLDEN, "softbox_states.npz"))
 
 
-@pytest.mark.parametrize("prec,lpw,aux", [(64, 8, 0), (64, 4, 0), (64, 32, 1), (64, 16, 0), (32, 8, 0)])
+@pytest.mark.parametrize("prec,lpw,aux", [(64, 8, 0), (64, 4, 0), (64, 32, 0), (64, 16, 0), (32, 8, 0)])
 def test_emulated_single_step_parity_against_golden_states(emu, states, prec, lpw, aux):
     W = 32 // lpw + 1                      # one full warp of worlds plus a ragged tail
     env = emu.EmuBatch(blob_path("softbox"), W, prec=prec, lpw=lpw, aux_smem=aux)
@@ -136,7 +136,7 @@ def test_emulated_multi_warp_cta_and_persistent_batches(emu, batched):
     W = 21
     ks = 300.0 + 50.0 * np.arange(W)
     out = []
-    for nw, lpw, qv, team in ((1, 8, 0, 0), (4, 8, 1, 1), (2, 16, 0, 0), (8, 8, 0, 1)):
+    for nw, lpw, qv, team in ((1, 8, 0, 0), (4, 8, 0, 1), (2, 16, 0, 0), (8, 8, 0, 1)):
         env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=lpw, nw=nw, qv_smem=qv, team=team)
         env.set_params(stiffness=ks)
         traj, touch, st = env.rollout(sched, want_touch=False)
@@ -274,3 +274,12 @@ def test_equality_sweep_schedule_is_a_valid_gauss_seidel_order(emu, model, lpw, 
         del os.environ["SOFTGRIP_NO_BANK_SCHEDULE"]
     assert perm0.tolist() == list(range(nrow))
     assert wavefronts + 6 * nstep <= wavefronts0 + 6 * nstep0
+
+
+def test_removed_placement_options_fail_loudly(emu):
+    """The shared-memory placement of the once-per-step data is gone from kernel 2: asking for it is an error, not a
+    silent fallback."""
+    with pytest.raises(RuntimeError, match="removed"):
+        emu.EmuBatch(blob_path("softbox"), 2, prec=32, lpw=8, aux_smem=1)
+    with pytest.raises(RuntimeError, match="removed"):
+        emu.EmuBatch(blob_path("softbox"), 2, prec=32, lpw=8, qv_smem=1)

@@ -12,8 +12,9 @@ cfgs = sys.argv[3:] or ["l8:n16:t0"]
 dm = batched.DeviceModel(os.path.join(ROOT, "tests", "golden", name + ".sgm"))
 for cfg in cfgs:
     parts = {x[0]: int(x[1:]) for x in cfg.split(":")}
-    os.environ["SOFTGRIP_LPW"] = str(parts.get("l", 8)); os.environ["SOFTGRIP_TEAM"] = str(parts.get("t", 0))
-    os.environ["SOFTGRIP_AUX_SMEM"] = str(parts.get("a", 0))
+    os.environ["SOFTGRIP_LPW"] = str(parts.get("l", 8))
+    os.environ.pop("SOFTGRIP_TEAM", None)
+    os.environ.pop("SOFTGRIP_AUX_SMEM", None)
     if "n" in parts: os.environ["SOFTGRIP_NW"] = str(parts["n"])
     else: os.environ.pop("SOFTGRIP_NW", None)
     env = batched.BatchedManEnv(dm, W, dtype=torch.float32, seed=0)

@@ -16,9 +16,9 @@ ref = None
 for cfg in cfgs:
     parts = {x[0]: int(x[1:]) for x in cfg.split(":")}
     k, l, a = parts.get("k", 2), parts.get("l", 8), parts.get("a", 0)
-    os.environ["SOFTGRIP_KERNEL"] = str(k); os.environ["SOFTGRIP_LPW"] = str(l); os.environ["SOFTGRIP_AUX_SMEM"] = str(a)
-    os.environ["SOFTGRIP_QV_SMEM"] = str(parts.get("q", 0))
-    os.environ["SOFTGRIP_TEAM"] = str(parts.get("t", 0))
+    os.environ["SOFTGRIP_KERNEL"] = str(k); os.environ["SOFTGRIP_LPW"] = str(l); os.environ.pop("SOFTGRIP_AUX_SMEM", None)
+    os.environ.pop("SOFTGRIP_QV_SMEM", None)
+    os.environ.pop("SOFTGRIP_TEAM", None)
     if parts.get("b", 1) == 0: os.environ["SOFTGRIP_NO_BANK_SCHEDULE"] = "1"
     else: os.environ.pop("SOFTGRIP_NO_BANK_SCHEDULE", None)
     os.environ["SOFTGRIP_STEP_BARRIER"] = str(parts.get("s", 1))

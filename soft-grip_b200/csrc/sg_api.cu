@@ -40,7 +40,6 @@ struct sg_batch {
   int kernel = 2;             // 2: sub-warp worlds (sg_kernels2.cuh); 1: one warp per world (sg_kernels.cuh)
   int lpw = 8;                // lanes per world of kernel 2
   int nwarp = 16;             // warps per CTA of kernel 2
-  int team = 0;               // kernel 2: one warp sweeps the limit/contact rows of 16 worlds (opt-in: measured slower, profiles/r01b_*)
   size_t smem2 = 0;           // dynamic shared memory per CTA of kernel 2
   Layout2 L2;
   unsigned char* scratch = nullptr;   // global aux slots of kernel 2 (when aux is not in shared memory)
@@ -254,8 +253,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
     }
     if (b->D.nrow >= 0xfff || b->D.ns >= 0xfff) { delete b; return fail("sg_batch_create: too many equality rows or shell joints for the packed warm-start table"); }
     if (b->L2.cand_cap < 16) { delete b; return fail("sg_batch_create: the collision scratch (the equality-row pairs of one world) is too small for this model"); }
-    b->team = 0;
-    if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) != 0 && b->lpw >= 4 && b->nwarp % (b->lpw / 2) == 0) b->team = 1; }
+    if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) != 0) { delete b; return fail("SOFTGRIP_TEAM: team mode was removed from kernel 2 (measured slower, profiles/r01b_*, r01g_*)"); } }
     if (b->smem2 > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: worlds of one warp do not fit in shared memory (use more lanes per world or SOFTGRIP_AUX_SMEM=0)"); }
     int e = k2_dispatch_configure(precision, b->lpw, 32 * b->nwarp, b->smem2, &per_sm);
     if (e == -12345) { delete b; return fail("SOFTGRIP_LPW: this lanes-per-world value is not compiled in"); }
@@ -316,7 +314,7 @@ extern "C" int sg_batch_config(const sg_batch* b, int* out) {
   const int wpw = 32 / b->lpw;
   out[0] = b->kernel == 2 ? b->lpw : 32; out[1] = b->kernel == 2 ? b->nwarp : 1; out[2] = b->kernel == 2 ? wpw * b->nwarp : 1;
   out[3] = b->per_sm; out[4] = b->kernel == 2 ? (int)b->smem2 : 0; out[5] = b->kernel == 2 ? b->L2.smem_stride : 0;
-  out[6] = b->kernel == 2 ? b->team : 0; out[7] = b->kernel;
+  out[6] = 0; out[7] = b->kernel;
   return 0;
 }
 
@@ -451,10 +449,8 @@ static int launch_v2(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
   K.D.cap_mask = b->model->plan.d.cap_mask; K.D.sph_mask = b->model->plan.d.sph_mask;
   K.C = make_cst<T>(K.D);
   K.tab = (const T*)b->tab; K.itab = b->itab; K.nworlds = b->W;
-  K.team = b->team;
   K.step_barrier = 1;
   if (const char* sb = std::getenv("SOFTGRIP_STEP_BARRIER")) K.step_barrier = std::atoi(sb) != 0;
-  if (b->team) K.step_barrier = 1;
   K.scratch = b->scratch;
   K.qpos = (T*)b->qpos; K.qvel = (T*)b->qvel; K.warm = (T*)b->warm; K.act = (T*)b->act; K.ctrl = (T*)b->ctrl;
   K.p_stiff = b->has_stiff ? b->p_stiff : nullptr; K.p_damp = b->has_damp ? b->p_damp : nullptr;

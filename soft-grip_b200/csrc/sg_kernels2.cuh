@@ -49,7 +49,7 @@ struct Layout2 {
   int row2;              // 2*(nrow+1) : (u, R) per equality row, schedule order; the last pair is the dummy row (0, 1)
   int minv;              // 16*MAXCHAIN
   int hlim;              // 4*MAXFD : f, aref, R, sign per finger dof (meaningful where the limit is active)
-  int h_impr;            // 1 (+pad): cost improvement of the limit/contact rows of the current sweep (team mode)
+  int h_impr;            // 1 (unused since team mode was removed; keeps the layout of the hot block)
   int hotT;
   int h_misc;            // 8 ints
   int hotI;
@@ -179,7 +179,6 @@ struct KArgs2 {
   const T* tab;
   const int* itab;
   int nworlds;
-  int team;                    // 1: the limit/contact rows of 16 worlds are swept by one warp (see World2::pgs)
   int step_barrier;            // 1: the warps of a CTA start every physics step together (CTA barrier per step)
   unsigned char* scratch;      // global aux slots [gridDim.x * WPW][L.gs_stride] (null when aux_in_smem)
   // state, world-major
@@ -977,7 +976,7 @@ struct World2 {
     // per-slider and per-lane latest time slots: in the scratch of the capsule centres, which are dead by now
     int* lastt = reinterpret_cast<int*>(scr(L.sc_cen));
     int* lanet = lastt + D.ns;
-    const int clpw = K.team ? 2 : LPW;                            // lanes that sweep this world's limit/contact rows
+    const int clpw = LPW;                                         // lanes that sweep this world's limit/contact rows
     const int nfree = clpw > MAXCHAIN ? clpw - MAXCHAIN : 0;
     for (int e = sl; e < D.ns; e += LPW) lastt[e] = 0;
     lanet[sl] = 0;
@@ -1510,35 +1509,13 @@ struct World2 {
     return impr;
   }
 
-  __device__ __forceinline__ void team_sync(int id, int nthreads) {
-#ifdef SG_SIMT_EMU
-    simt_named_barrier(id, nthreads);
-#elif defined(__CUDA_ARCH__)
-    // immediate barrier ids (1..8): a register id would make ptxas reserve all 16 hardware barriers for the CTA
-    switch (id) {
-      case 1: asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); break;
-      case 2: asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); break;
-      case 3: asm volatile("bar.sync 3, %0;" ::"r"(nthreads) : "memory"); break;
-      case 4: asm volatile("bar.sync 4, %0;" ::"r"(nthreads) : "memory"); break;
-      case 5: asm volatile("bar.sync 5, %0;" ::"r"(nthreads) : "memory"); break;
-      case 6: asm volatile("bar.sync 6, %0;" ::"r"(nthreads) : "memory"); break;
-      case 7: asm volatile("bar.sync 7, %0;" ::"r"(nthreads) : "memory"); break;
-      default: asm volatile("bar.sync 8, %0;" ::"r"(nthreads) : "memory"); break;
-    }
-#else
-    (void)id; (void)nthreads;
-#endif
-  }
-
   // projected Gauss-Seidel (mj_solPGS) in MuJoCo's row order.
-  // Team mode (K.team): the LPW/2 warps that hold 16 consecutive worlds form a team.  Every warp sweeps the equality
-  // block of its own worlds with LPW lanes per world; the limit and contact rows -- serial per finger chain, so they
-  // keep at most two lanes of a world busy -- are swept for all 16 worlds at once by the team's first warp through a
-  // 2-lanes-per-world view of the same shared memory (32 chains = 32 lanes), between two team barriers per sweep.
+  // (A "team mode" in which one warp swept the limit/contact rows of 16 worlds through a 2-lane view between named
+  // barriers was measured slower twice and removed; see DESIGN.md and the history.)
   __device__ void pgs(Tendon& tn, unsigned char* smem) {
     int iter = 0;
     bool done = false;
-    if (!K.team) {
+    {
       ChainState cs;
       chain_prologue(cs);
       const int tmaxw = wmax(misc(M2_TMAX));
@@ -1554,36 +1531,6 @@ struct World2 {
         if (!done) { iter++; if (impr < C.tol) done = true; }
       }
       chain_epilogue(cs);
-    } else {
-      constexpr int TEAMW = LPW / 2 > 0 ? LPW / 2 : 1;       // warps per team (16 worlds)
-      // the team's chain warp: a different position in every team, so that the chain warps of the CTA's teams sit on
-      // different warp schedulers (warp index modulo 4)
-      const int warp = threadIdx.x >> 5, team = warp / TEAMW, wit = (warp % TEAMW + TEAMW - team % TEAMW) % TEAMW;
-      const int bar_id = 1 + team, nthr = 32 * TEAMW;
-      World2<T, 2> V(K, smem, 0, false, team, (int)(blockDim.x >> 5) / TEAMW);
-      typename World2<T, 2>::ChainState cs;
-      int tmaxw = 0;
-      if (sl == 0) misc(M2_DONE) = 0;
-      team_sync(bar_id, nthr);                               // warm-start results of all 16 worlds are in place
-      if (wit == 0) { V.chain_prologue(cs); tmaxw = V.wmax(V.misc(M2_TMAX)); }
-      tick(PH_PGS_SETUP);
-      for (int it = 0; it < D.iters; it++) {
-        T impr = equality_sweep(tn, done);
-        tick(PH_PGS_EQUALITY);
-        team_sync(bar_id, nthr);
-        if (wit == 0) {
-          T ic = V.chain_phase(cs, tmaxw, V.misc(M2_DONE) != 0);
-          ic = V.gsum(ic);
-          if (V.sl == 0) V.hot[L.h_impr] = ic;
-        }
-        team_sync(bar_id, nthr);
-        tick(PH_PGS_CHAIN);
-        impr = (gsum(impr) + hot[L.h_impr]) * C.impr_scale;
-        if (!done) { iter++; if (impr < C.tol) done = true; }
-        if (sl == 0) misc(M2_DONE) = done ? 1 : 0;
-      }
-      if (wit == 0) V.chain_epilogue(cs);
-      team_sync(bar_id, nthr);
     }
     if (sl == 0) misc(M2_ITERS) = iter;
     __syncwarp();
@@ -1671,7 +1618,7 @@ struct World2 {
     }
     for (int pass = 0; pass < 2; pass++) {
       const bool bad = forward();
-      // CTA-uniform decision: forward() contains team barriers, so all warps of the CTA repeat it together
+      // CTA-uniform decision when the warps step together (per-step barrier)
       if (!integrate || !cta_any(bad)) break;
       // mj_step re-runs mj_forward after mj_resetData.  forward() is full of warp collectives, so the other
       // groups of the warp re-run it too, from their saved warm start: they recompute identical values.
@@ -1682,9 +1629,9 @@ struct World2 {
     if (integrate) { tick(PH_OTHER); euler(); tick(PH_EULER); }
   }
   __device__ __forceinline__ bool cta_any(bool p) const {
-    // without team mode and without the per-step barrier the warps of a CTA never wait for each other: the decision
+    // without the per-step barrier the warps of a CTA never wait for each other: the decision
     // only has to be uniform over the warp (forward() is full of warp collectives)
-    if (blockDim.x > 32 && (K.team || K.step_barrier)) return __syncthreads_or(p ? 1 : 0) != 0;
+    if (blockDim.x > 32 && K.step_barrier) return __syncthreads_or(p ? 1 : 0) != 0;
     return __any_sync(FULLMASK, p) != 0;
   }
   __device__ void reset_if(bool doit) {

@@ -49,7 +49,7 @@ def _p(a):
 class EmuBatch:
     """W worlds stepping under the emulator; mirrors the parts of BatchedManEnv the parity tests use."""
 
-    def __init__(self, blob_path, W, prec=64, lpw=8, aux_smem=0, nw=None, qv_smem=0, team=1, joint_ids=range(11, 64), tendon0=1):
+    def __init__(self, blob_path, W, prec=64, lpw=8, aux_smem=0, nw=None, qv_smem=0, team=0, joint_ids=range(11, 64), tendon0=1):
         batched = importlib.import_module("soft-grip_b200.batched")
         mjcf = importlib.import_module("soft-grip_b200.mjcf")
         lib_ = importlib.import_module("soft-grip_b200._lib")

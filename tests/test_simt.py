@@ -61,11 +61,11 @@ def test_emulated_single_step_parity_against_golden_states(emu, states, prec, lp
 
 
 @pytest.mark.parametrize("lpw,nw", [(8, 4), (4, 2), (16, 8)])
-def test_emulated_team_mode_parity(emu, states, lpw, nw):
-    """Team mode: the limit/contact rows of 16 worlds are swept by one warp through a 2-lanes-per-world view, between
-    named barriers.  Same parity bar as the per-warp path, on contact-rich golden states."""
-    W = 19                                  # one full team of 16 worlds + a ragged second team
-    env = emu.EmuBatch(blob_path("softbox"), W, prec=64, lpw=lpw, nw=nw, team=1)
+def test_emulated_multi_warp_cta_parity(emu, states, lpw, nw):
+    """Multi-warp CTAs (per-step CTA barrier, CTA-shared tables, ragged last warp) on contact-rich golden states: same
+    parity bar as the single-warp case."""
+    W = 19                                  # 16 worlds + a ragged tail
+    env = emu.EmuBatch(blob_path("softbox"), W, prec=64, lpw=lpw, nw=nw)
     env.set_params(stiffness=np.full(W, 700.0))
     env.set_debug_world(17)
     for i in (4, 6, 7, 9, 11):
@@ -136,8 +136,8 @@ def test_emulated_multi_warp_cta_and_persistent_batches(emu, batched):
     W = 21
     ks = 300.0 + 50.0 * np.arange(W)
     out = []
-    for nw, lpw, qv, team in ((1, 8, 0, 0), (4, 8, 0, 1), (2, 16, 0, 0), (8, 8, 0, 1)):
-        env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=lpw, nw=nw, qv_smem=qv, team=team)
+    for nw, lpw in ((1, 8), (4, 8), (2, 16), (8, 8)):
+        env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=lpw, nw=nw)
         env.set_params(stiffness=ks)
         traj, touch, st = env.rollout(sched, want_touch=False)
         assert (st == 0).all() and np.isfinite(traj).all()
@@ -150,7 +150,7 @@ def test_emulated_multi_warp_cta_and_persistent_batches(emu, batched):
 
 @pytest.mark.parametrize("W,nw", [(4, None), (18, 4)])
 def test_emulated_divergence_is_contained_in_its_group(emu, W, nw):
-    """A diverging world is reset and flagged; the other worlds of the same warp / team / CTA are bit-identical to a
+    """A diverging world is reset and flagged; the other worlds of the same warp / CTA are bit-identical to a
     clean run (the re-run of mj_forward after the reset is taken by the whole CTA)."""
     env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=8, nw=nw)
     q = np.zeros((W, 118)); q[1, 30] = 1e11
@@ -222,7 +222,7 @@ def test_equality_sweep_schedule_is_a_valid_gauss_seidel_order(emu, model, lpw, 
     import importlib
     mjcf = importlib.import_module("soft-grip_b200.mjcf")
     A = mjcf.load_blob(blob_path(model)).arrays
-    env = emu.EmuBatch(blob_path(model), 2, prec=prec, lpw=lpw, team=0)
+    env = emu.EmuBatch(blob_path(model), 2, prec=prec, lpw=lpw)
     nstep, lpw_, esize, nrow, wavefronts, sd, perm = _decode_schedule(env)
     assert lpw_ == lpw and esize == prec // 8 and nrow == len(A["eq_obj1id"]) - 1
     assert sorted(perm.tolist()) == list(range(nrow))
@@ -268,7 +268,7 @@ def test_equality_sweep_schedule_is_a_valid_gauss_seidel_order(emu, model, lpw, 
             last[d] = r
     os.environ["SOFTGRIP_NO_BANK_SCHEDULE"] = "1"
     try:
-        plain = emu.EmuBatch(blob_path(model), 2, prec=prec, lpw=lpw, team=0)
+        plain = emu.EmuBatch(blob_path(model), 2, prec=prec, lpw=lpw)
         nstep0, _, _, _, wavefronts0, _, perm0 = _decode_schedule(plain)
     finally:
         del os.environ["SOFTGRIP_NO_BANK_SCHEDULE"]
@@ -283,3 +283,5 @@ def test_removed_placement_options_fail_loudly(emu):
         emu.EmuBatch(blob_path("softbox"), 2, prec=32, lpw=8, aux_smem=1)
     with pytest.raises(RuntimeError, match="removed"):
         emu.EmuBatch(blob_path("softbox"), 2, prec=32, lpw=8, qv_smem=1)
+    with pytest.raises(RuntimeError, match="removed"):
+        emu.EmuBatch(blob_path("softbox"), 2, prec=32, lpw=8, nw=4, team=1)

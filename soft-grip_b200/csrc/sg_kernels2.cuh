@@ -9,18 +9,19 @@
 //                     emitted in MuJoCo's canonical order by ballot compaction, then scheduled per lane
 //   rows_and_smooth() equality / tendon / limit rows (impedance, R, aref) and the smooth forces
 //   warmstart()       forces from qacc_warmstart, dual cost test, qacc = qacc_smooth + M^-1 J^T f
-//   pgs()             projected Gauss-Seidel in exact MuJoCo row order.  Equality rows are swept by
-//                     *dependency levels* (rows of a level touch disjoint dofs, so lanes update them at once
-//                     with the result of the sequential sweep); the dense volume-tendon row is a sub-warp
-//                     shuffle reduction; limits and elliptic contact blocks run one lane per finger chain with
-//                     the chain's accelerations and inverse inertia held in registers
+//   pgs()             projected Gauss-Seidel in exact MuJoCo row order.  Equality rows are swept by a
+//                     *list schedule* built on the host (sg_plan.hpp build_step_tables: rows of a step touch
+//                     disjoint sliders, so lanes update them at once with the result of the sequential sweep);
+//                     the dense volume-tendon row is a sub-warp shuffle reduction; limits and elliptic contact
+//                     blocks run one lane per finger chain with the chain's accelerations in registers
 //   finish()/euler()  accelerometers, implicit-damping Euler, NaN checks
 //
 // What the sweeps touch stays in shared memory ("hot": the running qacc, two words per equality row, finger
-// inverse inertia).  The matrix AR = J M^-1 J^T + R is never formed.  Per equality row only u = R f - aref and R
-// are kept: the residual is J.qacc + u, and f itself is not needed (no clamp on equality rows).  Everything
-// that is touched once per step ("aux": qpos, qvel, smooth forces, contact records, candidate lists) lives
-// either in shared memory too or in an L2-resident global scratch slot of the group (Layout2::aux_in_smem).
+// inverse inertia).  The matrix AR = J M^-1 J^T + R is never formed.  Per equality row only u = R f - aref and
+// n = -1 / (1/m1 + 1/m2 + R) are kept: the residual is J.qacc + u, and neither f nor R is needed (no clamp on
+// equality rows).  Between the solve and the next rows_and_smooth() the row pairs are dead and serve gripper() and
+// collide() as scratch.  Everything that is touched once per step ("aux": qpos, qvel, smooth forces, contact
+// records) lives in an L2-resident global scratch slot of the group.
 //
 // No tensor cores: nothing here is a dense contraction (largest dense objects: 4x4 finger inertia blocks,
 // 3x3 contact blocks).  The kernel is bound by issue slots / dependent-issue latency of the Gauss-Seidel

@@ -122,8 +122,8 @@ int sg_batch_sync(sg_batch* b, void* stream);
 
 /* diagnostics of the last physics step of one world (synchronous, host fp64): key is one of
  * "qacc","qacc_smooth","ncon","nefc","solver_iter","con_dist","con_pos","con_frame","efc_force",
- * "efc_aref","efc_R"; "sweep_schedule" returns the host-side step tables of the equality sweep instead (layout in
- * sg_api.cu).  Returns the element count (<0 on error); writes at most cap values.
+ * "efc_aref","efc_R"; "sweep_schedule" / "pair_runs" return the host-side step tables of the equality sweep / the
+ * candidate pair list and its run-length form instead (layouts in sg_api.cu).  Returns the element count (<0 on error); writes at most cap values.
  * Only valid after sg_batch_set_debug_world(b, w) and a subsequent step/forward. */
 int sg_batch_set_debug_world(sg_batch* b, int world);
 int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int cap);

@@ -615,6 +615,16 @@ extern "C" int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int
   const int ncontot = (int)h[0], nefc = (int)h[1], ncon = (int)h[3], nlim = (int)h[4];
   const std::string k(key);
   auto put = [&](const double* src, int n) { if (out) for (int i = 0; i < n && i < cap; i++) out[i] = src[i]; return n; };
+  if (k == "pair_runs") {
+    // host-side collision tables (no device data): [npair, nrun], the candidate pair list in MuJoCo's contact order as
+    // (type, collider a, second geom b) triples, then the run-length blocks {type, a0 | na << 8, b0, nb} the device
+    // broadphase walks
+    const Plan& P = b->model->plan;
+    std::vector<double> t = {(double)P.d.npair, (double)P.d.nrun};
+    for (int p = 0; p < P.d.npair; p++) { t.push_back(P.itab[P.d.io_pair_t + p]); t.push_back(P.itab[P.d.io_pair_a + p]); t.push_back(P.itab[P.d.io_pair_b + p]); }
+    for (int i = 0; i < 4 * P.d.nrun; i++) t.push_back(P.itab[P.d.io_run + i]);
+    return put(t.data(), (int)t.size());
+  }
   if (k == "sweep_schedule") {
     // host-side tables of the equality sweep (no device data): [nstep, lanes per world, bytes per real, nrow, estimated
     // shared-memory wavefronts per sweep], the slot descriptors (2 ints per slot, nstep + 1 steps), then the storage

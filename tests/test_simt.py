@@ -285,3 +285,23 @@ def test_removed_placement_options_fail_loudly(emu):
         emu.EmuBatch(blob_path("softbox"), 2, prec=32, lpw=8, qv_smem=1)
     with pytest.raises(RuntimeError, match="removed"):
         emu.EmuBatch(blob_path("softbox"), 2, prec=32, lpw=8, nw=4, team=1)
+
+
+@pytest.mark.parametrize("model", ["softbox", "softball", "softcylinder"])
+def test_broadphase_runs_reproduce_the_pair_list(emu, model):
+    """Host logic of the collision tables (sg_plan.hpp): the run-length blocks the device broadphase walks expand to
+    exactly the candidate pair list, in MuJoCo's contact order (b-major, collider-minor inside a block)."""
+    env = emu.EmuBatch(blob_path(model), 2, prec=32, lpw=8)
+    t = env.debug("pair_runs").astype(int)
+    npair, nrun = int(t[0]), int(t[1])
+    pairs = t[2:2 + 3 * npair].reshape(npair, 3)
+    runs = t[2 + 3 * npair:].reshape(nrun, 4)
+    out = []
+    for pt, a, b0, nb in runs:
+        a0, na = a & 255, a >> 8
+        assert na >= 1 and nb >= 1
+        for j in range(na * nb):
+            out.append((pt, a0 + j % na, b0 + j // na))
+    assert len(out) == npair and nrun < npair // 8          # the point of the encoding: long runs
+    np.testing.assert_array_equal(np.array(out), pairs)
+    env.close()

@@ -180,6 +180,7 @@ static int k2_dispatch_launch(int lpw, const KArgs2<T>& K, int grid, int block, 
   return -12345;
 }
 
+extern "C" void sg_batch_destroy(sg_batch* b);
 extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int precision, sg_batch** out) {
   if (!m || !out) return fail("sg_batch_create: null argument");
   if (nworlds < 1) return fail("sg_batch_create: nworlds must be >= 1");
@@ -223,7 +224,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
     b->D.io_step_d = (int)((P.itab.size() + 3) / 4 * 4);
   }
   int rc = upload_tables(b, true);
-  if (rc) { delete b; return rc; }
+  if (rc) { sg_batch_destroy(b); return rc; }
   const size_t nv = b->D.nv, nu = b->D.nu > 0 ? b->D.nu : 1;
   CUDA_OK(cudaMalloc(&b->qpos, b->esize * nv * nworlds));
   CUDA_OK(cudaMalloc(&b->qvel, b->esize * nv * nworlds));
@@ -251,13 +252,13 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       if (b->smem2 <= prop.sharedMemPerBlockOptin || b->nwarp == 1) break;
       b->nwarp -= 1;                       // largest CTA that fits
     }
-    if (b->D.nrow >= 0xfff || b->D.ns >= 0xfff) { delete b; return fail("sg_batch_create: too many equality rows or shell joints for the packed warm-start table"); }
-    if (b->L2.cand_cap < 16) { delete b; return fail("sg_batch_create: the collision scratch (the equality-row pairs of one world) is too small for this model"); }
-    if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) != 0) { delete b; return fail("SOFTGRIP_TEAM: team mode was removed from kernel 2 (measured slower, profiles/r01b_*, r01g_*)"); } }
-    if (b->smem2 > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: worlds of one warp do not fit in shared memory (use more lanes per world or SOFTGRIP_AUX_SMEM=0)"); }
+    if (b->D.nrow >= 0xfff || b->D.ns >= 0xfff) { sg_batch_destroy(b); return fail("sg_batch_create: too many equality rows or shell joints for the packed warm-start table"); }
+    if (b->L2.cand_cap < 16) { sg_batch_destroy(b); return fail("sg_batch_create: the collision scratch (the equality-row pairs of one world) is too small for this model"); }
+    if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) != 0) { sg_batch_destroy(b); return fail("SOFTGRIP_TEAM: team mode was removed from kernel 2 (measured slower, profiles/r01b_*, r01g_*)"); } }
+    if (b->smem2 > prop.sharedMemPerBlockOptin) { sg_batch_destroy(b); return fail("sg_batch_create: worlds of one warp do not fit in shared memory (use more lanes per world or SOFTGRIP_AUX_SMEM=0)"); }
     int e = k2_dispatch_configure(precision, b->lpw, 32 * b->nwarp, b->smem2, &per_sm);
-    if (e == -12345) { delete b; return fail("SOFTGRIP_LPW: this lanes-per-world value is not compiled in"); }
-    if (e) { delete b; return fail(std::string("kernel configuration failed: ") + cudaGetErrorString((cudaError_t)e)); }
+    if (e == -12345) { sg_batch_destroy(b); return fail("SOFTGRIP_LPW: this lanes-per-world value is not compiled in"); }
+    if (e) { sg_batch_destroy(b); return fail(std::string("kernel configuration failed: ") + cudaGetErrorString((cudaError_t)e)); }
     if (per_sm < 1) per_sm = 1;
     b->max_ctas = per_sm * prop.multiProcessorCount; b->per_sm = per_sm;
     const int cta_worlds = wpw * b->nwarp;
@@ -278,7 +279,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
 #ifndef SG_SIMT_EMU
   else {
     b->L = precision == 32 ? make_layout<float>(b->D) : make_layout<double>(b->D);
-    if ((size_t)b->L.bytes > prop.sharedMemPerBlockOptin) { delete b; return fail("sg_batch_create: world does not fit in shared memory"); }
+    if ((size_t)b->L.bytes > prop.sharedMemPerBlockOptin) { sg_batch_destroy(b); return fail("sg_batch_create: world does not fit in shared memory"); }
     // resident CTAs: one warp per world, limited by shared memory
     if (precision == 32) {
       CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.bytes));

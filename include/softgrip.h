@@ -143,6 +143,25 @@ int sg_batch_prof_get(sg_batch* b, unsigned long long* out, int n);
 /* number of kernel launches issued by this batch since creation (bench.py's gpu_launches) */
 long long sg_batch_launch_count(const sg_batch* b);
 
+/* ---- the trajectory buffer downstream of the step path -----------------------------
+ * `traj` is [nrows][nchan] in `precision` (32: float, 64: double) on `device`, 16-byte aligned, nchan a multiple of 4
+ * (<= 64): a rollout's [W][T][12] buffer with nrows = W*T.  All calls are asynchronous on `stream`. */
+
+/* replaces functions/optimization.py:6-14 `noised_modality`: channels [0, nacc) += N(0, sigma_acc), channels
+ * [nacc, nchan) += N(0, sigma_gyro) (reference: nacc 6, 0.7, 0.06), traj_out may alias traj_in.  The draws are
+ * Philox4x32-10(key = seed, counter = element index / 4) + Box-Muller in fp32, i.e. a function of (seed, element index)
+ * only.  mean/std (dev fp64 [nchan], both or neither): fused standardisation out = (x + noise - mean) / std of
+ * functions/optimization.py:38. */
+int sg_traj_add_noise(const void* traj_in, void* traj_out, long long nrows, int nchan, int nacc, double sigma_acc,
+                      double sigma_gyro, unsigned long long seed, const double* mean, const double* std,
+                      int precision, int device, void* stream);
+/* replaces `np.mean(train_x, axis=(0, 1))` / `np.std(train_x, axis=(0, 1))` of functions/utils.py:39-40 (population
+ * standard deviation).  mean_out/std_out: dev fp64 [nchan]; workspace: dev, at least sg_traj_stats_workspace_bytes().
+ * fp64 accumulation in a fixed order: the result is bit-reproducible for a given shape and device. */
+int sg_traj_channel_stats(const void* traj, long long nrows, int nchan, int precision, int device, double* mean_out,
+                          double* std_out, void* workspace, long long workspace_bytes, void* stream);
+long long sg_traj_stats_workspace_bytes(long long nrows, int nchan, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -663,3 +663,120 @@ extern "C" int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int
   }
   return fail("sg_batch_debug_get: unknown key " + k);
 }
+
+// ---- trajectory post-processing (sg_traj.cuh): noise augmentation and channel statistics ------------------------------
+#include "sg_traj.cuh"
+
+static int traj_sm_count(int device, int* out) {
+  static int cached[64] = {0};
+  if (device < 0 || device >= 64) return fail("bad device index");
+  if (!cached[device]) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail("no CUDA device available (libsoftgrip has no CPU path)");
+    if (device >= ndev) return fail("bad device index");
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    cached[device] = prop.multiProcessorCount;
+  }
+  *out = cached[device];
+  return 0;
+}
+
+static int traj_check(const char* fn, const void* p, long long nrows, int nchan, int precision) {
+  if (!p) return fail(std::string(fn) + ": null trajectory");
+  if (precision != 32 && precision != 64) return fail(std::string(fn) + ": precision must be 32 or 64");
+  if (nrows < 0) return fail(std::string(fn) + ": negative row count");
+  if (nchan < 4 || nchan % 4 != 0 || nchan > TRAJ_STATS_MAX_CHAN) return fail(std::string(fn) + ": nchan must be a multiple of 4 in [4, 64]");
+  if (((uintptr_t)p & 15) != 0) return fail(std::string(fn) + ": trajectory must be 16-byte aligned");
+  return 0;
+}
+
+template <typename T>
+static int traj_noise_launch(const void* in, void* out, long long nrows, int nchan, int nacc, double sa, double sg_, unsigned long long seed,
+                             const double* mean, const double* stdev, int sms, void* stream) {
+  TrajNoiseArgs<T> A;
+  A.in = (const T*)in; A.out = (T*)out; A.nelem = nrows * nchan; A.nchan = nchan; A.nacc = nacc;
+  A.sigma_acc = (float)sa; A.sigma_gyro = (float)sg_;
+  A.k0 = (uint32_t)seed; A.k1 = (uint32_t)(seed >> 32);
+  A.mean = mean; A.stdev = stdev;
+  const int block = 256;
+  const long long nquad = A.nelem / 4;
+  long long grid = (nquad + block - 1) / block;
+  if (grid > (long long)sms * 8) grid = (long long)sms * 8;     // 8 x 256 threads resident per SM, grid-stride beyond that
+  auto kp = sg_traj_noise_kernel<T>;
+  SG_LAUNCH(kp, (int)grid, block, 0, (cudaStream_t)stream, A);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sg_traj_add_noise(const void* traj_in, void* traj_out, long long nrows, int nchan, int nacc, double sigma_acc,
+                                 double sigma_gyro, unsigned long long seed, const double* mean, const double* stdev,
+                                 int precision, int device, void* stream) {
+  if (int rc = traj_check("sg_traj_add_noise", traj_in, nrows, nchan, precision)) return rc;
+  if (int rc = traj_check("sg_traj_add_noise", traj_out, nrows, nchan, precision)) return rc;
+  if (nacc < 0 || nacc > nchan) return fail("sg_traj_add_noise: nacc out of range");
+  if (!(sigma_acc >= 0) || !(sigma_gyro >= 0)) return fail("sg_traj_add_noise: negative or NaN sigma");
+  if ((mean == nullptr) != (stdev == nullptr)) return fail("sg_traj_add_noise: mean and std must be given together");
+  int sms = 0;
+  if (int rc = traj_sm_count(device, &sms)) return rc;
+  if (nrows == 0) return 0;
+  CUDA_OK(cudaSetDevice(device));
+  return precision == 32 ? traj_noise_launch<float>(traj_in, traj_out, nrows, nchan, nacc, sigma_acc, sigma_gyro, seed, mean, stdev, sms, stream)
+                         : traj_noise_launch<double>(traj_in, traj_out, nrows, nchan, nacc, sigma_acc, sigma_gyro, seed, mean, stdev, sms, stream);
+}
+
+static int traj_stats_block(int nchan) {           // a multiple of 32 and of nchan / 4: 384 threads for 12 or 24 channels
+  const int qpr = nchan / 4;
+  int l = 32;
+  while (l % qpr) l += 32;                         // lcm(32, qpr) <= 480 for qpr <= 16
+  int block = l;
+  while (block + l <= 384) block += l;
+  return block;
+}
+
+static int traj_stats_grid(int nchan, long long nrows, int sms) {
+  const int block = traj_stats_block(nchan);
+  const long long nquad = nrows * (nchan / 4);
+  long long grid = (nquad + block - 1) / block;
+  const long long cap = (long long)sms * (1536 / block);
+  if (grid > cap) grid = cap;
+  return (int)(grid < 1 ? 1 : grid);
+}
+
+extern "C" long long sg_traj_stats_workspace_bytes(long long nrows, int nchan, int device) {
+  if (nrows < 0 || nchan < 4 || nchan % 4 != 0 || nchan > TRAJ_STATS_MAX_CHAN) return fail("sg_traj_stats_workspace_bytes: bad shape");
+  int sms = 0;
+  if (int rc = traj_sm_count(device, &sms)) return rc;
+  return (long long)traj_stats_grid(nchan, nrows, sms) * 2 * nchan * (long long)sizeof(double);
+}
+
+template <typename T>
+static int traj_stats_launch(const void* in, long long nrows, int nchan, double* mean, double* stdev, void* ws, int sms, void* stream) {
+  TrajStatsArgs<T> A;
+  A.in = (const T*)in; A.nrows = nrows; A.nchan = nchan; A.partial = (double*)ws; A.mean = mean; A.stdev = stdev;
+  const int block = traj_stats_block(nchan);
+  A.nblocks = traj_stats_grid(nchan, nrows, sms);
+  auto k1 = sg_traj_stats_partial_kernel<T>;
+  SG_LAUNCH(k1, A.nblocks, block, (size_t)block * 8 * sizeof(double), (cudaStream_t)stream, A);
+  CUDA_OK(cudaGetLastError());
+  auto k2 = sg_traj_stats_final_kernel<T>;
+  SG_LAUNCH(k2, 1, 64, 0, (cudaStream_t)stream, A);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sg_traj_channel_stats(const void* traj, long long nrows, int nchan, int precision, int device, double* mean_out,
+                                     double* std_out, void* workspace, long long workspace_bytes, void* stream) {
+  if (int rc = traj_check("sg_traj_channel_stats", traj, nrows, nchan, precision)) return rc;
+  if (!mean_out || !std_out || !workspace) return fail("sg_traj_channel_stats: null output or workspace");
+  if (nrows < 1) return fail("sg_traj_channel_stats: needs at least one row");
+  const long long need = sg_traj_stats_workspace_bytes(nrows, nchan, device);
+  if (need < 0) return (int)need;
+  if (workspace_bytes < need) return fail("sg_traj_channel_stats: workspace too small (see sg_traj_stats_workspace_bytes)");
+  int sms = 0;
+  if (int rc = traj_sm_count(device, &sms)) return rc;
+  CUDA_OK(cudaSetDevice(device));
+  return precision == 32 ? traj_stats_launch<float>(traj, nrows, nchan, mean_out, std_out, workspace, sms, stream)
+                         : traj_stats_launch<double>(traj, nrows, nchan, mean_out, std_out, workspace, sms, stream);
+}

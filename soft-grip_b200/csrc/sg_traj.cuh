@@ -1,0 +1,164 @@
+// sg_traj.cuh -- kernels on the trajectory buffer [N][T][C] that the step kernel writes (the data format downstream of
+// the hot path): what the reference's trainer does to a dataset before it reaches a net.
+//
+//   sg_traj_noise_kernel     functions/optimization.py:6-14 `noised_modality`: accelerometer channels += N(0, 0.7),
+//                            gyro channels += N(0, 0.06); optionally fused with the standardisation (x - mean) / std of
+//                            functions/optimization.py:38.
+//   sg_traj_stats_*_kernel   functions/utils.py:39-40: per-channel mean / standard deviation over axes (0, 1).
+//
+// Both are streaming, HBM-bound passes (no reuse): 128-bit loads/stores of four consecutive channels per thread, grids
+// sized as SM count x resident CTAs, grid-stride loops.  Algorithmic bytes: noise 2*s per element (read + write),
+// stats s per element (read once), s = 4 (fp32) or 8 (fp64).
+//
+// Random numbers: Philox4x32-10 (Salmon et al., SC'11; the generator behind tf.random / curand / torch.cuda) keyed by the
+// 64-bit seed, counter = index of the 4-element group, so a draw depends only on (seed, element index): not on the
+// grid, the sharding of worlds over GPUs or the batch precision.  Normals by Box-Muller in fp32 from the four words.
+#pragma once
+#include <stdint.h>
+
+#include "sg_rt.hpp"
+
+namespace sg {
+
+struct Philox4 { uint32_t x, y, z, w; };
+
+// ten rounds of Philox4x32 (multipliers 0xD2511F53 / 0xCD9E8D57, Weyl key increments 0x9E3779B9 / 0xBB67AE85)
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(Philox4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c.x, p1 = (uint64_t)0xCD9E8D57u * c.z;
+    Philox4 n;
+    n.x = (uint32_t)(p1 >> 32) ^ c.y ^ k0;
+    n.y = (uint32_t)p1;
+    n.z = (uint32_t)(p0 >> 32) ^ c.w ^ k1;
+    n.w = (uint32_t)p0;
+    c = n;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// uniform in (0, 1]: never 0, so the logarithm below is finite (x * 2^-32 is exact in fp32, so fma or mul+add agree)
+__device__ __forceinline__ float u01(uint32_t x) { return (float)x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }
+
+// two standard normals from two words
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  const float r = sqrtf(-2.0f * logf(u01(a)));
+  float s, c;
+  sincospif(2.0f * u01(b), &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+
+template <typename T> struct Vec4 { T v[4]; };
+__device__ __forceinline__ Vec4<float> load4(const float* p) { const float4 q = *(const float4*)p; return {{q.x, q.y, q.z, q.w}}; }
+__device__ __forceinline__ Vec4<double> load4(const double* p) {
+  const double2 a = *(const double2*)p, b = *(const double2*)(p + 2);
+  return {{a.x, a.y, b.x, b.y}};
+}
+__device__ __forceinline__ void store4(float* p, const Vec4<float>& v) { float4 q; q.x = v.v[0]; q.y = v.v[1]; q.z = v.v[2]; q.w = v.v[3]; *(float4*)p = q; }
+__device__ __forceinline__ void store4(double* p, const Vec4<double>& v) {
+  double2 a, b; a.x = v.v[0]; a.y = v.v[1]; b.x = v.v[2]; b.y = v.v[3];
+  *(double2*)p = a; *(double2*)(p + 2) = b;
+}
+
+template <typename T>
+struct TrajNoiseArgs {
+  const T* in;          // [nelem], 16-byte aligned; may alias out
+  T* out;
+  long long nelem;      // rows * nchan, nchan % 4 == 0
+  int nchan, nacc;      // channels < nacc get sigma_acc, the others sigma_gyro
+  float sigma_acc, sigma_gyro;
+  uint32_t k0, k1;      // seed
+  const double* mean;   // [nchan] or null: fused (x - mean) / std after the noise
+  const double* stdev;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) sg_traj_noise_kernel(const __grid_constant__ TrajNoiseArgs<T> A) {
+  const long long nquad = A.nelem >> 2, stride = (long long)gridDim.x * blockDim.x;
+  const int qpr = A.nchan >> 2;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += stride) {
+    Vec4<T> v = load4(A.in + 4 * q);
+    const Philox4 r = philox4x32_10(Philox4{(uint32_t)q, (uint32_t)((uint64_t)q >> 32), 0u, 0u}, A.k0, A.k1);
+    float z[4];
+    box_muller(r.x, r.y, z[0], z[1]);
+    box_muller(r.z, r.w, z[2], z[3]);
+    const int c0 = (int)(q % qpr) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int c = c0 + j;
+      T x = v.v[j] + (T)(c < A.nacc ? A.sigma_acc : A.sigma_gyro) * (T)z[j];
+      if (A.mean) x = (x - (T)A.mean[c]) / (T)A.stdev[c];
+      v.v[j] = x;
+    }
+    store4(A.out + 4 * q, v);
+  }
+}
+
+// ---- per-channel mean / std ---------------------------------------------------------------------------------------
+// Pass 1: every thread owns one 4-channel group of the row (blockDim.x and therefore the grid stride are multiples of
+// nchan / 4, so the group never changes) and accumulates sum and sum of squares of (x - x[row 0]) in fp64 -- the shift
+// removes the cancellation of the one-pass variance.  The CTA's threads are then added per channel in thread order and
+// the per-CTA partials are added in CTA order by pass 2: the result does not depend on scheduling.
+constexpr int TRAJ_STATS_MAX_CHAN = 64;
+
+template <typename T>
+struct TrajStatsArgs {
+  const T* in;          // [nrows][nchan], 16-byte aligned, nchan % 4 == 0
+  long long nrows;
+  int nchan;
+  double* partial;      // [gridDim.x][2][nchan]
+  double* mean;         // [nchan]  (pass 2)
+  double* stdev;        // [nchan]
+  int nblocks;          // gridDim.x of pass 1 (pass 2)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(512) sg_traj_stats_partial_kernel(const __grid_constant__ TrajStatsArgs<T> A) {
+  SG_SHARED_BYTES(smem_raw);
+  double* sh = (double*)smem_raw;                      // [8][blockDim.x]
+  const int qpr = A.nchan >> 2, tid = threadIdx.x, nt = blockDim.x;
+  const long long nquad = A.nrows * qpr, stride = (long long)gridDim.x * nt;
+  const int g = tid % qpr;                             // this thread's channel group
+  const Vec4<T> sv = load4(A.in + 4 * g);
+  double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+#pragma unroll 4
+  for (long long q = (long long)blockIdx.x * nt + tid; q < nquad; q += stride) {
+    const Vec4<T> v = load4(A.in + 4 * q);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const double d = (double)v.v[j] - (double)sv.v[j];
+      s[j] += d;
+      ss[j] = fma(d, d, ss[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) { sh[j * nt + tid] = s[j]; sh[(4 + j) * nt + tid] = ss[j]; }
+  __syncthreads();
+  if (tid < 2 * A.nchan) {
+    const int which = tid / A.nchan, c = tid % A.nchan, cg = c >> 2, j = c & 3;
+    const double* col = sh + (which * 4 + j) * nt;
+    double acc = 0;
+    for (int u = cg; u < nt; u += qpr) acc += col[u];
+    A.partial[((long long)blockIdx.x * 2 + which) * A.nchan + c] = acc;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(64) sg_traj_stats_final_kernel(const __grid_constant__ TrajStatsArgs<T> A) {
+  const int c = threadIdx.x;
+  if (c >= A.nchan) return;
+  double s = 0, ss = 0;
+  for (int b = 0; b < A.nblocks; b++) {
+    s += A.partial[((long long)b * 2 + 0) * A.nchan + c];
+    ss += A.partial[((long long)b * 2 + 1) * A.nchan + c];
+  }
+  const double n = (double)A.nrows * 1.0, m = s / n;
+  const double var = ss / n - m * m;
+  A.mean[c] = (double)A.in[c] + m;
+  A.stdev[c] = sqrt(var > 0 ? var : 0.0);
+}
+
+}  // namespace sg

@@ -1,6 +1,7 @@
 // cuda_shim.h -- TEST INFRASTRUCTURE: the handful of CUDA runtime calls that soft-grip_b200/csrc/sg_api.cu makes,
 // mapped to host memory, so that the C-ABI host logic + the kernel source run under the SIMT emulator (simt.h).
 #pragma once
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -33,3 +34,4 @@ template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribu
 template <typename F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t smem) {
   *n = (int)((227 * 1024) / (smem ? smem : 1)); if (*n > 32) *n = 32; return cudaSuccess;
 }
+inline void sincospif(float x, float* s, float* c) { const double a = 3.14159265358979323846 * (double)x; *s = (float)sin(a); *c = (float)cos(a); }

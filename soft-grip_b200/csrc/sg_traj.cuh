@@ -79,13 +79,18 @@ template <typename T>
 __global__ void __launch_bounds__(256) sg_traj_noise_kernel(const __grid_constant__ TrajNoiseArgs<T> A) {
   const long long nquad = A.nelem >> 2, stride = (long long)gridDim.x * blockDim.x;
   const int qpr = A.nchan >> 2;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nquad; q += stride) {
+  const long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int g = (int)(q0 % qpr);                               // channel group of q, carried along instead of a 64-bit modulo per quad
+  const int gstep = (int)(stride % qpr);
+  for (long long q = q0; q < nquad; q += stride) {
     Vec4<T> v = load4(A.in + 4 * q);
     const Philox4 r = philox4x32_10(Philox4{(uint32_t)q, (uint32_t)((uint64_t)q >> 32), 0u, 0u}, A.k0, A.k1);
     float z[4];
     box_muller(r.x, r.y, z[0], z[1]);
     box_muller(r.z, r.w, z[2], z[3]);
-    const int c0 = (int)(q % qpr) * 4;
+    const int c0 = g * 4;
+    g += gstep;
+    if (g >= qpr) g -= qpr;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int c = c0 + j;

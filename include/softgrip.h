@@ -161,6 +161,15 @@ int sg_traj_add_noise(const void* traj_in, void* traj_out, long long nrows, int 
 int sg_traj_channel_stats(const void* traj, long long nrows, int nchan, int precision, int device, double* mean_out,
                           double* std_out, void* workspace, long long workspace_bytes, void* stream);
 long long sg_traj_stats_workspace_bytes(long long nrows, int nchan, int device);
+/* replaces `if args.mask_contact and not contact: readings = np.zeros_like(readings)` (ref: create_dataset.py:43-44,
+ * 57-58) for a whole rollout: traj [nworlds][nrows_per_world][nchan] in place, touch dev [nworlds][nrows_per_world] as
+ * written by sg_batch_rollout (finger-group bits of the row's object contacts, any_bit set when ncon >= 1).
+ * mode 0 "intended": a row is kept iff (touch & all_fingers) == all_fingers.  mode 1 "reference-literal"
+ * (ref: manenv.py:65-83 with its aliased class-level finger list): while fingers are left the flag is "all fingers seen
+ * so far", afterwards "ncon >= 1"; fingers_left (dev [nworlds] ints, in/out, NULL = every episode starts with the full
+ * list and nothing is carried) holds the finger bits not yet seen. */
+int sg_traj_mask_contact(void* traj, const int* touch, int nworlds, int nrows_per_world, int nchan, int all_fingers,
+                         int any_bit, int mode, int* fingers_left, int precision, int device, void* stream);
 
 #ifdef __cplusplus
 }

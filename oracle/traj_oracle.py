@@ -10,6 +10,8 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import 
   Box-Muller evaluated in float64.  Parity of the reference's semantics is distributional (mean 0, the two sigmas,
   which channels get which) and is tested as such.
 * ``channel_mean_std`` is the reference's own numpy expression, ref: functions/utils.py:39-40.
+* ``mask_contact`` follows ref: create_dataset.py:43-44,57-58 with the contact flag of ref: manenv.py:65-83, written the
+  way the reference writes it (a finger-name list that contacts remove entries from), per world and per recorded row.
 """
 import numpy as np
 
@@ -75,3 +77,37 @@ def channel_mean_std(train_x):
     train_x = np.asarray(train_x, dtype=np.float64)
     ax = tuple(range(train_x.ndim - 1))
     return np.mean(train_x, axis=ax, keepdims=True), np.std(train_x, axis=ax, keepdims=True)
+
+
+def contact_flag_literal(fingers_left, row_fingers, ncon_positive):
+    """One call of get_sensor_sensordata (ref: manenv.py:65-83) reduced to what decides its flag.  ``fingers_left`` is the
+    class-level list the method aliases and mutates (ref: manenv.py:70,80); ``row_fingers`` are the finger names that
+    touch an object geom in this row's contacts.  While the list is non-empty the flag turns true when the row's contacts
+    empty it; once it is empty, ``len(fingers_left) == 0`` holds at the first contact, so the flag is ``ncon >= 1``."""
+    if len(fingers_left) == 0:
+        return bool(ncon_positive)
+    for name in list(row_fingers):
+        if name in fingers_left:
+            fingers_left.remove(name)
+    return len(fingers_left) == 0
+
+
+def mask_contact(traj, touch, nfingers, any_bit, mode, fingers_left=None):
+    """traj (W,T,C), touch (W,T) int bit masks (bit k: finger k touches an object geom in that row; any_bit: ncon >= 1).
+    mode "intended": flag = every finger touches in this row.  mode "reference": the literal list semantics, one list per
+    world, carried across rows (and across calls when ``fingers_left`` -- a list of per-world lists -- is given).
+    Returns the masked copy (rows with a false flag zeroed, ref: create_dataset.py:43-44,57-58)."""
+    traj = np.array(traj, copy=True)
+    touch = np.asarray(touch)
+    W, T = touch.shape
+    for w in range(W):
+        left = list(range(nfingers)) if fingers_left is None else fingers_left[w]
+        for t in range(T):
+            row = [k for k in range(nfingers) if (int(touch[w, t]) >> k) & 1]
+            if mode == "intended":
+                flag = len(row) == nfingers
+            else:
+                flag = contact_flag_literal(left, row, int(touch[w, t]) & any_bit)
+            if not flag:
+                traj[w, t] = 0
+    return traj

@@ -63,6 +63,7 @@ SIGNATURES = {
                                     C.c_int, C.c_int, V]),
     "sg_traj_channel_stats": (C.c_int, [V, C.c_longlong, C.c_int, C.c_int, C.c_int, V, V, V, C.c_longlong, V]),
     "sg_traj_stats_workspace_bytes": (C.c_longlong, [C.c_longlong, C.c_int, C.c_int]),
+    "sg_traj_mask_contact": (C.c_int, [V, V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, V, C.c_int, C.c_int, V]),
 }
 
 

@@ -146,6 +146,7 @@ class BatchedManEnv:
         self.info = self.dm.info
         h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._device_index = int(idx)
         check(self.L.sg_batch_create(self.dm.h, self.W, idx, 32 if dtype == torch.float32 else 64, C.byref(h)))
         self.h = h
         self.nsd, self.nu, self.nv = self.info.nsensordata, self.info.nu, self.info.nv
@@ -278,6 +279,22 @@ class BatchedManEnv:
         check(self.L.sg_batch_rollout(self.h, C.byref(sc), self._ptr(traj), self._ptr(touch), self._stream()))
         st = torch.from_numpy(self.status()).to(self.device)
         return (traj, k, st, touch) if return_touch else (traj, k, st)
+
+    def mask_contact(self, traj, touch):
+        """``--mask-contact`` of the reference driver for a whole rollout, on the device and in place: rows recorded
+        without finger-object contact are zeroed (ref: create_dataset.py:43-44,57-58), with this environment's
+        ``contact_mode`` ("reference": the aliased finger list of manenv.py:70,80 is carried from row to row and from
+        episode to episode in ``_fingers_left``).  traj [W,T,C] and touch [W,T] as returned by :meth:`rollout`."""
+        if traj.shape[:2] != touch.shape or traj.shape[0] != self.W or not traj.is_contiguous() or not touch.is_contiguous():
+            raise ValueError("traj must be [W,T,C] and touch [W,T], both contiguous")
+        if touch.dtype != self.torch.int32 or traj.dtype != self.dtype:
+            raise TypeError("touch must be int32 and traj in the batch precision")
+        mode = 1 if self.contact_mode == "reference" else 0
+        check(self.L.sg_traj_mask_contact(self._ptr(traj), self._ptr(touch), self.W, int(traj.shape[1]), int(traj.shape[2]),
+                                          self.dm.all_fingers, TOUCH_ANY, mode, self._ptr(self._fingers_left) if mode else None,
+                                          32 if self.dtype == self.torch.float32 else 64,
+                                          self._device_index, self._stream()))
+        return traj
 
     # ---- state access (parity tests) ---------------------------------------------------------
     def get_state(self):

@@ -89,10 +89,9 @@ def log_into_file_batched(args):
                                     sim_start=args.sim_start, sim_step=args.sim_step)
         sched = batched.default_schedule(env.nu, START_STEP, MAX_ITER_PER_EP, OPEN_CLOSE_DIV)
         traj, k, st, touch = env.rollout(schedule=sched, return_touch=True)
-        traj = traj.double().cpu().numpy()
         if args.mask_contact:
-            allf = env.dm.all_fingers
-            traj = dataset.mask_contact(traj, (touch.cpu().numpy() & allf) == allf)
+            env.mask_contact(traj, touch)            # on the device, in place
+        traj = traj.double().cpu().numpy()
         ndiv = int(((st.cpu().numpy() & batched.ST_DIVERGED) != 0).sum())
         if ndiv:
             print("warning: {} of {} worlds diverged and were reset mid-episode".format(ndiv, args.batched))

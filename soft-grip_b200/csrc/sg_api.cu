@@ -780,3 +780,33 @@ extern "C" int sg_traj_channel_stats(const void* traj, long long nrows, int ncha
   return precision == 32 ? traj_stats_launch<float>(traj, nrows, nchan, mean_out, std_out, workspace, sms, stream)
                          : traj_stats_launch<double>(traj, nrows, nchan, mean_out, std_out, workspace, sms, stream);
 }
+
+template <typename T>
+static int traj_mask_launch(void* traj, const int* touch, int nworlds, int T_, int nchan, int allf, int anybit, int mode, int* fleft,
+                            int sms, void* stream) {
+  TrajMaskArgs<T> A;
+  A.traj = (T*)traj; A.touch = touch; A.nworlds = nworlds; A.T_ = T_; A.nchan = nchan; A.allf = allf; A.anybit = anybit; A.mode = mode;
+  A.fleft = fleft;
+  const int block = 256, wpb = block / 32;
+  long long grid = ((long long)nworlds + wpb - 1) / wpb;
+  if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+  auto kp = sg_traj_mask_kernel<T>;
+  SG_LAUNCH(kp, (int)grid, block, 0, (cudaStream_t)stream, A);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int sg_traj_mask_contact(void* traj, const int* touch, int nworlds, int nrows_per_world, int nchan, int all_fingers,
+                                    int any_bit, int mode, int* fingers_left, int precision, int device, void* stream) {
+  if (int rc = traj_check("sg_traj_mask_contact", traj, (long long)nworlds * nrows_per_world, nchan, precision)) return rc;
+  if (!touch) return fail("sg_traj_mask_contact: null touch");
+  if (nworlds < 0 || nrows_per_world < 0) return fail("sg_traj_mask_contact: negative shape");
+  if (mode != 0 && mode != 1) return fail("sg_traj_mask_contact: mode must be 0 (intended) or 1 (reference-literal)");
+  if (all_fingers & any_bit) return fail("sg_traj_mask_contact: any_bit overlaps the finger bits");
+  int sms = 0;
+  if (int rc = traj_sm_count(device, &sms)) return rc;
+  if (nworlds == 0 || nrows_per_world == 0) return 0;
+  CUDA_OK(cudaSetDevice(device));
+  return precision == 32 ? traj_mask_launch<float>(traj, touch, nworlds, nrows_per_world, nchan, all_fingers, any_bit, mode, fingers_left, sms, stream)
+                         : traj_mask_launch<double>(traj, touch, nworlds, nrows_per_world, nchan, all_fingers, any_bit, mode, fingers_left, sms, stream);
+}

@@ -6,7 +6,10 @@
 //                            functions/optimization.py:38.
 //   sg_traj_stats_*_kernel   functions/utils.py:39-40: per-channel mean / standard deviation over axes (0, 1).
 //
-// Both are streaming, HBM-bound passes (no reuse): 128-bit loads/stores of four consecutive channels per thread, grids
+//   sg_traj_mask_kernel      create_dataset.py:43-44,57-58 `--mask-contact`: rows recorded without finger-object contact are
+//                            zeroed, with the contact flag of manenv.py:65-83 in its intended and its literal meaning.
+//
+// The first two are streaming, HBM-bound passes (no reuse): 128-bit loads/stores of four consecutive channels per thread, grids
 // sized as SM count x resident CTAs, grid-stride loops.  Algorithmic bytes: noise 2*s per element (read + write),
 // stats s per element (read once), s = 4 (fp32) or 8 (fp64).
 //
@@ -164,6 +167,62 @@ __global__ void __launch_bounds__(64) sg_traj_stats_final_kernel(const __grid_co
   const double var = ss / n - m * m;
   A.mean[c] = (double)A.in[c] + m;
   A.stdev[c] = sqrt(var > 0 ? var : 0.0);
+}
+
+// ---- --mask-contact -------------------------------------------------------------------------------------------------
+// One warp per world: 32 rows' touch words per coalesced load, the keep flag per row, then the rows without contact are
+// zeroed by 128-bit stores that cover the 32 rows contiguously (a kept row costs no trajectory traffic at all).
+//   mode 0 "intended": keep a row iff every finger group touched an object geom during it: (touch & allf) == allf.
+//   mode 1 "reference-literal" (SURVEY App. C item 2): get_sensor_sensordata removes the fingers it has seen from a
+//     class-level list that is never refilled; while fingers are left the flag is "the list ran empty during this row",
+//     afterwards it is "ncon >= 1".  Per world that is a prefix-OR over the rows (warp shuffle scan + carry), with the
+//     fingers still left carried in and out through `fleft` so that consecutive episodes continue the list.
+template <typename T>
+struct TrajMaskArgs {
+  T* traj;              // [nworlds][T][nchan], 16-byte aligned, nchan % 4 == 0
+  const int* touch;     // [nworlds][T]: finger-group bits of the row's object contacts | anybit when ncon >= 1
+  int nworlds, T_, nchan;
+  int allf, anybit, mode;
+  int* fleft;           // [nworlds] or null (mode 1): fingers not yet seen, in/out
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) sg_traj_mask_kernel(const __grid_constant__ TrajMaskArgs<T> A) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, qpr = A.nchan >> 2;
+  const unsigned FULL = 0xffffffffu;
+  Vec4<T> zero;
+  zero.v[0] = zero.v[1] = zero.v[2] = zero.v[3] = T(0);
+  for (long long w = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); w < A.nworlds; w += (long long)gridDim.x * wpb) {
+    int seen = 0;                                        // finger bits seen before this chunk (mode 1)
+    if (A.mode == 1 && A.fleft) seen = A.allf & ~A.fleft[w];
+    for (int r0 = 0; r0 < A.T_; r0 += 32) {
+      const bool in = r0 + lane < A.T_;
+      const int tv = in ? A.touch[w * A.T_ + r0 + lane] : 0;
+      bool keep;
+      if (A.mode == 0) {
+        keep = (tv & A.allf) == A.allf;
+      } else {
+        int inc = tv & A.allf;                           // inclusive prefix OR over the chunk's rows
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_sync(FULL, inc, (lane - d) & 31);
+          if (lane >= d) inc |= o;
+        }
+        int exc = __shfl_sync(FULL, inc, (lane - 1) & 31);
+        exc = (lane ? exc : 0) | seen;
+        inc |= seen;
+        keep = exc == A.allf ? (tv & A.anybit) != 0 : inc == A.allf;
+        seen = __shfl_sync(FULL, inc, 31);
+      }
+      const int kept = (keep || !in) ? 1 : 0;
+      T* base = A.traj + (w * A.T_ + r0) * A.nchan;
+      for (int i = 0; i < qpr; i++) {
+        const int lq = i * 32 + lane;
+        if (!__shfl_sync(FULL, kept, lq / qpr)) store4(base + 4 * lq, zero);
+      }
+    }
+    if (A.mode == 1 && A.fleft && lane == 0) A.fleft[w] = A.allf & ~seen;
+  }
 }
 
 }  // namespace sg

@@ -117,6 +117,58 @@ def test_emulated_channel_stats_match_numpy(emulib, dtype, shape):
     assert (mean2 == mean).all() and (std2 == std).all()                 # fixed summation order
 
 
+def _touch(W, T, seed, p_finger=0.3):
+    """Random per-row contact words: finger bits 0/1, TOUCH_ANY (bit 30) when there is any contact at all."""
+    rng = np.random.default_rng(seed)
+    f = (rng.random((W, T)) < p_finger).astype(np.int32) | ((rng.random((W, T)) < p_finger).astype(np.int32) << 1)
+    anyc = (f != 0) | (rng.random((W, T)) < 0.3)
+    t = f | (anyc.astype(np.int32) << 30)
+    t[0] = 0                       # a world that never touches
+    t[1] = 3 | (1 << 30)           # a world that always touches with both fingers
+    return np.ascontiguousarray(t)
+
+
+@pytest.mark.parametrize("dtype,T,nchan", [(np.float32, 200, 12), (np.float64, 200, 12), (np.float32, 33, 24), (np.float32, 1, 4)])
+@pytest.mark.parametrize("mode", ["intended", "reference"])
+def test_emulated_mask_contact_matches_the_literal_restatement(emulib, dtype, T, nchan, mode):
+    W = 21                                                    # 16 warps in the emulated grid: grid-stride over worlds
+    x = _traj(W, T, nchan, dtype, seed=6) + 1000.0            # no accidental zeros
+    touch = _touch(W, T, seed=7, p_finger=0.08 if mode == "reference" else 0.6)
+    prec = 32 if dtype == np.float32 else 64
+    y = x.copy()
+    left = np.full(W, 3, dtype=np.int32)
+    left[5] = 0                                               # a world whose list ran empty in an earlier episode
+    lists = [[k for k in range(2) if (int(v) >> k) & 1] for v in left]
+    m = 1 if mode == "reference" else 0
+    assert emulib.sg_traj_mask_contact(_vp(y), _vp(touch), W, T, nchan, 3, 1 << 30, m, _vp(left) if m else None, prec, 0, None) == 0
+    want = to.mask_contact(x, touch, 2, 1 << 30, mode, fingers_left=lists)
+    assert (y == want).all()
+    assert 0 < (want == 0).all(axis=-1).mean() < 1            # the case masks some rows and keeps some
+    if m:
+        assert [[k for k in range(2) if (int(v) >> k) & 1] for v in left] == lists      # the carried list state
+        # second episode continues with the carried lists
+        y2 = x.copy()
+        assert emulib.sg_traj_mask_contact(_vp(y2), _vp(touch), W, T, nchan, 3, 1 << 30, 1, _vp(left), prec, 0, None) == 0
+        assert (y2 == to.mask_contact(x, touch, 2, 1 << 30, mode, fingers_left=lists)).all()
+        # without carried state every call starts from the full list
+        y3 = x.copy()
+        assert emulib.sg_traj_mask_contact(_vp(y3), _vp(touch), W, T, nchan, 3, 1 << 30, 1, None, prec, 0, None) == 0
+        assert (y3 == to.mask_contact(x, touch, 2, 1 << 30, mode)).all()
+
+
+def test_batched_contact_flag_agrees_with_the_row_scan():
+    """BatchedManEnv._contact_flag (the per-step torch expression) and the rollout mask use the same semantics."""
+    touch = _touch(6, 40, seed=9, p_finger=0.1)
+    x = np.ones((6, 40, 4))
+    want = to.mask_contact(x, touch, 2, 1 << 30, "reference")
+    left = np.full(6, 3)
+    for t in range(40):
+        was_empty = left == 0
+        left = left & ~(touch[:, t] & 3)
+        flag = np.where(was_empty, (touch[:, t] & (1 << 30)) != 0, left == 0)     # batched.py _contact_flag
+        assert (flag == (want[:, t, 0] != 0)).all()
+
+
 def test_trajectory_entry_points_reject_bad_arguments(emulib):
     x = np.zeros((4, 12), dtype=np.float32)
     bad = np.zeros(4 * 12 + 1, dtype=np.float32)[1:]                     # 4-byte aligned only
@@ -134,6 +186,11 @@ def test_trajectory_entry_points_reject_bad_arguments(emulib):
     assert emulib.sg_traj_channel_stats(_vp(x), 4, 12, 32, 0, _vp(m), _vp(m), _vp(ws), 8, None) < 0 and "workspace" in err()
     assert emulib.sg_traj_channel_stats(_vp(x), 0, 12, 32, 0, _vp(m), _vp(m), _vp(ws), 64, None) < 0 and "one row" in err()
     assert emulib.sg_traj_stats_workspace_bytes(4, 7, 0) < 0
+    t = np.zeros(4, dtype=np.int32)
+    assert emulib.sg_traj_mask_contact(_vp(x), None, 4, 1, 12, 3, 1 << 30, 0, None, 32, 0, None) < 0 and "touch" in err()
+    assert emulib.sg_traj_mask_contact(_vp(x), _vp(t), 4, 1, 12, 3, 1 << 30, 2, None, 32, 0, None) < 0 and "mode" in err()
+    assert emulib.sg_traj_mask_contact(_vp(x), _vp(t), 4, 1, 12, 3, 1, 0, None, 32, 0, None) < 0 and "any_bit" in err()
+    assert emulib.sg_traj_mask_contact(_vp(x), _vp(t), 0, 1, 12, 3, 1 << 30, 0, None, 32, 0, None) == 0
 
 
 def test_python_mirror_fails_loudly_without_a_gpu():
@@ -182,6 +239,30 @@ def test_gpu_noise_and_stats_match_the_oracle(torch_cuda, dtype):
     wantf = to.noised_modality(x, seed, mean=wm, std=wsd)
     tolf = (sig * Z_TOL) / wsd.reshape(-1) + (np.abs(wantf) + np.abs(wm / wsd).reshape(-1)) * (4e-7 if dtype == "float32" else 1e-14)
     assert (np.abs(fused.cpu().numpy() - wantf) <= tolf).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["intended", "reference"])
+def test_gpu_rollout_mask_contact_matches_the_restatement(torch_cuda, mode):
+    """A real rollout's touch words: the device mask equals the literal restatement, and (reference mode) the carried
+    finger lists continue into a second episode."""
+    torch = torch_cuda
+    from conftest import blob_path
+    batched = pkg("batched")
+    env = batched.BatchedManEnv(blob_path("softbox"), 96, dtype=torch.float32, seed=3, contact_mode=mode)
+    sched = batched.default_schedule(2, n_settle=4, n_iter=60, open_close_div=30)
+    lists = [[0, 1] for _ in range(96)]
+    for episode in range(2):
+        traj, k, st, touch = env.rollout(schedule=sched, return_touch=True)
+        raw = traj.cpu().numpy().copy()
+        env.mask_contact(traj, touch)
+        want = to.mask_contact(raw, touch.cpu().numpy(), 2, batched.TOUCH_ANY, mode, fingers_left=lists if mode == "reference" else None)
+        assert (traj.cpu().numpy() == want).all()
+        zero_rows = (want == 0).all(axis=-1)
+        assert zero_rows[:, :4].all()                                   # nothing touches during the settle rows
+        assert not zero_rows.all()                                      # the squeeze makes contact
+    if mode == "reference":
+        assert env._fingers_left.cpu().numpy().tolist() == [sum(1 << k for k in l) for l in lists]
 
 
 @pytest.mark.gpu

@@ -277,7 +277,7 @@ def test_gpu_trajectory_kernels_at_full_size_properties(torch_cuda):
     d = (y - x).double()
     sd = d.std(dim=(0, 1)).cpu().numpy()
     assert np.allclose(sd[:6], 0.7, rtol=2e-3) and np.allclose(sd[6:], 0.06, rtol=2e-3)
-    assert float(d.mean(dim=(0, 1)).abs().max()) < 5e-4
+    assert float(d.mean(dim=(0, 1)).abs().max()) < 1.5e-3            # 0.7 / sqrt(1.3e7) = 2e-4 per channel
     # sharding invariance: the second half of the buffer noised on its own with the matching element offset is not
     # expressible through the API, but the first half is a prefix of the same counter stream
     yh = fn.noised_modality(x[: W // 2].contiguous(), seed=7)

@@ -1,0 +1,185 @@
+"""Regenerate the simulated part of the paper's dataset tree in one go (BASELINE.json configs[3]).
+
+The reference produces these files by running ``create_dataset.py`` once per file with ``NUM_EPISODES`` edited by hand
+(ref: create_dataset.py:14,83-93) and consumes them in ``run_experiments.sh`` (ref: run_experiments.sh:2-7):
+
+    sim_box/train.pickle  sim_box/val.pickle                                   (stage 1 and 3: softbox only)
+    sim_all/train.pickle  sim_all/{softball,softbox,softcylinder}_testing.pickle   (stage 2: all three shapes)
+
+every file in the layout of ref: create_dataset.py:75-78 (``{"data": [N x (200,12) f64], "stiffness": [N x f64]}``).
+The repo does not state the paper's sample counts (SURVEY section 8d cfg 4), so they are parameters.
+
+Each sample is one squeeze episode of one world; samples of a model are numbered by a *global world id* and the
+per-world stiffness is drawn from that id (``batched.world_uniform``), so the files are disjoint by construction and do
+not depend on how many worlds went into a launch or on how many GPUs were used.  Per file a ``*.stats.npz`` holds the
+per-channel mean / std computed on the device (ref: functions/utils.py:39-40) and the per-stiffness-bin feature
+statistics; ``--npz`` also writes the tensors ``(N,200,12)`` / ``(N,)`` for loaders that do not want Python lists.
+
+    python regenerate.py --out data/experiments --train 4096 --val 512 --test 512 \
+        --softbox A.xml --softball B.xml --softcylinder C.xml
+"""
+import importlib
+import os
+import sys
+import time
+from argparse import ArgumentParser
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+if os.path.dirname(_HERE) not in sys.path:
+    sys.path.insert(0, os.path.dirname(_HERE))
+_PKG = os.path.basename(_HERE)
+
+SHAPES = ("softball", "softbox", "softcylinder")      # order of the stage-2 command line (ref: run_experiments.sh:7)
+
+
+def plan_files(n_train, n_val, n_test, shapes=SHAPES):
+    """-> list of (relative file stem, [(shape, first global world id, count), ...]).
+
+    World ids of a shape are handed out consecutively, file after file, so no two files share a sample."""
+    nxt = {s: 0 for s in shapes}
+
+    def take(shape, n):
+        part = (shape, nxt[shape], int(n))
+        nxt[shape] += int(n)
+        return part
+
+    files = []
+    if "softbox" in shapes:
+        files.append(("sim_box/train", [take("softbox", n_train)]))
+        files.append(("sim_box/val", [take("softbox", n_val)]))
+    files.append(("sim_all/train", [take(s, n_train // len(shapes) + (i < n_train % len(shapes))) for i, s in enumerate(shapes)]))
+    for s in shapes:
+        files.append(("sim_all/{}_testing".format(s), [take(s, n_test)]))
+    return [(stem, [p for p in parts if p[2] > 0]) for stem, parts in files]
+
+
+class DeviceRollouts:
+    """Episodes of global world ids [first, first + count) of one model, ``worlds_per_launch`` at a time.
+
+    Yields device tensors (traj [n,200,12] fp32, stiffness [n] fp64, status [n] int32); masking happens on the device."""
+
+    def __init__(self, model_paths, seed=0, worlds_per_launch=16384, device="cuda:0", mask_contact=False, contact_mode="intended",
+                 sim_start=1, sim_step=7):
+        self.batched = importlib.import_module(_PKG + ".batched")
+        self.paths, self.seed, self.wpl, self.device = dict(model_paths), int(seed), int(worlds_per_launch), device
+        self.mask, self.mode, self.sim_start, self.sim_step = bool(mask_contact), contact_mode, sim_start, sim_step
+        self._dm = {}
+
+    def __call__(self, shape, first, count):
+        import torch
+        b = self.batched
+        if shape not in self._dm:
+            self._dm[shape] = b.DeviceModel(self.paths[shape])
+        done = 0
+        while done < count:
+            n = min(self.wpl, count - done)
+            env = b.BatchedManEnv(self._dm[shape], n, device=self.device, dtype=torch.float32, seed=self.seed,
+                                  sim_start=self.sim_start, sim_step=self.sim_step, world_offset=first + done, contact_mode=self.mode)
+            traj, k, st, touch = env.rollout(return_touch=True)
+            if self.mask:
+                env.mask_contact(traj, touch)
+            yield traj, k, st
+            done += n
+            del env
+
+
+def write_file(out_dir, stem, chunks, dataset, stats_fn=None, npz=False, drop_diverged=True):
+    """chunks: iterable of (traj, stiffness, status) (numpy or torch).  A world whose state was reset by the NaN / 1e10
+    check mid-episode (status bit 1; the reference's `except MujocoException: self.reset()`, ref: manenv.py:50-51) yields
+    a trace with a discontinuity; such samples are dropped unless drop_diverged is False.  Returns a summary dict."""
+    trajs, ks, dev_chunks, ndiv = [], [], [], 0
+    for traj, k, st in chunks:
+        st_np = st.cpu().numpy() if hasattr(st, "cpu") else np.asarray(st)
+        bad = (st_np & 1) != 0
+        ndiv += int(bad.sum())
+        if drop_diverged and bad.any():
+            keep = np.nonzero(~bad)[0]
+            if hasattr(traj, "cpu"):
+                import torch
+                keep = torch.from_numpy(keep).to(traj.device)
+            traj, k = traj[keep], k[keep]
+        if hasattr(traj, "cpu"):
+            dev_chunks.append(traj)
+            trajs.append(traj.double().cpu().numpy())
+            ks.append(k.double().cpu().numpy())
+        else:
+            trajs.append(np.asarray(traj, dtype=np.float64))
+            ks.append(np.asarray(k, dtype=np.float64))
+    traj = np.concatenate(trajs, 0) if trajs else np.zeros((0, 200, 12))
+    k = np.concatenate(ks, 0) if ks else np.zeros((0,))
+    path = os.path.join(out_dir, stem + ".pickle")
+    dataset.write_pickle(path, traj, k)
+    extra = {}
+    if stats_fn is not None and traj.shape[0] > 0:
+        if dev_chunks:
+            import torch
+            mean, std = stats_fn(torch.cat(dev_chunks, 0).contiguous())     # on the device, before the host copy is used
+        else:
+            mean, std = stats_fn(traj)
+        extra = {"mean": np.asarray(mean.cpu() if hasattr(mean, "cpu") else mean).reshape(-1),
+                 "std": np.asarray(std.cpu() if hasattr(std, "cpu") else std).reshape(-1)}
+    if traj.shape[0] > 0:
+        edges, bins = dataset.feature_stats(traj, k)
+        extra["bin_edges"] = edges
+        for i, b in enumerate(bins):
+            if b is not None:
+                extra.update({"bin%d_n" % i: b["n"], "bin%d_mean" % i: b["mean"], "bin%d_std" % i: b["std"], "bin%d_peak" % i: b["peak"]})
+    np.savez(os.path.join(out_dir, stem + ".stats.npz"), n=traj.shape[0], diverged=ndiv, **extra)
+    if npz:
+        dataset.write_npz(os.path.join(out_dir, stem + ".npz"), traj.astype(np.float32), k)
+    return {"file": path, "samples": int(traj.shape[0]), "diverged": ndiv}
+
+
+def regenerate(out_dir, n_train, n_val, n_test, rollouts, shapes=SHAPES, stats_fn=None, npz=False, drop_diverged=True, log=print):
+    """rollouts(shape, first_world, count) -> iterable of (traj, stiffness, status) chunks.  Returns the per-file summaries."""
+    dataset = importlib.import_module(_PKG + ".dataset")
+    out = []
+    t0 = time.perf_counter()
+    for stem, parts in plan_files(n_train, n_val, n_test, shapes):
+        def chunks():
+            for shape, first, count in parts:
+                yield from rollouts(shape, first, count)
+        s = write_file(out_dir, stem, chunks(), dataset, stats_fn=stats_fn, npz=npz, drop_diverged=drop_diverged)
+        s["parts"] = parts
+        out.append(s)
+        log("{file}: {samples} samples ({diverged} diverged)".format(**s))
+    log("dataset tree written in %.1f s" % (time.perf_counter() - t0))
+    return out
+
+
+def build_parser():
+    p = ArgumentParser(description=__doc__.split("\n")[0])
+    p.add_argument("--out", type=str, default="./data/experiments")
+    p.add_argument("--train", type=int, default=4096)
+    p.add_argument("--val", type=int, default=512)
+    p.add_argument("--test", type=int, default=512)
+    for s in SHAPES:
+        p.add_argument("--" + s, type=str, default=None, help="MJCF (.xml) or compiled blob (.sgm) of the %s scene" % s)
+    p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--worlds-per-launch", type=int, default=16384)
+    p.add_argument("--device", type=str, default="cuda:0")
+    p.add_argument("--mask-contact", action="store_true")
+    p.add_argument("--contact-mode", choices=["intended", "reference"], default="intended")
+    p.add_argument("--keep-diverged", action="store_true")
+    p.add_argument("--npz", action="store_true")
+    p.add_argument("--sim-step", type=int, default=7)
+    p.add_argument("--sim-start", type=int, default=1)
+    return p
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    paths = {s: getattr(args, s) for s in SHAPES if getattr(args, s)}
+    if not paths:
+        raise SystemExit("give at least one of --softball / --softbox / --softcylinder")
+    fn = importlib.import_module(_PKG + ".functions")
+    roll = DeviceRollouts(paths, seed=args.seed, worlds_per_launch=args.worlds_per_launch, device=args.device,
+                          mask_contact=args.mask_contact, contact_mode=args.contact_mode, sim_start=args.sim_start, sim_step=args.sim_step)
+    return regenerate(args.out, args.train, args.val, args.test, roll, shapes=tuple(s for s in SHAPES if s in paths),
+                      stats_fn=fn.channel_mean_std, npz=args.npz, drop_diverged=not args.keep_diverged)
+
+
+if __name__ == "__main__":
+    main()

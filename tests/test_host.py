@@ -143,3 +143,57 @@ def test_two_rank_sharding_with_gloo(tmp_path):
                           "127.0.0.1", "--master-port", "29617", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "OK" in out.stdout
+
+
+def test_regenerate_plans_the_reference_file_tree_with_disjoint_samples(tmp_path):
+    """BASELINE configs[3]: the simulated files run_experiments.sh consumes (ref: run_experiments.sh:2-7), each in the
+    pickle layout of create_dataset.py:75-78, no sample shared between files; driven by a stub rollout (no GPU)."""
+    rg = pkg("regenerate")
+    ds = pkg("dataset")
+    batched = pkg("batched")
+    plan = rg.plan_files(10, 4, 3)
+    stems = [s for s, _ in plan]
+    assert stems == ["sim_box/train", "sim_box/val", "sim_all/train", "sim_all/softball_testing", "sim_all/softbox_testing",
+                     "sim_all/softcylinder_testing"]
+    used = {}
+    for stem, parts in plan:
+        for shape, first, count in parts:
+            ids = set(range(first, first + count))
+            assert not (ids & used.setdefault(shape, set()))
+            used[shape] |= ids
+    assert sum(c for _, _, c in dict(plan)["sim_all/train"]) == 10 and [c for _, _, c in dict(plan)["sim_all/train"]] == [4, 3, 3]
+    assert rg.plan_files(6, 2, 2, shapes=("softbox",))[2] == ("sim_all/train", [("softbox", 8, 6)])
+
+    calls = []
+
+    def rollouts(shape, first, count):
+        calls.append((shape, first, count))
+        for a in range(0, count, 4):                      # chunks of 4 worlds per "launch"
+            n = min(4, count - a)
+            ids = np.arange(first + a, first + a + n)
+            k = batched.world_uniform(0, ids, 300.0, 1400.0)
+            traj = np.broadcast_to(k[:, None, None], (n, 200, 12)).astype(np.float32) + SHAPE_TAG[shape]
+            st = np.where(ids % 7 == 5, 1, 0)              # some worlds "diverged"
+            yield traj, k, st
+
+    SHAPE_TAG = {"softball": 0.0, "softbox": 10000.0, "softcylinder": 20000.0}
+    out = rg.regenerate(str(tmp_path), 10, 4, 3, rollouts, stats_fn=lambda t: (np.mean(t, axis=(0, 1)), np.std(t, axis=(0, 1))),
+                        npz=True, log=lambda *_: None)
+    assert [o["file"] for o in out] == [str(tmp_path / (s + ".pickle")) for s in stems]
+    seen = {}
+    for o, (stem, parts) in zip(out, plan):
+        x, y = ds.read_pickle(o["file"])                   # what functions/utils.create_tf_generators does
+        want_n = sum(c for _, _, c in parts) - o["diverged"]
+        assert x.shape == (want_n, 200, 12) and y.shape == (want_n,) and o["samples"] == want_n
+        assert ((y >= 300) & (y <= 1400)).all()
+        st = np.load(str(tmp_path / (stem + ".stats.npz")))
+        assert int(st["n"]) == want_n and np.allclose(st["mean"], x.mean(axis=(0, 1))) and st["std"].shape == (12,)
+        z = np.load(str(tmp_path / (stem + ".npz")))
+        assert z["data"].dtype == np.float32 and z["data"].shape == x.shape
+        for xi, yi in zip(x, y):                           # (shape tag, stiffness) identifies a sample: no file shares one
+            key = (round(float(xi[0, 0] - yi), -3), float(yi))
+            assert key not in seen, (stem, seen.get(key))
+            seen[key] = stem
+    assert sum(o["diverged"] for o in out) > 0
+    kept = rg.regenerate(str(tmp_path / "all"), 10, 4, 3, rollouts, drop_diverged=False, log=lambda *_: None)
+    assert [o["samples"] for o in kept] == [10, 4, 10, 3, 3, 3]

@@ -291,3 +291,28 @@ def test_gpu_trajectory_kernels_at_full_size_properties(torch_cuda):
     z = fn.noised_modality(x, seed=7, mean=mean, std=std)
     zm, zs = fn.channel_mean_std(z)
     assert float(zm.abs().max()) < 1e-4 and float((zs - 1).abs().max()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_gpu_regenerated_tree_does_not_depend_on_the_launch_size(torch_cuda, tmp_path):
+    """BASELINE configs[3] in small: the file tree from real rollouts, identical whichever way the worlds were packed into
+    launches, with the device statistics equal to numpy's on the written file."""
+    from conftest import blob_path
+    rg, fn, ds = pkg("regenerate"), pkg("functions"), pkg("dataset")
+    outs = []
+    for wpl, sub in ((64, "a"), (24, "b")):
+        roll = rg.DeviceRollouts({"softbox": blob_path("softbox")}, seed=5, worlds_per_launch=wpl)
+        outs.append(rg.regenerate(str(tmp_path / sub), 40, 8, 8, roll, shapes=("softbox",), stats_fn=fn.channel_mean_std,
+                                  drop_diverged=False, log=lambda *_: None))
+    assert [os.path.relpath(o["file"], str(tmp_path / "a")) for o in outs[0]] == [
+        "sim_box/train.pickle", "sim_box/val.pickle", "sim_all/train.pickle", "sim_all/softbox_testing.pickle"]
+    allk = []
+    for a, b in zip(*outs):
+        xa, ya = ds.read_pickle(a["file"])
+        xb, yb = ds.read_pickle(b["file"])
+        assert xa.shape == (a["samples"], 200, 12) and a["diverged"] == 0 and np.isfinite(xa).all()
+        assert (ya == yb).all() and (xa == xb).all()
+        st = np.load(a["file"].replace(".pickle", ".stats.npz"))
+        assert np.allclose(st["mean"], xa.mean(axis=(0, 1)), rtol=1e-9, atol=1e-9) and np.allclose(st["std"], xa.std(axis=(0, 1)), rtol=1e-8)
+        allk += list(ya)
+    assert len(set(allk)) == len(allk) == 40 + 8 + 40 + 8          # no sample shared between files

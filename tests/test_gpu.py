@@ -295,3 +295,37 @@ def test_many_worlds_identical_inputs_are_identical(torch_cuda, batched):
     traj, k, st = env.rollout(schedule=sched, stiffness=np.full(4096, 700.0))
     assert int((st != 0).sum()) == 0
     assert bool((traj == traj[0:1]).all())
+
+
+def test_contact_capacity_overflow_keeps_the_first_contacts(torch_cuda, batched, states, mjcf, oracle, tmp_path):
+    """More active contacts than the per-world capacity (MuJoCo: nconmax warning): the first `maxcon` contacts in MuJoCo's
+    order keep their rows, the rest are dropped and SG_ST_CON_FULL is set -- the same step as the oracle at that nconmax."""
+    torch = torch_cuda
+    cap, W = 16, 3
+    model = mjcf.load_blob(blob_path("softbox"))
+    model.opt["nconmax"] = cap
+    blob = mjcf.model_to_blob(model)
+    p = tmp_path / "softbox_cap.sgm"
+    p.write_bytes(blob)
+    ow = oracle.OracleWorld(oracle.OracleModel(blob))
+    ow.set_geom_mask(batched.geom_name_mask(model.names["geom"], "OBJ", ("g12", "g2")))
+    ow.set_stiffness(700.0)
+    os.environ["SOFTGRIP_MAXCON"] = str(cap)
+    try:
+        env = batched.BatchedManEnv(str(p), W, dtype=torch.float64)
+    finally:
+        os.environ.pop("SOFTGRIP_MAXCON", None)
+    env.set_new_stiffness(stiffness=[700.0] * W)
+    env.set_debug_world(1)
+    for i in (4, 6, 7):                               # 8 (fits), 35 and 58 contacts
+        env.status(clear=True)
+        (q1, v1, a1, qacc), sens, touch = one_step_from(env, states["q"][i], states["v"][i], states["act"][i], states["warm"][i],
+                                                        [states["ctrl"][i]] * 2, W)
+        ow.set_state(states["q"][i], states["v"][i], states["act"][i], states["warm"][i])
+        ow.set_ctrl([states["ctrl"][i]] * 2)
+        ost = ow.step()
+        oq, ov, oa, owarm = ow.get_state()
+        full = states["ncon1"][i] > cap
+        assert int(env.debug(1, "ncon_rows")[0]) == min(cap, int(states["ncon1"][i])) == ow.get_int("ncon")
+        assert bool(ost & 2) == full and all(bool(s & 2) == full for s in env.status())
+        assert rel(q1[1], oq) < FP64_TOL and rel(v1[1], ov) < FP64_TOL and rel(qacc[1], owarm) < FP64_TOL

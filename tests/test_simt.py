@@ -305,3 +305,42 @@ def test_broadphase_runs_reproduce_the_pair_list(emu, model):
     assert len(out) == npair and nrun < npair // 8          # the point of the encoding: long runs
     np.testing.assert_array_equal(np.array(out), pairs)
     env.close()
+
+
+def test_emulated_contact_capacity_overflow_keeps_the_first_contacts(emu, states, mjcf, oracle, batched, tmp_path):
+    """More contacts than the capacity (MuJoCo: nconmax warning): the first `maxcon` contacts in MuJoCo's order are kept,
+    the rest dropped, status bit SG_ST_CON_FULL set -- same step as the oracle with the same nconmax."""
+    cap = 16
+    model = mjcf.load_blob(blob_path("softbox"))
+    model.opt["nconmax"] = cap
+    blob = mjcf.model_to_blob(model)
+    p = tmp_path / "softbox_cap.sgm"
+    p.write_bytes(blob)
+    om = oracle.OracleModel(blob)
+    ow = oracle.OracleWorld(om)
+    ow.set_geom_mask(batched.geom_name_mask(model.names["geom"], "OBJ", ("g12", "g2")))
+    ow.set_stiffness(700.0)
+    os.environ["SOFTGRIP_MAXCON"] = str(cap)
+    try:
+        env = emu.EmuBatch(str(p), 5, prec=64, lpw=8)
+    finally:
+        os.environ.pop("SOFTGRIP_MAXCON", None)
+    env.set_params(stiffness=np.full(5, 700.0))
+    env.set_debug_world(4)
+    for i in (4, 6, 7):                               # 8 (fits), 35 and 58 contacts
+        env.set_state(states["q"][i], states["v"][i], states["act"][i], states["warm"][i])
+        env.set_ctrl([states["ctrl"][i]] * 2)
+        env.status(clear=True)
+        env.step(1)
+        q1, v1, a1, qacc = env.get_state()
+        ow.set_state(states["q"][i], states["v"][i], states["act"][i], states["warm"][i])
+        ow.set_ctrl([states["ctrl"][i]] * 2)
+        ost = ow.step()
+        oq, ov, oa, owarm = ow.get_state()
+        full = states["ncon1"][i] > cap
+        # "ncon" counts every detected contact, "ncon_rows" the ones that were given constraint rows (the capped list)
+        assert int(env.debug("ncon")[0]) == int(states["ncon1"][i])
+        assert int(env.debug("ncon_rows")[0]) == min(cap, int(states["ncon1"][i])) == ow.get_int("ncon")
+        assert bool(ost & 2) == full and all(bool(s & 2) == full for s in env.status())
+        assert rel(q1[-1], oq) < 1e-9 and rel(v1[-1], ov) < 1e-9 and rel(qacc[-1], owarm) < 1e-9
+    env.close()

@@ -17,6 +17,8 @@ processed in per-GPU batches so that one step takes seconds, not minutes.  Weak 
 `roofline`: HBM roofline of the rollout kernel on its algorithmic bytes (the kernel is latency/issue bound on
             the Gauss-Seidel sweep, so this fraction is tiny by construction).
 `cpu_baseline`: the fp64 oracle (a port, not libmujoco) on the host cores, bounded sample, rank 0 at N=1.
+`traj_kernels`: (N=1, outside the timed region) the HBM-bound kernels that post-process the trajectory buffer, each timed
+            alone against the HBM roof; informational, a failure there is reported in the key and never raised.
 """
 import argparse
 import ctypes as C
@@ -219,6 +221,43 @@ def workload_config(args, per_gpu, note=None):
     return cfg
 
 
+def measure_traj_kernels(torch, traj, flush, hbm_peak, reps=5):
+    """Outside the timed region, N = 1 only: the HBM-bound kernels that post-process the trajectory buffer where the rollout
+    left it (csrc/sg_traj.cuh: noise augmentation, channel statistics), each timed alone with CUDA events on the current
+    stream after an L2 flush; achieved = algorithmic bytes (noise: read + write, statistics: read) / average launch time.
+    Extra information next to the headline numbers: a failure here is reported in the key, never raised."""
+    try:
+        fn = importlib.import_module("soft-grip_b200.functions")
+        out = torch.empty_like(traj)
+        nbytes = traj.numel() * traj.element_size()
+        cases = (("sg_traj_noise_kernel<float>", lambda: fn.noised_modality(traj, seed=1, out=out), 2 * nbytes),
+                 ("sg_traj_stats_partial_kernel<float> + final", lambda: fn.channel_mean_std(traj), nbytes))
+        res = {}
+        for name, f, algo in cases:
+            ms = []
+            for r in range(reps + 2):
+                flush.fill_(r & 255)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                f()
+                e1.record()
+                torch.cuda.synchronize()
+                if r >= 2:
+                    ms.append(e0.elapsed_time(e1))
+            avg = sum(ms) / len(ms)
+            gbs = algo / (avg * 1e-3) / 1e9
+            res[name] = {"ms": avg, "algorithmic_bytes": algo, "achieved_GBps": gbs, "peak_GBps": hbm_peak, "frac": gbs / hbm_peak}
+        mean, std = fn.channel_mean_std(out)
+        ref_std = (out - traj).double().std(dim=(0, 1), unbiased=False)
+        res["check"] = {"noise_std_acc": float(ref_std[:6].mean()), "noise_std_gyro": float(ref_std[6:].mean()),
+                        "stats_vs_torch_max_rel": float(((mean.reshape(-1) - out.double().mean(dim=(0, 1))).abs()
+                                                         / (out.double().std(dim=(0, 1)) + 1e-30)).max())}
+        return res
+    except Exception as e:                                   # noqa: BLE001 -- informational key only
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -353,6 +392,10 @@ def main():
         v, cores, secs, sample, pgs_flops = cpu_throughput(blob, args.cpu_episodes_per_core, seed=args.seed)
         cpu = {"value": v, "unit": "world-steps/s", "cores": cores, "kind": "port", "sample": sample + ", %.1f s" % secs}
 
+    traj_kernels = None
+    if world == 1:
+        traj_kernels = measure_traj_kernels(torch, traj, flush, peaks["hbm_gbs"])
+
     line = {"metric": METRIC, "value": value, "unit": "world-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, Wg),
@@ -363,6 +406,8 @@ def main():
         fp32_peak = 148 * 128 * 2 * (line["clocks"]["sm_mhz"] or 1965.0) * 1e6 / 1e12
         line["fp32_pipe"] = {"pgs_flops_per_world_step_last": pgs_flops, "achieved_tflops": value / world * pgs_flops / 1e12,
                              "peak_tflops_at_sampled_clock": fp32_peak}
+    if traj_kernels is not None:
+        line["traj_kernels"] = traj_kernels
     print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

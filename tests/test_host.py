@@ -197,3 +197,15 @@ def test_regenerate_plans_the_reference_file_tree_with_disjoint_samples(tmp_path
     assert sum(o["diverged"] for o in out) > 0
     kept = rg.regenerate(str(tmp_path / "all"), 10, 4, 3, rollouts, drop_diverged=False, log=lambda *_: None)
     assert [o["samples"] for o in kept] == [10, 4, 10, 3, 3, 3]
+
+
+def test_bench_traj_kernel_probe_never_raises():
+    """bench.py's informational `traj_kernels` key: without a device the probe reports the error instead of raising, so it
+    can never take the headline JSON line down with it."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    sys.path.insert(0, ROOT)
+    import bench
+    out = bench.measure_traj_kernels(torch, torch.zeros(4, 200, 12), torch.zeros(16, dtype=torch.uint8), 6546.2)
+    assert list(out) == ["error"] and out["error"]

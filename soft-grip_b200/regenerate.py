@@ -17,6 +17,11 @@ statistics; ``--npz`` also writes the tensors ``(N,200,12)`` / ``(N,)`` for load
 
     python regenerate.py --out data/experiments --train 4096 --val 512 --test 512 \
         --softbox A.xml --softball B.xml --softcylinder C.xml
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 regenerate.py ...   # 8 GPUs
+
+Multi-GPU: every rank simulates a contiguous slice of each file's world ids and writes a shard file; after one barrier
+rank 0 concatenates the shards in rank order (the "final gather of dataset shards" -- the only exchange; nothing is
+communicated on the step path).  The merged files are identical to a single-GPU run.
 """
 import importlib
 import os
@@ -132,6 +137,94 @@ def write_file(out_dir, stem, chunks, dataset, stats_fn=None, npz=False, drop_di
     return {"file": path, "samples": int(traj.shape[0]), "diverged": ndiv}
 
 
+def shard_parts(parts, rank, world):
+    """Rank `rank` of `world` takes a contiguous slice of every part's world-id range (the sharding of SURVEY section 8e:
+    no collective on the step path; per-world draws depend on the global id only, so the union over ranks, in rank order,
+    is exactly the single-GPU result)."""
+    out = []
+    for shape, first, count in parts:
+        lo, hi = (count * rank) // world, (count * (rank + 1)) // world
+        if hi > lo:
+            out.append((shape, first + lo, hi - lo))
+    return out
+
+
+def merge_shards(out_dir, stems, world, dataset, npz=False, remove=True):
+    """The "final gather of dataset shards": concatenate `<stem>.rank<r>.pickle` of all ranks, part by part in rank order
+    (every rank wrote its slice of each part as its own list of samples), into `<stem>.pickle`."""
+    import pickle
+    out = []
+    for stem in stems:
+        shards = []
+        for r in range(world):
+            with open(os.path.join(out_dir, "%s.rank%d.pickle" % (stem, r)), "rb") as f:
+                shards.append(pickle.load(f))
+        nparts = max(len(sh["part_sizes"]) for sh in shards)
+        data, ks = [], []
+        for p in range(nparts):
+            for sh in shards:
+                a = sum(sh["part_sizes"][:p])
+                b = a + (sh["part_sizes"][p] if p < len(sh["part_sizes"]) else 0)
+                data += sh["data"][a:b]
+                ks += sh["stiffness"][a:b]
+        traj = np.stack(data) if data else np.zeros((0, 200, 12))
+        dataset.write_pickle(os.path.join(out_dir, stem + ".pickle"), traj, ks)
+        if npz:
+            dataset.write_npz(os.path.join(out_dir, stem + ".npz"), traj.astype(np.float32), np.asarray(ks))
+        if remove:
+            for r in range(world):
+                os.remove(os.path.join(out_dir, "%s.rank%d.pickle" % (stem, r)))
+        out.append({"file": os.path.join(out_dir, stem + ".pickle"), "samples": len(data)})
+    return out
+
+
+def regenerate_shard(out_dir, n_train, n_val, n_test, rollouts, rank, world, shapes=SHAPES, drop_diverged=True):
+    """What one rank of a multi-GPU regeneration does: its slice of every part of every file -> `<stem>.rank<r>.pickle`
+    (reference layout plus the per-part sample counts the merge needs).  Returns the stems."""
+    import pickle
+    dataset = importlib.import_module(_PKG + ".dataset")
+    stems = []
+    for stem, parts in plan_files(n_train, n_val, n_test, shapes):
+        data, ks, sizes = [], [], []
+        for shape, first, count in parts:
+            n0 = len(data)
+            for myshape, myfirst, mycount in shard_parts([(shape, first, count)], rank, world):
+                for traj, k, st in rollouts(myshape, myfirst, mycount):
+                    traj = traj.double().cpu().numpy() if hasattr(traj, "cpu") else np.asarray(traj, dtype=np.float64)
+                    k = k.double().cpu().numpy() if hasattr(k, "cpu") else np.asarray(k, dtype=np.float64)
+                    st = st.cpu().numpy() if hasattr(st, "cpu") else np.asarray(st)
+                    keep = (st & 1) == 0 if drop_diverged else np.ones(len(k), dtype=bool)
+                    d = dataset.to_reference_dict(traj[keep], k[keep])
+                    data += d["data"]
+                    ks += d["stiffness"]
+            sizes.append(len(data) - n0)
+        path = os.path.join(out_dir, "%s.rank%d.pickle" % (stem, rank))
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "wb") as f:
+            pickle.dump({"data": data, "stiffness": ks, "part_sizes": sizes}, f)
+        stems.append(stem)
+    return stems
+
+
+def regenerate_distributed(out_dir, n_train, n_val, n_test, rollouts, shapes=SHAPES, npz=False, drop_diverged=True, backend="nccl"):
+    """Under torchrun (RANK / WORLD_SIZE / MASTER_* in the environment): one rank per GPU, world shards with no collective
+    on the step path; the only exchange is the barrier before rank 0 concatenates the shard files.  Returns the merged
+    file summaries on rank 0, None elsewhere."""
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    own = not dist.is_initialized()
+    if own:
+        dist.init_process_group(backend)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    stems = regenerate_shard(out_dir, n_train, n_val, n_test, rollouts, rank, world, shapes=shapes, drop_diverged=drop_diverged)
+    dist.barrier()
+    out = merge_shards(out_dir, stems, world, importlib.import_module(_PKG + ".dataset"), npz=npz) if rank == 0 else None
+    dist.barrier()
+    if own:
+        dist.destroy_process_group()
+    return out
+
+
 def regenerate(out_dir, n_train, n_val, n_test, rollouts, shapes=SHAPES, stats_fn=None, npz=False, drop_diverged=True, log=print):
     """rollouts(shape, first_world, count) -> iterable of (traj, stiffness, status) chunks.  Returns the per-file summaries."""
     dataset = importlib.import_module(_PKG + ".dataset")
@@ -175,6 +268,13 @@ def main(argv=None):
     if not paths:
         raise SystemExit("give at least one of --softball / --softbox / --softcylinder")
     fn = importlib.import_module(_PKG + ".functions")
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        roll = DeviceRollouts(paths, seed=args.seed, worlds_per_launch=args.worlds_per_launch, device="cuda:%d" % local,
+                              mask_contact=args.mask_contact, contact_mode=args.contact_mode, sim_start=args.sim_start, sim_step=args.sim_step)
+        return regenerate_distributed(args.out, args.train, args.val, args.test, roll, shapes=tuple(s for s in SHAPES if s in paths),
+                                      npz=args.npz, drop_diverged=not args.keep_diverged, backend="nccl")
     roll = DeviceRollouts(paths, seed=args.seed, worlds_per_launch=args.worlds_per_launch, device=args.device,
                           mask_contact=args.mask_contact, contact_mode=args.contact_mode, sim_start=args.sim_start, sim_step=args.sim_step)
     return regenerate(args.out, args.train, args.val, args.test, roll, shapes=tuple(s for s in SHAPES if s in paths),

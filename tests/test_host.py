@@ -209,3 +209,70 @@ def test_bench_traj_kernel_probe_never_raises():
     import bench
     out = bench.measure_traj_kernels(torch, torch.zeros(4, 200, 12), torch.zeros(16, dtype=torch.uint8), 6546.2)
     assert list(out) == ["error"] and out["error"]
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_regenerate_shards_merge_to_the_single_gpu_tree(tmp_path, world):
+    """worlds shard over ranks with no collective; the only exchange is the final gather of dataset
+    shards, and the merged files equal the single-GPU files sample for sample (stub rollouts, no GPU)."""
+    rg, ds, batched = pkg("regenerate"), pkg("dataset"), pkg("batched")
+    tag = {"softball": 0.0, "softbox": 10000.0, "softcylinder": 20000.0}
+
+    def rollouts(shape, first, count):
+        for a in range(0, count, 5):
+            n = min(5, count - a)
+            ids = np.arange(first + a, first + a + n)
+            k = batched.world_uniform(3, ids, 300.0, 1400.0)
+            yield np.broadcast_to(k[:, None, None], (n, 200, 12)) + tag[shape], k, np.where(ids % 6 == 1, 1, 0)
+
+    single = rg.regenerate(str(tmp_path / "one"), 11, 5, 4, rollouts, log=lambda *_: None)
+    stems = None
+    for r in range(world):
+        stems = rg.regenerate_shard(str(tmp_path / "many"), 11, 5, 4, rollouts, r, world)
+    merged = rg.merge_shards(str(tmp_path / "many"), stems, world, ds)
+    assert [m["samples"] for m in merged] == [s["samples"] for s in single]
+    for m, s1 in zip(merged, single):
+        xa, ya = ds.read_pickle(s1["file"])
+        xb, yb = ds.read_pickle(m["file"])
+        assert (xa == xb).all() and (ya == yb).all()
+    assert not [f for f in os.listdir(str(tmp_path / "many" / "sim_all")) if ".rank" in f]       # shard files removed
+    # every world id of a part lands on exactly one rank
+    for _, parts in rg.plan_files(11, 5, 4):
+        for part in parts:
+            got = sorted(i for r in range(world) for (_, f, c) in rg.shard_parts([part], r, world) for i in range(f, f + c))
+            assert got == list(range(part[1], part[1] + part[2]))
+
+
+REGEN_WORKER = r'''
+import importlib, os, sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+rg = importlib.import_module("soft-grip_b200.regenerate")
+batched = importlib.import_module("soft-grip_b200.batched")
+def rollouts(shape, first, count):
+    ids = np.arange(first, first + count)
+    k = batched.world_uniform(1, ids, 300.0, 1400.0)
+    yield np.broadcast_to(k[:, None, None], (count, 200, 12)) + len(shape), k, np.zeros(count, dtype=np.int32)
+out = rg.regenerate_distributed(sys.argv[2], 9, 3, 2, rollouts, backend="gloo")
+if int(os.environ["RANK"]) == 0:
+    one = rg.regenerate(sys.argv[2] + "_one", 9, 3, 2, rollouts, log=lambda *_: None)
+    ds = importlib.import_module("soft-grip_b200.dataset")
+    for a, b in zip(out, one):
+        xa, ya = ds.read_pickle(a["file"]); xb, yb = ds.read_pickle(b["file"])
+        assert a["samples"] == b["samples"] and (xa == xb).all() and (ya == yb).all()
+    print("OK")
+else:
+    assert out is None
+'''
+
+
+def test_two_rank_dataset_regeneration_with_gloo(tmp_path):
+    """The N>1 dataset path end to end on CPU (gloo, world_size 2, stub rollouts): shard files, barrier, rank-0 merge."""
+    pytest.importorskip("torch")
+    script = tmp_path / "regen_worker.py"
+    script.write_text(REGEN_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29618")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29618", str(script), ROOT, str(tmp_path / "tree")],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "OK" in out.stdout

@@ -137,11 +137,13 @@ def measured_peaks():
 _W = {}
 
 
-def _cpu_init(blob_path):
+def _cpu_init(blob_path, tendon_damping=None):
     from oracle import sgoracle as so
     blob = open(blob_path, "rb").read()
     _W["m"] = so.OracleModel(blob)
     _W["w"] = so.OracleWorld(_W["m"])
+    if tendon_damping is not None:
+        _W["w"].set_tendon_damping(0, float(tendon_damping))
 
 
 def _cpu_episodes(ks):
@@ -156,13 +158,13 @@ def _cpu_episodes(ks):
     return chk, flops / max(1, n)
 
 
-def cpu_throughput(blob_path, episodes_per_core, repeats=1, cores=None, seed=0):
+def cpu_throughput(blob_path, episodes_per_core, repeats=1, cores=None, seed=0, tendon_damping=None, model="softbox"):
     """world-steps/s of the oracle with one process per host core; returns (value, cores, seconds, sample text)."""
     from concurrent.futures import ProcessPoolExecutor
     batched = importlib.import_module("soft-grip_b200.batched")
     cores = cores or len(os.sched_getaffinity(0))
     best = None
-    with ProcessPoolExecutor(cores, initializer=_cpu_init, initargs=(blob_path,)) as ex:
+    with ProcessPoolExecutor(cores, initializer=_cpu_init, initargs=(blob_path, tendon_damping)) as ex:
         list(ex.map(_cpu_episodes, [[700.0][:0]] * cores))      # spin the workers up (model load excluded)
         for rep in range(repeats):
             ks = batched.world_uniform(seed + rep, np.arange(cores * episodes_per_core), 300, 1400)
@@ -173,7 +175,7 @@ def cpu_throughput(blob_path, episodes_per_core, repeats=1, cores=None, seed=0):
             val = cores * episodes_per_core * STEPS_PER_EPISODE / dt
             if best is None or val > best[0]:
                 best = (val, dt, res[0][1])
-    sample = "%d processes x %d full squeeze episodes (softbox, stiffness U(300,1400), fp64 oracle port)" % (cores, episodes_per_core)
+    sample = "%d processes x %d full squeeze episodes (%s, stiffness U(300,1400), fp64 oracle port)" % (cores, episodes_per_core, model)
     return best[0], cores, best[1], sample, best[2]
 
 
@@ -188,7 +190,7 @@ def run_reference_arm(args, rank):
     from concurrent.futures import ProcessPoolExecutor
     batched = importlib.import_module("soft-grip_b200.batched")
     times = []
-    with ProcessPoolExecutor(cores, initializer=_cpu_init, initargs=(blob,)) as ex:
+    with ProcessPoolExecutor(cores, initializer=_cpu_init, initargs=(blob, args.tendon_damping)) as ex:
         list(ex.map(_cpu_episodes, [[]] * cores))
         for it in range(args.warmup + args.steps):
             ks = batched.world_uniform(args.seed + it, np.arange(cores * args.ref_episodes_per_core), 300, 1400)
@@ -216,6 +218,9 @@ def workload_config(args, per_gpu, note=None):
            "model": args.model, "worlds_per_gpu_per_step": per_gpu, "physics_steps_per_world_per_step": STEPS_PER_EPISODE,
            "sim_step": 7, "sim_start": 1, "rows": 200, "parallelism": "independent world shards, no collective on the step path",
            "l2": "256 MiB scratch buffer written between timed steps (L2 flush); kernel inputs are tiny, state lives in shared memory"}
+    if getattr(args, "tendon_damping", None) is not None:
+        cfg["tendon_damping"] = ("volume-tendon damper set to %g (model file: 100): the value at which this model is stable under the "
+                                 "restated engine semantics, SURVEY App. E / section 8d cfg 3" % args.tendon_damping)
     if note:
         cfg["note"] = note
     return cfg
@@ -267,6 +272,8 @@ def main():
     ap.add_argument("--model", default="softbox")
     ap.add_argument("--worlds-per-gpu", type=int, default=18944)   # 2 x (148 SMs x 64 resident worlds)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--tendon-damping", type=float, default=None,
+                    help="override the composite's volume-tendon damper for every world (softball / softcylinder: 50 is stable)")
     ap.add_argument("--cpu-episodes-per-core", type=int, default=24)
     ap.add_argument("--ref-episodes-per-core", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -297,6 +304,8 @@ def main():
     Wg = args.worlds_per_gpu
     blob = os.path.join(ROOT, "tests", "golden", args.model + ".sgm")
     env = batched.BatchedManEnv(blob, Wg, device=dev, dtype=torch.float32, seed=args.seed, world_offset=rank * Wg)
+    if args.tendon_damping is not None:
+        env.set_params(tendon_damping=np.full(Wg, args.tendon_damping))
     ev, val = batched.default_schedule(env.nu)
     T = ev.shape[0]
     sc = lib.SgSchedule(1, 7, T, ev.ctypes.data_as(C.POINTER(C.c_int)), val.ctypes.data_as(C.POINTER(C.c_double)))
@@ -389,7 +398,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         from oracle import sgoracle as so
         so.build()
-        v, cores, secs, sample, pgs_flops = cpu_throughput(blob, args.cpu_episodes_per_core, seed=args.seed)
+        v, cores, secs, sample, pgs_flops = cpu_throughput(blob, args.cpu_episodes_per_core, seed=args.seed, tendon_damping=args.tendon_damping, model=args.model)
         cpu = {"value": v, "unit": "world-steps/s", "cores": cores, "kind": "port", "sample": sample + ", %.1f s" % secs}
 
     traj_kernels = None

@@ -344,3 +344,45 @@ def test_emulated_contact_capacity_overflow_keeps_the_first_contacts(emu, states
         assert bool(ost & 2) == full and all(bool(s & 2) == full for s in env.status())
         assert rel(q1[-1], oq) < 1e-9 and rel(v1[-1], ov) < 1e-9 and rel(qacc[-1], owarm) < 1e-9
     env.close()
+
+
+STABLE_TENDON_DAMPING = 50.0     # ball / cylinder are stable for a volume-tendon damper <= ~70 (committed: 100)
+
+
+def _protocol_ctrl(step):
+    """ctrl of create_dataset's episode at physics step `step` (ref: create_dataset.py:33-60 with sim_start 1, sim_step 7)."""
+    return 0.0 if step < 281 else (-0.2 if step < 841 else 0.2)
+
+
+@pytest.mark.parametrize("name", ["softball", "softcylinder"])
+def test_emulated_other_models_along_a_stabilised_episode(emu, make_world, name):
+    """SURVEY 8d cfg 3: softball / softcylinder run away under the restated semantics at the committed tendon damper; with
+    the damper at a stable value (stated: 50) the whole squeeze episode runs clean in the oracle, and the kernel source
+    agrees with it step for step from snapshots taken all along that episode (settle, closing, peak contact, release)."""
+    w = make_world(name)
+    w.set_tendon_damping(0, STABLE_TENDON_DAMPING)
+    w.reset()
+    snaps, want = {}, (0, 150, 285, 500, 838, 1000, 1395)
+    for step in range(1401):
+        w.set_ctrl([_protocol_ctrl(step)] * 2)
+        if step in want:
+            snaps[step] = w.get_state()
+        assert w.step() == 0, step                       # no divergence, no capacity / unsupported-pair flags
+        if step in want:
+            snaps[step] = (snaps[step], w.get_state(), w.get_int("ncon"))
+    q_end = w.get_state()[0]
+    assert np.isfinite(q_end).all() and np.abs(q_end).max() < 1.0
+    env = emu.EmuBatch(blob_path(name), 2, prec=64, lpw=8)
+    env.set_params(stiffness=np.full(2, 700.0), tdamping=np.full(2, STABLE_TENDON_DAMPING))
+    env.set_debug_world(1)
+    ncons = []
+    for step in want:
+        (q, v, a, ws), (oq, ov, oa, oacc), ncon = snaps[step]
+        env.set_state(q, v, a, ws); env.set_ctrl([_protocol_ctrl(step)] * 2)
+        env.step(1)
+        q1, v1, a1, qacc = env.get_state()
+        assert int(env.debug("ncon")[0]) == ncon
+        assert rel(q1[1], oq) < 1e-8 and rel(v1[1], ov) < 1e-8 and rel(qacc[1], oacc) < 1e-8 and rel(a1[1], oa) < 1e-12, step
+        ncons.append(ncon)
+    assert (env.status() == 0).all() and max(ncons) > min(ncons)
+    env.close()

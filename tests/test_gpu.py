@@ -331,7 +331,10 @@ def test_contact_capacity_overflow_keeps_the_first_contacts(torch_cuda, batched,
         assert rel(q1[1], oq) < FP64_TOL and rel(v1[1], ov) < FP64_TOL and rel(qacc[1], owarm) < FP64_TOL
 
 
-STABLE_TENDON_DAMPING = 50.0     # ball / cylinder are stable for a volume-tendon damper <= ~70 (committed: 100)
+# under the restated semantics the volume mode is stable iff (1 + n d_t / d_j) / 65.7 < 2, i.e. n d_t < ~130 d_j:
+# ball / cylinder (n = 218 / 192) need a volume-tendon damper d_t <= ~70, the refined softbox of BASELINE configs[4]
+# (7x9x13 grid, n = 434) d_t <= ~30; the committed files have d_t = d_j = 100.  These are the stated stable values.
+STABLE_TENDON_DAMPING = {"softball": 50.0, "softcylinder": 50.0, "softbox_refined": 20.0}
 
 
 def _protocol_ctrl(step):
@@ -339,15 +342,15 @@ def _protocol_ctrl(step):
     return 0.0 if step < 281 else (-0.2 if step < 841 else 0.2)
 
 
-@pytest.mark.parametrize("name", ["softball", "softcylinder"])
+@pytest.mark.parametrize("name", ["softball", "softcylinder", "softbox_refined"])
 def test_other_models_along_a_stabilised_episode(torch_cuda, batched, make_world, name):
-    """SURVEY 8d cfg 3: with the volume-tendon damper at a stable value (stated: 50) ball and cylinder run the whole squeeze
+    """SURVEY 8d cfg 3: with the volume-tendon damper at a stable value (stated above) ball, cylinder and the refined softbox of configs[4] run the whole squeeze
     episode clean; fp64 step parity from oracle snapshots all along it, and the fp64 / fp32 rollouts finish with no world
     flagged (drift against the oracle is printed, not asserted: contacts exist from step 0, so round-off is amplified
     from the first row on)."""
     torch = torch_cuda
     w = make_world(name)
-    w.set_tendon_damping(0, STABLE_TENDON_DAMPING)
+    w.set_tendon_damping(0, STABLE_TENDON_DAMPING[name])
     w.reset()
     snaps, want = {}, (0, 150, 285, 500, 838, 1000, 1395)
     for step in range(1401):
@@ -359,7 +362,7 @@ def test_other_models_along_a_stabilised_episode(torch_cuda, batched, make_world
             snaps[step] = (snaps[step], w.get_state(), w.get_int("ncon"))
     env = make_env(batched, torch, name=name, W=2)
     env.set_new_stiffness(stiffness=[700.0, 700.0])
-    env.set_params(tendon_damping=[STABLE_TENDON_DAMPING] * 2)
+    env.set_params(tendon_damping=[STABLE_TENDON_DAMPING[name]] * 2)
     env.set_debug_world(1)
     for step in want:
         (q, v, a, ws), (oq, ov, oa, oacc), ncon = snaps[step]
@@ -368,12 +371,12 @@ def test_other_models_along_a_stabilised_episode(torch_cuda, batched, make_world
         assert rel(q1[1], oq) < 1e-8 and rel(v1[1], ov) < 1e-8 and rel(qacc[1], oacc) < 1e-8, step
     assert (env.status() == 0).all()
     w2 = make_world(name)
-    w2.set_tendon_damping(0, STABLE_TENDON_DAMPING)
+    w2.set_tendon_damping(0, STABLE_TENDON_DAMPING[name])
     rows, otouch, ost = w2.episode()
     assert ost == 0
     for dtype in (torch.float64, torch.float32):
         e = make_env(batched, torch, name=name, W=64, dtype=dtype, seed=2)
-        e.set_params(tendon_damping=[STABLE_TENDON_DAMPING] * 64)
+        e.set_params(tendon_damping=[STABLE_TENDON_DAMPING[name]] * 64)
         traj, k, st = e.rollout(stiffness=[700.0] + list(np.linspace(300, 1400, 63)))
         flagged = st if dtype == torch.float64 else (st & batched.ST_DIVERGED)      # fp32: no world may run away
         assert bool(torch.isfinite(traj).all()) and int((flagged != 0).sum()) == 0, (name, dtype, st.cpu().numpy())

@@ -346,7 +346,10 @@ def test_emulated_contact_capacity_overflow_keeps_the_first_contacts(emu, states
     env.close()
 
 
-STABLE_TENDON_DAMPING = 50.0     # ball / cylinder are stable for a volume-tendon damper <= ~70 (committed: 100)
+# under the restated semantics the volume mode is stable iff (1 + n d_t / d_j) / 65.7 < 2, i.e. n d_t < ~130 d_j:
+# ball / cylinder (n = 218 / 192) need a volume-tendon damper d_t <= ~70, the refined softbox of BASELINE configs[4]
+# (7x9x13 grid, n = 434) d_t <= ~30; the committed files have d_t = d_j = 100.  These are the stated stable values.
+STABLE_TENDON_DAMPING = {"softball": 50.0, "softcylinder": 50.0, "softbox_refined": 20.0}
 
 
 def _protocol_ctrl(step):
@@ -354,13 +357,13 @@ def _protocol_ctrl(step):
     return 0.0 if step < 281 else (-0.2 if step < 841 else 0.2)
 
 
-@pytest.mark.parametrize("name", ["softball", "softcylinder"])
+@pytest.mark.parametrize("name", ["softball", "softcylinder", "softbox_refined"])
 def test_emulated_other_models_along_a_stabilised_episode(emu, make_world, name):
     """SURVEY 8d cfg 3: softball / softcylinder run away under the restated semantics at the committed tendon damper; with
-    the damper at a stable value (stated: 50) the whole squeeze episode runs clean in the oracle, and the kernel source
+    the damper at a stable value (stated above) the whole squeeze episode runs clean in the oracle, and the kernel source
     agrees with it step for step from snapshots taken all along that episode (settle, closing, peak contact, release)."""
     w = make_world(name)
-    w.set_tendon_damping(0, STABLE_TENDON_DAMPING)
+    w.set_tendon_damping(0, STABLE_TENDON_DAMPING[name])
     w.reset()
     snaps, want = {}, (0, 150, 285, 500, 838, 1000, 1395)
     for step in range(1401):
@@ -373,7 +376,7 @@ def test_emulated_other_models_along_a_stabilised_episode(emu, make_world, name)
     q_end = w.get_state()[0]
     assert np.isfinite(q_end).all() and np.abs(q_end).max() < 1.0
     env = emu.EmuBatch(blob_path(name), 2, prec=64, lpw=8)
-    env.set_params(stiffness=np.full(2, 700.0), tdamping=np.full(2, STABLE_TENDON_DAMPING))
+    env.set_params(stiffness=np.full(2, 700.0), tdamping=np.full(2, STABLE_TENDON_DAMPING[name]))
     env.set_debug_world(1)
     ncons = []
     for step in want:

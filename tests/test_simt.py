@@ -3,6 +3,7 @@ under the SIMT emulator of tests/simt (test infrastructure; never part of the pr
 and the golden vectors.  Warp collectives are emulated exactly (the emulator aborts on divergent collectives), so
 these tests pin the warp-synchronous logic: sub-warp worlds, ballot compaction, contact scheduling, level sweeps.
 The `-m gpu` tests repeat the same comparisons on the real device through libsoftgrip.so."""
+import importlib
 import os
 import sys
 
@@ -388,4 +389,37 @@ def test_emulated_other_models_along_a_stabilised_episode(emu, make_world, name)
         assert rel(q1[1], oq) < 1e-8 and rel(v1[1], ov) < 1e-8 and rel(qacc[1], oacc) < 1e-8 and rel(a1[1], oa) < 1e-12, step
         ncons.append(ncon)
     assert (env.status() == 0).all() and max(ncons) > min(ncons)
+    env.close()
+
+
+def test_c_abi_rejects_empty_and_malformed_requests(emu):
+    """Empty / malformed inputs at the boundary are error returns with a message, never a launch: zero sub-steps, an empty
+    or negative schedule, null buffers, zero worlds, unknown precision, a device that does not exist."""
+    import ctypes as C
+    lib_ = importlib.import_module("soft-grip_b200._lib")
+    env = emu.EmuBatch(blob_path("softbox"), 1, prec=32, lpw=8)
+    env.reset()
+    L = env.L
+    err = lambda: L.sg_last_error().decode()
+    for nsub in (0, -1):
+        assert L.sg_batch_step(env.b, nsub, None, None, None) < 0 and "nsub" in err()
+    traj = np.zeros((1, 3, 12), dtype=np.float32)
+    ev, val = np.zeros(3, dtype=np.int32), np.zeros((3, 2))
+    pe, pv = ev.ctypes.data_as(C.POINTER(C.c_int)), val.ctypes.data_as(C.POINTER(C.c_double))
+    for T, sim_step, sim_start, ok in ((0, 7, 1, False), (3, 0, 1, False), (3, -1, 1, False), (3, 7, -1, False), (3, 7, 0, True), (3, 7, 1, True)):
+        sc = lib_.SgSchedule(sim_start, sim_step, T, pe, pv)
+        rc = L.sg_batch_rollout(env.b, C.byref(sc), traj.ctypes.data_as(C.c_void_p), None, None)
+        assert (rc == 0) == ok, (T, sim_step, sim_start, err())
+        if not ok:
+            assert "schedule" in err()
+    assert np.isfinite(traj).all()
+    sc = lib_.SgSchedule(1, 7, 3, None, None)
+    assert L.sg_batch_rollout(env.b, C.byref(sc), traj.ctypes.data_as(C.c_void_p), None, None) < 0 and "schedule" in err()
+    sc = lib_.SgSchedule(1, 7, 3, pe, pv)
+    assert L.sg_batch_rollout(env.b, C.byref(sc), None, None, None) < 0 and "null" in err()
+    b = C.c_void_p()
+    assert L.sg_batch_create(env.m, 0, 0, 32, C.byref(b)) < 0 and "nworlds" in err()
+    assert L.sg_batch_create(env.m, 1, 0, 16, C.byref(b)) < 0 and "precision" in err()
+    assert L.sg_batch_create(env.m, 1, 5, 32, C.byref(b)) < 0 and "device" in err()
+    assert L.sg_batch_set_debug_world(env.b, 7) < 0 and "range" in err()
     env.close()

@@ -149,11 +149,12 @@ long long sg_batch_launch_count(const sg_batch* b);
 
 /* replaces functions/optimization.py:6-14 `noised_modality`: channels [0, nacc) += N(0, sigma_acc), channels
  * [nacc, nchan) += N(0, sigma_gyro) (reference: nacc 6, 0.7, 0.06), traj_out may alias traj_in.  The draws are
- * Philox4x32-10(key = seed, counter = element index / 4) + Box-Muller in fp32, i.e. a function of (seed, element index)
- * only.  mean/std (dev fp64 [nchan], both or neither): fused standardisation out = (x + noise - mean) / std of
+ * Philox4x32-10(key = seed, counter = global element index / 4) + Box-Muller in fp32, i.e. a function of (seed, element
+ * index) only; first_row is the row index of traj_in[0] inside the whole dataset tensor (0 for a whole tensor), so that
+ * shards noised separately -- per launch, per GPU -- equal the corresponding rows of the tensor noised in one call.  mean/std (dev fp64 [nchan], both or neither): fused standardisation out = (x + noise - mean) / std of
  * functions/optimization.py:38. */
-int sg_traj_add_noise(const void* traj_in, void* traj_out, long long nrows, int nchan, int nacc, double sigma_acc,
-                      double sigma_gyro, unsigned long long seed, const double* mean, const double* std,
+int sg_traj_add_noise(const void* traj_in, void* traj_out, long long nrows, long long first_row, int nchan, int nacc,
+                      double sigma_acc, double sigma_gyro, unsigned long long seed, const double* mean, const double* std,
                       int precision, int device, void* stream);
 /* replaces `np.mean(train_x, axis=(0, 1))` / `np.std(train_x, axis=(0, 1))` of functions/utils.py:39-40 (population
  * standard deviation).  mean_out/std_out: dev fp64 [nchan]; workspace: dev, at least sg_traj_stats_workspace_bytes().

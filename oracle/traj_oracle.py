@@ -47,10 +47,11 @@ def _u01(x):
     return (x.astype(np.float32) * np.float32(2.0 ** -32) + np.float32(2.0 ** -33)).astype(np.float32)
 
 
-def standard_normals(nelem, seed):
-    """The N(0,1) draw of every flat element index in [0, nelem), nelem % 4 == 0: float64 Box-Muller of the fp32 uniforms."""
+def standard_normals(nelem, seed, first_elem=0):
+    """The N(0,1) draw of every flat element index in [first_elem, first_elem + nelem), both multiples of 4: float64
+    Box-Muller of the fp32 uniforms."""
     nq = nelem // 4
-    q = np.arange(nq, dtype=np.uint64)
+    q = np.arange(nq, dtype=np.uint64) + np.uint64(first_elem // 4)
     ctr = np.stack([q & _LO, q >> np.uint64(32), np.zeros_like(q), np.zeros_like(q)], axis=-1)
     r = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
     z = np.empty((nq, 4), dtype=np.float64)
@@ -61,12 +62,12 @@ def standard_normals(nelem, seed):
     return z.reshape(-1)
 
 
-def noised_modality(data, seed, sigma_acc=0.7, sigma_gyro=0.06, nacc=None, mean=None, std=None):
+def noised_modality(data, seed, sigma_acc=0.7, sigma_gyro=0.06, nacc=None, mean=None, std=None, first_row=0):
     data = np.asarray(data)
     nchan = data.shape[-1]
     nacc = nchan // 2 if nacc is None else nacc
     sig = np.where(np.arange(nchan) < nacc, np.float32(sigma_acc), np.float32(sigma_gyro)).astype(np.float64)
-    z = standard_normals(data.size, seed).reshape(data.shape)
+    z = standard_normals(data.size, seed, first_elem=first_row * nchan).reshape(data.shape)
     out = data.astype(np.float64) + sig * z
     if mean is not None:
         out = (out - np.asarray(mean, dtype=np.float64).reshape(-1)) / np.asarray(std, dtype=np.float64).reshape(-1)

@@ -59,7 +59,7 @@ SIGNATURES = {
     "sg_batch_launch_count": (C.c_longlong, [P]),
     "sg_batch_config": (C.c_int, [P, I]),
     "sg_batch_prof_get": (C.c_int, [P, C.POINTER(C.c_ulonglong), C.c_int]),
-    "sg_traj_add_noise": (C.c_int, [V, V, C.c_longlong, C.c_int, C.c_int, C.c_double, C.c_double, C.c_ulonglong, V, V,
+    "sg_traj_add_noise": (C.c_int, [V, V, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_double, C.c_double, C.c_ulonglong, V, V,
                                     C.c_int, C.c_int, V]),
     "sg_traj_channel_stats": (C.c_int, [V, C.c_longlong, C.c_int, C.c_int, C.c_int, V, V, V, C.c_longlong, V]),
     "sg_traj_stats_workspace_bytes": (C.c_longlong, [C.c_longlong, C.c_int, C.c_int]),

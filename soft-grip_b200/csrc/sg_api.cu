@@ -693,12 +693,13 @@ static int traj_check(const char* fn, const void* p, long long nrows, int nchan,
 }
 
 template <typename T>
-static int traj_noise_launch(const void* in, void* out, long long nrows, int nchan, int nacc, double sa, double sg_, unsigned long long seed,
-                             const double* mean, const double* stdev, int sms, void* stream) {
+static int traj_noise_launch(const void* in, void* out, long long nrows, long long first_row, int nchan, int nacc, double sa, double sg_,
+                             unsigned long long seed, const double* mean, const double* stdev, int sms, void* stream) {
   TrajNoiseArgs<T> A;
   A.in = (const T*)in; A.out = (T*)out; A.nelem = nrows * nchan; A.nchan = nchan; A.nacc = nacc;
   A.sigma_acc = (float)sa; A.sigma_gyro = (float)sg_;
   A.k0 = (uint32_t)seed; A.k1 = (uint32_t)(seed >> 32);
+  A.first_quad = (unsigned long long)first_row * (unsigned long long)(nchan / 4);
   A.mean = mean; A.stdev = stdev;
   const int block = 256;
   const long long nquad = A.nelem / 4;
@@ -710,20 +711,21 @@ static int traj_noise_launch(const void* in, void* out, long long nrows, int nch
   return 0;
 }
 
-extern "C" int sg_traj_add_noise(const void* traj_in, void* traj_out, long long nrows, int nchan, int nacc, double sigma_acc,
-                                 double sigma_gyro, unsigned long long seed, const double* mean, const double* stdev,
+extern "C" int sg_traj_add_noise(const void* traj_in, void* traj_out, long long nrows, long long first_row, int nchan, int nacc,
+                                 double sigma_acc, double sigma_gyro, unsigned long long seed, const double* mean, const double* stdev,
                                  int precision, int device, void* stream) {
   if (int rc = traj_check("sg_traj_add_noise", traj_in, nrows, nchan, precision)) return rc;
   if (int rc = traj_check("sg_traj_add_noise", traj_out, nrows, nchan, precision)) return rc;
   if (nacc < 0 || nacc > nchan) return fail("sg_traj_add_noise: nacc out of range");
+  if (first_row < 0) return fail("sg_traj_add_noise: negative first_row");
   if (!(sigma_acc >= 0) || !(sigma_gyro >= 0)) return fail("sg_traj_add_noise: negative or NaN sigma");
   if ((mean == nullptr) != (stdev == nullptr)) return fail("sg_traj_add_noise: mean and std must be given together");
   int sms = 0;
   if (int rc = traj_sm_count(device, &sms)) return rc;
   if (nrows == 0) return 0;
   CUDA_OK(cudaSetDevice(device));
-  return precision == 32 ? traj_noise_launch<float>(traj_in, traj_out, nrows, nchan, nacc, sigma_acc, sigma_gyro, seed, mean, stdev, sms, stream)
-                         : traj_noise_launch<double>(traj_in, traj_out, nrows, nchan, nacc, sigma_acc, sigma_gyro, seed, mean, stdev, sms, stream);
+  return precision == 32 ? traj_noise_launch<float>(traj_in, traj_out, nrows, first_row, nchan, nacc, sigma_acc, sigma_gyro, seed, mean, stdev, sms, stream)
+                         : traj_noise_launch<double>(traj_in, traj_out, nrows, first_row, nchan, nacc, sigma_acc, sigma_gyro, seed, mean, stdev, sms, stream);
 }
 
 static int traj_stats_block(int nchan) {           // a multiple of 32 and of nchan / 4: 384 threads for 12 or 24 channels

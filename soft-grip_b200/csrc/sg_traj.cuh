@@ -14,8 +14,9 @@
 // stats s per element (read once), s = 4 (fp32) or 8 (fp64).
 //
 // Random numbers: Philox4x32-10 (Salmon et al., SC'11; the generator behind tf.random / curand / torch.cuda) keyed by the
-// 64-bit seed, counter = index of the 4-element group, so a draw depends only on (seed, element index): not on the
-// grid, the sharding of worlds over GPUs or the batch precision.  Normals by Box-Muller in fp32 from the four words.
+// 64-bit seed, counter = index of the 4-element group (plus the caller's row offset when the buffer is a shard of a larger
+// tensor), so a draw depends only on (seed, global element index): not on the grid, the sharding of worlds over GPUs or
+// launches, or the batch precision.  Normals by Box-Muller in fp32 from the four words.
 #pragma once
 #include <stdint.h>
 
@@ -74,6 +75,7 @@ struct TrajNoiseArgs {
   int nchan, nacc;      // channels < nacc get sigma_acc, the others sigma_gyro
   float sigma_acc, sigma_gyro;
   uint32_t k0, k1;      // seed
+  unsigned long long first_quad;   // counter of this buffer's first quad (a shard of a larger tensor continues its stream)
   const double* mean;   // [nchan] or null: fused (x - mean) / std after the noise
   const double* stdev;
 };
@@ -87,7 +89,8 @@ __global__ void __launch_bounds__(256) sg_traj_noise_kernel(const __grid_constan
   const int gstep = (int)(stride % qpr);
   for (long long q = q0; q < nquad; q += stride) {
     Vec4<T> v = load4(A.in + 4 * q);
-    const Philox4 r = philox4x32_10(Philox4{(uint32_t)q, (uint32_t)((uint64_t)q >> 32), 0u, 0u}, A.k0, A.k1);
+    const unsigned long long ctr = A.first_quad + (unsigned long long)q;
+    const Philox4 r = philox4x32_10(Philox4{(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, A.k0, A.k1);
     float z[4];
     box_muller(r.x, r.y, z[0], z[1]);
     box_muller(r.z, r.w, z[2], z[3]);

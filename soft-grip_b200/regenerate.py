@@ -72,7 +72,9 @@ class DeviceRollouts:
         self.mask, self.mode, self.sim_start, self.sim_step = bool(mask_contact), contact_mode, sim_start, sim_step
         self._dm = {}
 
-    def __call__(self, shape, first, count):
+    def __call__(self, shape, first, count, noise_seed=None):
+        """noise_seed: also apply the trainer's noise augmentation (ref: functions/optimization.py:6-14) on the device; the
+        draw of a sample depends only on (noise_seed, shape, global world id), not on launches or ranks."""
         import torch
         b = self.batched
         if shape not in self._dm:
@@ -85,6 +87,10 @@ class DeviceRollouts:
             traj, k, st, touch = env.rollout(return_touch=True)
             if self.mask:
                 env.mask_contact(traj, touch)
+            if noise_seed is not None:
+                fn = importlib.import_module(_PKG + ".functions")
+                fn.noised_modality(traj, seed=int(noise_seed) * len(SHAPES) + SHAPES.index(shape), out=traj,
+                                   first_row=(first + done) * int(traj.shape[1]))
             yield traj, k, st
             done += n
             del env
@@ -225,15 +231,20 @@ def regenerate_distributed(out_dir, n_train, n_val, n_test, rollouts, shapes=SHA
     return out
 
 
-def regenerate(out_dir, n_train, n_val, n_test, rollouts, shapes=SHAPES, stats_fn=None, npz=False, drop_diverged=True, log=print):
-    """rollouts(shape, first_world, count) -> iterable of (traj, stiffness, status) chunks.  Returns the per-file summaries."""
+def regenerate(out_dir, n_train, n_val, n_test, rollouts, shapes=SHAPES, stats_fn=None, npz=False, drop_diverged=True, log=print,
+               noise_seed=None):
+    """rollouts(shape, first_world, count) -> iterable of (traj, stiffness, status) chunks.  Returns the per-file summaries.
+    noise_seed: bake the trainer's noise augmentation into the ``*/train`` files (the reference adds it to training batches
+    only, ref: functions/optimization.py:32-33); passed on as ``rollouts(..., noise_seed=...)``."""
     dataset = importlib.import_module(_PKG + ".dataset")
     out = []
     t0 = time.perf_counter()
     for stem, parts in plan_files(n_train, n_val, n_test, shapes):
+        kw = {"noise_seed": noise_seed} if (noise_seed is not None and stem.endswith("/train")) else {}
+
         def chunks():
             for shape, first, count in parts:
-                yield from rollouts(shape, first, count)
+                yield from rollouts(shape, first, count, **kw)
         s = write_file(out_dir, stem, chunks(), dataset, stats_fn=stats_fn, npz=npz, drop_diverged=drop_diverged)
         s["parts"] = parts
         out.append(s)
@@ -257,6 +268,8 @@ def build_parser():
     p.add_argument("--contact-mode", choices=["intended", "reference"], default="intended")
     p.add_argument("--keep-diverged", action="store_true")
     p.add_argument("--npz", action="store_true")
+    p.add_argument("--noise-seed", type=int, default=None,
+                   help="bake noised_modality (sigma 0.7 / 0.06) into the */train files on the device (single-GPU path)")
     p.add_argument("--sim-step", type=int, default=7)
     p.add_argument("--sim-start", type=int, default=1)
     return p
@@ -278,7 +291,7 @@ def main(argv=None):
     roll = DeviceRollouts(paths, seed=args.seed, worlds_per_launch=args.worlds_per_launch, device=args.device,
                           mask_contact=args.mask_contact, contact_mode=args.contact_mode, sim_start=args.sim_start, sim_step=args.sim_step)
     return regenerate(args.out, args.train, args.val, args.test, roll, shapes=tuple(s for s in SHAPES if s in paths),
-                      stats_fn=fn.channel_mean_std, npz=args.npz, drop_diverged=not args.keep_diverged)
+                      stats_fn=fn.channel_mean_std, npz=args.npz, drop_diverged=not args.keep_diverged, noise_seed=args.noise_seed)
 
 
 if __name__ == "__main__":

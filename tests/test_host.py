@@ -197,6 +197,16 @@ def test_regenerate_plans_the_reference_file_tree_with_disjoint_samples(tmp_path
     assert sum(o["diverged"] for o in out) > 0
     kept = rg.regenerate(str(tmp_path / "all"), 10, 4, 3, rollouts, drop_diverged=False, log=lambda *_: None)
     assert [o["samples"] for o in kept] == [10, 4, 10, 3, 3, 3]
+    # noise_seed is handed to the rollouts of the */train files only
+    calls.clear()
+    noisy = []
+
+    def rollouts_n(shape, first, count, noise_seed=None):
+        noisy.append((shape, first, noise_seed))
+        return rollouts(shape, first, count)
+
+    rg.regenerate(str(tmp_path / "noise"), 10, 4, 3, rollouts_n, log=lambda *_: None, noise_seed=5)
+    assert [n for _, _, n in noisy] == [5, None, 5, 5, 5, None, None, None]
 
 
 def test_bench_traj_kernel_probe_never_raises():

@@ -68,19 +68,26 @@ def test_emulated_noise_kernel_matches_the_oracle(emulib, dtype, nchan):
     out = np.empty_like(x)
     prec = 32 if dtype == np.float32 else 64
     seed = 0x1234567890ABCDEF
-    assert emulib.sg_traj_add_noise(_vp(x), _vp(out), x.size // nchan, nchan, nchan // 2, 0.7, 0.06, seed, None, None, prec, 0, None) == 0
+    assert emulib.sg_traj_add_noise(_vp(x), _vp(out), x.size // nchan, 0, nchan, nchan // 2, 0.7, 0.06, seed, None, None, prec, 0, None) == 0
     want = to.noised_modality(x, seed)
     sig = np.where(np.arange(nchan) < nchan // 2, 0.7, 0.06)
     tol = sig * Z_TOL + (np.abs(want) * (2e-7 if prec == 32 else 1e-15))
     assert (np.abs(out - want) <= tol).all()
     # in place (the reference's `acc += ...`) gives the same bits
     y = x.copy()
-    assert emulib.sg_traj_add_noise(_vp(y), _vp(y), x.size // nchan, nchan, nchan // 2, 0.7, 0.06, seed, None, None, prec, 0, None) == 0
+    assert emulib.sg_traj_add_noise(_vp(y), _vp(y), x.size // nchan, 0, nchan, nchan // 2, 0.7, 0.06, seed, None, None, prec, 0, None) == 0
     assert (y == out).all()
+    # a shard noised on its own with its row offset equals the same rows of the whole tensor (per-launch / per-GPU shards)
+    rows, cut = x.size // nchan, 3 * 200 + 7
+    tail = np.ascontiguousarray(x.reshape(rows, nchan)[cut:])
+    ytail = np.empty_like(tail)
+    assert emulib.sg_traj_add_noise(_vp(tail), _vp(ytail), rows - cut, cut, nchan, nchan // 2, 0.7, 0.06, seed, None, None, prec, 0, None) == 0
+    assert (ytail == out.reshape(rows, nchan)[cut:]).all()
+    assert (np.abs(ytail - to.noised_modality(tail, seed, first_row=cut)) <= tol.reshape(rows, nchan)[cut:]).all()
     # sigma 0 is the identity; another seed is another draw
-    assert emulib.sg_traj_add_noise(_vp(x), _vp(y), x.size // nchan, nchan, nchan // 2, 0.0, 0.0, seed, None, None, prec, 0, None) == 0
+    assert emulib.sg_traj_add_noise(_vp(x), _vp(y), x.size // nchan, 0, nchan, nchan // 2, 0.0, 0.0, seed, None, None, prec, 0, None) == 0
     assert (y == x).all()
-    assert emulib.sg_traj_add_noise(_vp(x), _vp(y), x.size // nchan, nchan, nchan // 2, 0.7, 0.06, seed + 1, None, None, prec, 0, None) == 0
+    assert emulib.sg_traj_add_noise(_vp(x), _vp(y), x.size // nchan, 0, nchan, nchan // 2, 0.7, 0.06, seed + 1, None, None, prec, 0, None) == 0
     assert (y != out).mean() > 0.99
 
 
@@ -91,7 +98,7 @@ def test_emulated_noise_kernel_fused_standardisation(emulib, dtype):
     mean, std = np.ascontiguousarray(mean.reshape(-1)), np.ascontiguousarray(std.reshape(-1))
     out = np.empty_like(x)
     prec = 32 if dtype == np.float32 else 64
-    assert emulib.sg_traj_add_noise(_vp(x), _vp(out), x.size // 12, 12, 6, 0.7, 0.06, 99, _vp(mean), _vp(std), prec, 0, None) == 0
+    assert emulib.sg_traj_add_noise(_vp(x), _vp(out), x.size // 12, 0, 12, 6, 0.7, 0.06, 99, _vp(mean), _vp(std), prec, 0, None) == 0
     want = to.noised_modality(x, 99, mean=mean, std=std)                # ref: optimization.py:33,38
     tol = (np.where(np.arange(12) < 6, 0.7, 0.06) * Z_TOL) / std + (np.abs(want) + np.abs(mean / std)) * (4e-7 if prec == 32 else 1e-14)
     assert (np.abs(out - want) <= tol).all()
@@ -174,14 +181,15 @@ def test_trajectory_entry_points_reject_bad_arguments(emulib):
     bad = np.zeros(4 * 12 + 1, dtype=np.float32)[1:]                     # 4-byte aligned only
     m = np.zeros(12)
     err = lambda: emulib.sg_last_error().decode()
-    assert emulib.sg_traj_add_noise(None, _vp(x), 4, 12, 6, 0.7, 0.06, 0, None, None, 32, 0, None) < 0 and "null" in err()
-    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 4, 10, 5, 0.7, 0.06, 0, None, None, 32, 0, None) < 0 and "multiple of 4" in err()
-    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 4, 12, 13, 0.7, 0.06, 0, None, None, 32, 0, None) < 0 and "nacc" in err()
-    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 4, 12, 6, -1.0, 0.06, 0, None, None, 32, 0, None) < 0 and "sigma" in err()
-    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 4, 12, 6, 0.7, 0.06, 0, _vp(m), None, 32, 0, None) < 0 and "together" in err()
-    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 4, 12, 6, 0.7, 0.06, 0, None, None, 16, 0, None) < 0 and "precision" in err()
-    assert emulib.sg_traj_add_noise(_vp(bad), _vp(x), 4, 12, 6, 0.7, 0.06, 0, None, None, 32, 0, None) < 0 and "aligned" in err()
-    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 0, 12, 6, 0.7, 0.06, 0, None, None, 32, 0, None) == 0           # empty is a no-op
+    assert emulib.sg_traj_add_noise(None, _vp(x), 4, 0, 12, 6, 0.7, 0.06, 0, None, None, 32, 0, None) < 0 and "null" in err()
+    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 4, 0, 10, 5, 0.7, 0.06, 0, None, None, 32, 0, None) < 0 and "multiple of 4" in err()
+    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 4, 0, 12, 13, 0.7, 0.06, 0, None, None, 32, 0, None) < 0 and "nacc" in err()
+    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 4, -1, 12, 6, 0.7, 0.06, 0, None, None, 32, 0, None) < 0 and "first_row" in err()
+    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 4, 0, 12, 6, -1.0, 0.06, 0, None, None, 32, 0, None) < 0 and "sigma" in err()
+    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 4, 0, 12, 6, 0.7, 0.06, 0, _vp(m), None, 32, 0, None) < 0 and "together" in err()
+    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 4, 0, 12, 6, 0.7, 0.06, 0, None, None, 16, 0, None) < 0 and "precision" in err()
+    assert emulib.sg_traj_add_noise(_vp(bad), _vp(x), 4, 0, 12, 6, 0.7, 0.06, 0, None, None, 32, 0, None) < 0 and "aligned" in err()
+    assert emulib.sg_traj_add_noise(_vp(x), _vp(x), 0, 0, 12, 6, 0.7, 0.06, 0, None, None, 32, 0, None) == 0           # empty is a no-op
     ws = np.zeros(8)
     assert emulib.sg_traj_channel_stats(_vp(x), 4, 12, 32, 0, _vp(m), _vp(m), _vp(ws), 8, None) < 0 and "workspace" in err()
     assert emulib.sg_traj_channel_stats(_vp(x), 0, 12, 32, 0, _vp(m), _vp(m), _vp(ws), 64, None) < 0 and "one row" in err()
@@ -206,7 +214,7 @@ def test_python_mirror_fails_loudly_without_a_gpu():
     # the C entry points themselves refuse to run without a device
     L = lib.lib()
     x = np.zeros((4, 12), dtype=np.float32)
-    assert L.sg_traj_add_noise(_vp(x), _vp(x), 4, 12, 6, 0.7, 0.06, 0, None, None, 32, 0, None) < 0
+    assert L.sg_traj_add_noise(_vp(x), _vp(x), 4, 0, 12, 6, 0.7, 0.06, 0, None, None, 32, 0, None) < 0
     assert b"no CUDA device" in L.sg_last_error()
 
 
@@ -278,10 +286,11 @@ def test_gpu_trajectory_kernels_at_full_size_properties(torch_cuda):
     sd = d.std(dim=(0, 1)).cpu().numpy()
     assert np.allclose(sd[:6], 0.7, rtol=2e-3) and np.allclose(sd[6:], 0.06, rtol=2e-3)
     assert float(d.mean(dim=(0, 1)).abs().max()) < 1.5e-3            # 0.7 / sqrt(1.3e7) = 2e-4 per channel
-    # sharding invariance: the second half of the buffer noised on its own with the matching element offset is not
-    # expressible through the API, but the first half is a prefix of the same counter stream
+    # sharding invariance: each half noised on its own (the second with its row offset) equals the halves of the whole
     yh = fn.noised_modality(x[: W // 2].contiguous(), seed=7)
     assert torch.equal(yh, y[: W // 2])
+    yt = fn.noised_modality(x[W // 2:].contiguous(), seed=7, first_row=(W // 2) * 200)
+    assert torch.equal(yt, y[W // 2:])
     mean, std = fn.channel_mean_std(y)
     m64, s64 = y.double().mean(dim=(0, 1)), y.double().std(dim=(0, 1), unbiased=False)
     assert torch.allclose(mean.reshape(-1), m64, rtol=1e-9, atol=1e-9) and torch.allclose(std.reshape(-1), s64, rtol=1e-8)
@@ -303,7 +312,7 @@ def test_gpu_regenerated_tree_does_not_depend_on_the_launch_size(torch_cuda, tmp
     for wpl, sub in ((64, "a"), (24, "b")):
         roll = rg.DeviceRollouts({"softbox": blob_path("softbox")}, seed=5, worlds_per_launch=wpl)
         outs.append(rg.regenerate(str(tmp_path / sub), 40, 8, 8, roll, shapes=("softbox",), stats_fn=fn.channel_mean_std,
-                                  drop_diverged=False, log=lambda *_: None))
+                                  drop_diverged=False, log=lambda *_: None, noise_seed=9))      # noise baked into */train
     assert [os.path.relpath(o["file"], str(tmp_path / "a")) for o in outs[0]] == [
         "sim_box/train.pickle", "sim_box/val.pickle", "sim_all/train.pickle", "sim_all/softbox_testing.pickle"]
     allk = []
@@ -316,3 +325,7 @@ def test_gpu_regenerated_tree_does_not_depend_on_the_launch_size(torch_cuda, tmp
         assert np.allclose(st["mean"], xa.mean(axis=(0, 1)), rtol=1e-9, atol=1e-9) and np.allclose(st["std"], xa.std(axis=(0, 1)), rtol=1e-8)
         allk += list(ya)
     assert len(set(allk)) == len(allk) == 40 + 8 + 40 + 8          # no sample shared between files
+    # the settle rows of a clean file are smooth, those of a noised */train file carry the accelerometer sigma
+    xt, _ = ds.read_pickle(outs[0][0]["file"])
+    xv, _ = ds.read_pickle(outs[0][1]["file"])
+    assert 0.5 < np.diff(xt[:, 5:35, 0], axis=1).std() / np.sqrt(2) < 0.9 and np.diff(xv[:, 5:35, 0], axis=1).std() < 0.1

@@ -3,6 +3,7 @@
 // entry point that would compute needs a CUDA device and fails with an error otherwise.
 #include "sg_rt.hpp"
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +18,7 @@
 #include "sg_kernels.cuh"      // first-generation kernel (one warp per world), kept for A/B runs: SOFTGRIP_KERNEL=1
 #endif
 #include "sg_launch.hpp"
+#include "sg_traj.cuh"
 
 using namespace sg;
 
@@ -664,22 +666,20 @@ extern "C" int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int
   return fail("sg_batch_debug_get: unknown key " + k);
 }
 
-// ---- trajectory post-processing (sg_traj.cuh): noise augmentation and channel statistics ------------------------------
-#include "sg_traj.cuh"
-
+// ---- trajectory post-processing (sg_traj.cuh): noise augmentation, channel statistics, --mask-contact ----------------
 static int traj_sm_count(int device, int* out) {
-  static int cached[64] = {0};
+  static std::atomic<int> cached[64];                // SM count per device; racing first calls store the same value
   if (device < 0 || device >= 64) return fail("bad device index");
-  if (!cached[device]) {
+  if (!cached[device].load(std::memory_order_relaxed)) {
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return fail("no CUDA device available (libsoftgrip has no CPU path)");
     if (device >= ndev) return fail("bad device index");
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    cached[device] = prop.multiProcessorCount;
+    cached[device].store(prop.multiProcessorCount, std::memory_order_relaxed);
   }
-  *out = cached[device];
+  *out = cached[device].load(std::memory_order_relaxed);
   return 0;
 }
 

@@ -48,11 +48,22 @@ __device__ __forceinline__ float u01(uint32_t x) { return (float)x * 2.328306436
 
 // two standard normals from two words
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+#ifdef SG_TRAJ_FAST_NORMALS
+  // A/B build only (make NVCCFLAGS+=-DSG_TRAJ_FAST_NORMALS, never the default and not what the parity tests pin): the
+  // special-function unit instead of the FFMA polynomials of logf / sincospif -- ~140 instead of ~260 instructions per
+  // quad, at ~3e-6 absolute error on the normal (up to 8e-4 in the 1e-6-probability corner u -> 1).  See DESIGN.md 3b.
+  const float r = sqrtf(-2.0f * __logf(u01(a)));
+  float s, c;
+  __sincosf(6.2831853071795865f * (u01(b) - 0.5f), &s, &c);      // angle in (-pi, pi]: the intrinsic's accurate range
+  z0 = -r * c;
+  z1 = -r * s;
+#else
   const float r = sqrtf(-2.0f * logf(u01(a)));
   float s, c;
   sincospif(2.0f * u01(b), &s, &c);
   z0 = r * c;
   z1 = r * s;
+#endif
 }
 
 template <typename T> struct Vec4 { T v[4]; };

@@ -17,6 +17,7 @@ processed in per-GPU batches so that one step takes seconds, not minutes.  Weak 
 `roofline`: HBM roofline of the rollout kernel on its algorithmic bytes (the kernel is latency/issue bound on
             the Gauss-Seidel sweep, so this fraction is tiny by construction).
 `cpu_baseline`: the fp64 oracle (a port, not libmujoco) on the host cores, bounded sample, rank 0 at N=1.
+`sensor_trace_error`: (N=1) four of the worlds just simulated against the fp64 oracle with the same stiffness; informational.
 `traj_kernels`: (N=1, outside the timed region) the HBM-bound kernels that post-process the trajectory buffer, each timed
             alone against the HBM roof; informational, a failure there is reported in the key and never raised.
 """
@@ -177,6 +178,30 @@ def cpu_throughput(blob_path, episodes_per_core, repeats=1, cores=None, seed=0, 
                 best = (val, dt, res[0][1])
     sample = "%d processes x %d full squeeze episodes (%s, stiffness U(300,1400), fp64 oracle port)" % (cores, episodes_per_core, model)
     return best[0], cores, best[1], sample, best[2]
+
+
+def sensor_trace_error(blob_path, rows, ks, tendon_damping=None):
+    """The metric's second half ("sensor-trace error"), informational: the sensor traces the bench just produced for a few
+    worlds against the fp64 oracle run on the host with the same stiffness (the oracle as the checker, inside the
+    cpu_baseline leg).  Relative to each channel's peak; the settle rows are contact-free and must agree tightly, over the
+    squeeze contact make/break events amplify round-off, so the median row is reported (tests/test_gpu.py holds the bars)."""
+    try:
+        _cpu_init(blob_path, tendon_damping)
+        w = _W["w"]
+        settle, med, worst = 0.0, [], 0.0
+        for r, k in zip(rows, ks):
+            w.set_stiffness(float(k))
+            want, _, st = w.episode()
+            scale = np.abs(want).max(axis=0) + 1e-12
+            err = (np.abs(np.asarray(r, dtype=np.float64) - want) / scale).max(axis=1)
+            settle = max(settle, float(err[:40].max()))
+            med.append(float(np.median(err)))
+            worst = max(worst, float(err.max()))
+        return {"worlds": len(med), "settle_rows_max_rel": settle, "row_median_rel": float(np.median(med)), "row_max_rel": worst,
+                "against": "fp64 oracle port on the host (not libmujoco), same stiffness, relative to each channel's peak",
+                "stated_fp32_tolerance": {"settle_rows": 1e-4, "row_median": 5e-3}}
+    except Exception as e:                                   # noqa: BLE001 -- informational key only
+        return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -395,9 +420,14 @@ def main():
 
     cpu = None
     pgs_flops = None
+    trace_err = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import sgoracle as so
         so.build()
+        last = args.warmup + args.steps - 1                  # `traj` still holds the last timed step
+        k_last = batched.world_uniform(args.seed, ids, 300, 1400, stream=last)
+        pick = [0, Wg // 3, (2 * Wg) // 3, Wg - 1]
+        trace_err = sensor_trace_error(blob, traj[pick].double().cpu().numpy(), k_last[pick], args.tendon_damping)
         v, cores, secs, sample, pgs_flops = cpu_throughput(blob, args.cpu_episodes_per_core, seed=args.seed, tendon_damping=args.tendon_damping, model=args.model)
         cpu = {"value": v, "unit": "world-steps/s", "cores": cores, "kind": "port", "sample": sample + ", %.1f s" % secs}
 
@@ -417,6 +447,8 @@ def main():
                              "peak_tflops_at_sampled_clock": fp32_peak}
     if traj_kernels is not None:
         line["traj_kernels"] = traj_kernels
+    if trace_err is not None:
+        line["sensor_trace_error"] = trace_err
     print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

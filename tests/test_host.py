@@ -7,7 +7,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import ROOT, pkg
+from conftest import ROOT, blob_path, pkg
 
 
 def test_default_schedule_is_the_reference_protocol(batched):
@@ -286,3 +286,21 @@ def test_two_rank_dataset_regeneration_with_gloo(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "OK" in out.stdout
+
+
+def test_bench_sensor_trace_error_against_the_oracle(oracle):
+    """bench.py's informational sensor_trace_error: zero for the oracle's own traces, the perturbation otherwise, and an
+    error key (never an exception) when it cannot run."""
+    sys.path.insert(0, ROOT)
+    import bench
+    w = oracle.OracleWorld(oracle.OracleModel(open(blob_path("softbox"), "rb").read()))
+    rows = []
+    for k in (400.0, 900.0):
+        w.set_stiffness(k)
+        rows.append(w.episode()[0])
+    out = bench.sensor_trace_error(blob_path("softbox"), np.array(rows), [400.0, 900.0])
+    assert out["worlds"] == 2 and out["settle_rows_max_rel"] == 0.0 and out["row_max_rel"] == 0.0
+    bumped = np.array(rows) * (1 + 1e-3)
+    out = bench.sensor_trace_error(blob_path("softbox"), bumped, [400.0, 900.0])
+    assert 5e-4 < out["row_max_rel"] < 2e-3 and 0 < out["settle_rows_max_rel"] < 2e-3
+    assert "error" in bench.sensor_trace_error("/nonexistent.sgm", bumped, [400.0, 900.0])

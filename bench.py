@@ -427,7 +427,10 @@ def main():
         last = args.warmup + args.steps - 1                  # `traj` still holds the last timed step
         k_last = batched.world_uniform(args.seed, ids, 300, 1400, stream=last)
         pick = [0, Wg // 3, (2 * Wg) // 3, Wg - 1]
-        trace_err = sensor_trace_error(blob, traj[pick].double().cpu().numpy(), k_last[pick], args.tendon_damping)
+        try:
+            trace_err = sensor_trace_error(blob, traj[pick].double().cpu().numpy(), k_last[pick], args.tendon_damping)
+        except Exception as e:                               # noqa: BLE001 -- informational key only
+            trace_err = {"error": "%s: %s" % (type(e).__name__, e)}
         v, cores, secs, sample, pgs_flops = cpu_throughput(blob, args.cpu_episodes_per_core, seed=args.seed, tendon_damping=args.tendon_damping, model=args.model)
         cpu = {"value": v, "unit": "world-steps/s", "cores": cores, "kind": "port", "sample": sample + ", %.1f s" % secs}
 

@@ -86,3 +86,26 @@ def test_batch_create_fails_loudly_without_gpu(libpath):
     batched = pkg("batched")
     with pytest.raises(lib.SoftGripError):
         batched.BatchedManEnv(blob_path("softbox"), 4)
+
+
+def build_c_caller(libpath, out_dir):
+    """tests/cabi/rollout_host.c: a plain C99 program against include/softgrip.h and libsoftgrip.so (no Python, no torch)."""
+    exe = os.path.join(str(out_dir), "rollout_host")
+    libdir = os.path.dirname(libpath)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-O1", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cabi", "rollout_host.c"), "-L" + libdir, "-l:libsoftgrip.so",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_plain_c_caller_builds_and_fails_loudly_without_gpu(libpath, tmp_path):
+    """The boundary is usable from C as declared (header is valid C99, symbols link), model loading needs no GPU, and a
+    CPU-only box gets the explicit "no CUDA device" error instead of a fallback."""
+    torch = pytest.importorskip("torch")
+    exe = build_c_caller(libpath, tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present: the full run is tests/test_gpu.py::test_plain_c_caller_matches_the_python_path")
+    out = subprocess.run([exe, blob_path("softbox"), "4", str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 3, (out.returncode, out.stderr)
+    assert "nv 118 nshell 110 neq 327 nu 2 nsensordata 12 levels 53" in out.stdout
+    assert "no CUDA device" in out.stderr and not os.path.exists(str(tmp_path / "out.bin"))

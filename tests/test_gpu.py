@@ -382,3 +382,22 @@ def test_other_models_along_a_stabilised_episode(torch_cuda, batched, make_world
         assert bool(torch.isfinite(traj).all()) and int((flagged != 0).sum()) == 0, (name, dtype, st.cpu().numpy())
         err = (np.abs(traj[0].double().cpu().numpy() - rows) / np.abs(rows).max(axis=0)).max(axis=1)
         print("%s %s stabilised episode vs oracle: first row %.2e, median row %.2e, max row %.2e" % (name, dtype, err[0], np.median(err), err.max()))
+
+
+def test_plain_c_caller_matches_the_python_path(torch_cuda, batched, tmp_path):
+    """tests/cabi/rollout_host.c -- a C99 program with host buffers only -- produces the same bits as BatchedManEnv.rollout."""
+    import subprocess
+    torch = torch_cuda
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_abi import build_c_caller
+    lib = pkg("_lib")
+    exe = build_c_caller(lib.LIB_PATH, tmp_path)
+    W = 6
+    out = subprocess.run([exe, blob_path("softbox"), str(W), str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    raw = np.fromfile(str(tmp_path / "out.bin"), dtype=np.float32, count=W * 200 * 12).reshape(W, 200, 12)
+    status = np.fromfile(str(tmp_path / "out.bin"), dtype=np.int32, offset=W * 200 * 12 * 4)
+    assert status.shape == (W,) and (status == 0).all()
+    env = make_env(batched, torch, W=W, dtype=torch.float32)
+    traj, k, st = env.rollout(stiffness=[300.0 + 1100.0 * w / (W - 1) for w in range(W)])
+    np.testing.assert_array_equal(traj.cpu().numpy(), raw)

@@ -329,3 +329,37 @@ def test_gpu_regenerated_tree_does_not_depend_on_the_launch_size(torch_cuda, tmp
     xt, _ = ds.read_pickle(outs[0][0]["file"])
     xv, _ = ds.read_pickle(outs[0][1]["file"])
     assert 0.5 < np.diff(xt[:, 5:35, 0], axis=1).std() / np.sqrt(2) < 0.9 and np.diff(xv[:, 5:35, 0], axis=1).std() < 0.1
+
+
+def test_emulated_trajectory_kernels_on_random_ragged_shapes(emulib):
+    """Seeded sweep over odd shapes (worlds, rows per world and channel counts that are not multiples of the warp / CTA /
+    grid sizes): all three kernels against their restatements."""
+    rng = np.random.default_rng(1234)
+    for case in range(12):
+        W, T, nchan = int(rng.integers(1, 40)), int(rng.integers(1, 75)), int(rng.choice([4, 8, 12, 16, 24, 36, 64]))
+        dtype = np.float32 if case % 2 == 0 else np.float64
+        prec = 32 if dtype == np.float32 else 64
+        x = _traj(W, T, nchan, dtype, seed=100 + case) + 500.0
+        rows = W * T
+        # statistics
+        nbytes = emulib.sg_traj_stats_workspace_bytes(rows, nchan, 0)
+        ws, mean, std = np.zeros(nbytes // 8), np.empty(nchan), np.empty(nchan)
+        assert emulib.sg_traj_channel_stats(_vp(x), rows, nchan, prec, 0, _vp(mean), _vp(std), _vp(ws), nbytes, None) == 0, (W, T, nchan)
+        wm, wsd = to.channel_mean_std(x)
+        assert np.allclose(mean, wm.reshape(-1), rtol=1e-12) and np.allclose(std, wsd.reshape(-1), rtol=1e-9, atol=1e-10), (W, T, nchan)
+        # noise with a row offset
+        first = int(rng.integers(0, 1 << 20))
+        nacc = int(rng.integers(0, nchan + 1))
+        out = np.empty_like(x)
+        assert emulib.sg_traj_add_noise(_vp(x), _vp(out), rows, first, nchan, nacc, 0.7, 0.06, case, None, None, prec, 0, None) == 0
+        want = to.noised_modality(x, case, nacc=nacc, first_row=first)
+        sig = np.where(np.arange(nchan) < nacc, 0.7, 0.06)
+        assert (np.abs(out - want) <= sig * Z_TOL + np.abs(want) * (2e-7 if prec == 32 else 1e-15)).all(), (W, T, nchan)
+        # mask, both modes
+        touch = _touch(max(W, 2), T, seed=200 + case, p_finger=0.15)[:W]
+        touch = np.ascontiguousarray(touch)
+        for mode, m in (("intended", 0), ("reference", 1)):
+            y = x.copy()
+            left = np.full(W, 3, dtype=np.int32)
+            assert emulib.sg_traj_mask_contact(_vp(y), _vp(touch), W, T, nchan, 3, 1 << 30, m, _vp(left) if m else None, prec, 0, None) == 0
+            assert (y == to.mask_contact(x, touch, 2, 1 << 30, mode)).all(), (W, T, nchan, mode)

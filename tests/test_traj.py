@@ -363,3 +363,24 @@ def test_emulated_trajectory_kernels_on_random_ragged_shapes(emulib):
             left = np.full(W, 3, dtype=np.int32)
             assert emulib.sg_traj_mask_contact(_vp(y), _vp(touch), W, T, nchan, 3, 1 << 30, m, _vp(left) if m else None, prec, 0, None) == 0
             assert (y == to.mask_contact(x, touch, 2, 1 << 30, mode)).all(), (W, T, nchan, mode)
+
+
+@pytest.mark.gpu
+def test_gpu_trajectory_kernels_on_random_ragged_shapes(torch_cuda):
+    """The ragged-shape sweep on the device (real grid sizes, ragged last CTAs / warps) through the Python mirror."""
+    torch = torch_cuda
+    fn = pkg("functions")
+    rng = np.random.default_rng(4321)
+    for case in range(10):
+        W, T, nchan = int(rng.integers(1, 3000)), int(rng.integers(1, 75)), int(rng.choice([4, 8, 12, 16, 24, 36, 64]))
+        dtype = np.float32 if case % 2 == 0 else np.float64
+        x = _traj(W, T, nchan, dtype, seed=300 + case) + 500.0
+        xd = torch.from_numpy(x).cuda()
+        mean, std = fn.channel_mean_std(xd)
+        wm, wsd = to.channel_mean_std(x)
+        assert np.allclose(mean.cpu().numpy(), wm, rtol=1e-12) and np.allclose(std.cpu().numpy(), wsd, rtol=1e-9, atol=1e-10), (W, T, nchan)
+        first, nacc = int(rng.integers(0, 1 << 20)), int(rng.integers(0, nchan + 1))
+        out = fn.noised_modality(xd, seed=case, nacc=nacc, first_row=first)
+        want = to.noised_modality(x, case, nacc=nacc, first_row=first)
+        sig = np.where(np.arange(nchan) < nacc, 0.7, 0.06)
+        assert (np.abs(out.cpu().numpy() - want) <= sig * Z_TOL + np.abs(want) * (2e-7 if dtype == np.float32 else 1e-15)).all(), (W, T, nchan)

@@ -220,7 +220,13 @@ def regenerate_distributed(out_dir, n_train, n_val, n_test, rollouts, shapes=SHA
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     own = not dist.is_initialized()
     if own:
-        dist.init_process_group(backend)
+        if backend == "nccl":                              # one rank per GPU: the barrier's communicator lives on this rank's device
+            import torch
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
     rank, world = dist.get_rank(), dist.get_world_size()
     stems = regenerate_shard(out_dir, n_train, n_val, n_test, rollouts, rank, world, shapes=shapes, drop_diverged=drop_diverged)
     dist.barrier()

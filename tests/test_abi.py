@@ -109,3 +109,10 @@ def test_plain_c_caller_builds_and_fails_loudly_without_gpu(libpath, tmp_path):
     assert out.returncode == 3, (out.returncode, out.stderr)
     assert "nv 118 nshell 110 neq 327 nu 2 nsensordata 12 levels 53" in out.stdout
     assert "no CUDA device" in out.stderr and not os.path.exists(str(tmp_path / "out.bin"))
+
+
+def test_integration_doc_maps_every_entry_point():
+    """INTEGRATION.md's call-site map names every symbol the header declares."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in declared_symbols() if s not in doc]
+    assert not missing, missing

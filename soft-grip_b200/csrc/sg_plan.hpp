@@ -383,10 +383,8 @@ inline Plan build_plan(const void* blob, size_t nbytes) {
   }
   D.nchain = nchain;
 
-  size_t o = 0;
   auto alloc_d = [&](size_t n) { size_t r = P.tab.size(); P.tab.resize(r + n, 0.0); return (int)r; };
   auto alloc_i = [&](size_t n) { size_t r = P.itab.size(); P.itab.resize(r + n, 0); return (int)r; };
-  (void)o;
 
   // ---- chain descriptors ----
   D.o_chain = alloc_d((size_t)MAXCHAIN * CH_STRIDE);

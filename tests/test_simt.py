@@ -358,8 +358,9 @@ def _protocol_ctrl(step):
     return 0.0 if step < 281 else (-0.2 if step < 841 else 0.2)
 
 
+@pytest.mark.parametrize("prec", [64, 32])
 @pytest.mark.parametrize("name", ["softball", "softcylinder", "softbox_refined"])
-def test_emulated_other_models_along_a_stabilised_episode(emu, make_world, name):
+def test_emulated_other_models_along_a_stabilised_episode(emu, make_world, name, prec):
     """SURVEY 8d cfg 3: softball / softcylinder run away under the restated semantics at the committed tendon damper; with
     the damper at a stable value (stated above) the whole squeeze episode runs clean in the oracle, and the kernel source
     agrees with it step for step from snapshots taken all along that episode (settle, closing, peak contact, release)."""
@@ -376,7 +377,7 @@ def test_emulated_other_models_along_a_stabilised_episode(emu, make_world, name)
             snaps[step] = (snaps[step], w.get_state(), w.get_int("ncon"))
     q_end = w.get_state()[0]
     assert np.isfinite(q_end).all() and np.abs(q_end).max() < 1.0
-    env = emu.EmuBatch(blob_path(name), 2, prec=64, lpw=8)
+    env = emu.EmuBatch(blob_path(name), 2, prec=prec, lpw=8)
     env.set_params(stiffness=np.full(2, 700.0), tdamping=np.full(2, STABLE_TENDON_DAMPING[name]))
     env.set_debug_world(1)
     ncons = []
@@ -386,7 +387,10 @@ def test_emulated_other_models_along_a_stabilised_episode(emu, make_world, name)
         env.step(1)
         q1, v1, a1, qacc = env.get_state()
         assert int(env.debug("ncon")[0]) == ncon
-        assert rel(q1[1], oq) < 1e-8 and rel(v1[1], ov) < 1e-8 and rel(qacc[1], oacc) < 1e-8 and rel(a1[1], oa) < 1e-12, step
+        err = {"q": rel(q1[1], oq), "v": rel(v1[1], ov), "qacc": rel(qacc[1], oacc)}
+        for key, e in err.items():
+            assert e < (1e-8 if prec == 64 else FP32_TOL[key]), (step, key, e)
+        assert rel(a1[1], oa) < (1e-12 if prec == 64 else 1e-6), step
         ncons.append(ncon)
     assert (env.status() == 0).all() and max(ncons) > min(ncons)
     env.close()

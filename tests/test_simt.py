@@ -427,3 +427,31 @@ def test_c_abi_rejects_empty_and_malformed_requests(emu):
     assert L.sg_batch_create(env.m, 1, 5, 32, C.byref(b)) < 0 and "device" in err()
     assert L.sg_batch_set_debug_world(env.b, 7) < 0 and "range" in err()
     env.close()
+
+
+@pytest.mark.parametrize("name,lpw", [("softbox_refined", 16), ("softbox_refined", 32), ("softball", 16)])
+def test_emulated_larger_models_at_more_lanes_per_world(emu, make_world, name, lpw):
+    """The lane counts DESIGN.md section 7 proposes for the larger models (shorter equality sweeps): same step parity at
+    peak contact as the default 8 lanes, and the sweep really is shorter."""
+    w = make_world(name)
+    w.set_tendon_damping(0, STABLE_TENDON_DAMPING[name])
+    w.reset()
+    for step in range(839):
+        w.set_ctrl([_protocol_ctrl(step)] * 2)
+        before = w.get_state()
+        assert w.step() == 0
+    oq, ov, oa, oacc = w.get_state()
+    steps = {}
+    for lanes in (8, lpw):
+        env = emu.EmuBatch(blob_path(name), 32 // lanes + 1, prec=64, lpw=lanes)
+        W = 32 // lanes + 1
+        env.set_params(stiffness=np.full(W, 700.0), tdamping=np.full(W, STABLE_TENDON_DAMPING[name]))
+        env.set_debug_world(W - 1)
+        env.set_state(*before); env.set_ctrl([_protocol_ctrl(838)] * 2)
+        env.step(1)
+        q1, v1, a1, qacc = env.get_state()
+        assert int(env.debug("ncon")[0]) == w.get_int("ncon") > 20
+        assert rel(q1[-1], oq) < 1e-8 and rel(v1[-1], ov) < 1e-8 and rel(qacc[-1], oacc) < 1e-8
+        steps[lanes] = int(env.debug("sweep_schedule")[0])
+        env.close()
+    assert steps[lpw] < 0.7 * steps[8], steps

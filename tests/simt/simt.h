@@ -149,7 +149,7 @@ inline void launch(F kernel, unsigned grid, unsigned block, size_t smem, const A
   gridDim.x = grid; blockDim.x = block;
   for (unsigned b = 0; b < grid; b++) {
     blockIdx.x = b;
-    memset(CTA.smem, 0xff, smem);   // NaN pattern: reads of never-written shared memory show up as NaNs
+    if (smem) memset(CTA.smem, 0xff, smem);   // NaN pattern: reads of never-written shared memory show up as NaNs
     run_cta();
   }
 }

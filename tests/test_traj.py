@@ -176,6 +176,24 @@ def test_batched_contact_flag_agrees_with_the_row_scan():
         assert (flag == (want[:, t, 0] != 0)).all()
 
 
+def test_trajectory_kernel_source_is_clean_under_asan_and_ubsan(tmp_path):
+    """tests/simt/asan_traj.cpp: the three kernels over ragged shapes / grids on exact-size heap buffers with
+    -fsanitize=address,undefined -- no out-of-bounds access, no undefined behaviour in the kernel source."""
+    import subprocess
+    exe = str(tmp_path / "asan_traj")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
+           "-I" + os.path.join(ROOT, "tests", "simt"), "-I" + os.path.join(ROOT, "soft-grip_b200", "csrc"), "-Wno-unknown-pragmas",
+           "-o", exe, os.path.join(ROOT, "tests", "simt", "asan_traj.cpp")]
+    built = subprocess.run(cmd, capture_output=True, text=True)
+    if built.returncode != 0 and "sanitize" in built.stderr:
+        pytest.skip("this g++ has no sanitizer runtime")
+    assert built.returncode == 0, built.stderr[-2000:]
+    env = dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0:detect_leaks=0")
+    out = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "asan driver done" in out.stdout, (out.stdout[-500:], out.stderr[-3000:])
+    assert "ERROR: AddressSanitizer" not in out.stderr and "runtime error" not in out.stderr, out.stderr[-3000:]
+
+
 def test_trajectory_entry_points_reject_bad_arguments(emulib):
     x = np.zeros((4, 12), dtype=np.float32)
     bad = np.zeros(4 * 12 + 1, dtype=np.float32)[1:]                     # 4-byte aligned only

@@ -5,21 +5,24 @@
     python bench.py --impl reference --gpus N --steps K ...   # the CPU path (oracle port, all host cores)
     N>1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one full squeeze episode (reset + 1 + 200*7 = 1401 physics steps, ref: create_dataset.py:14-17,
-33-60) of a batch of `--worlds-per-gpu` worlds per GPU, i.e. one launch of the rollout kernel per GPU.
-Workload = BASELINE.json configs[2] (randomised stiffness U(300,1400), fp32 fast path, worlds sharded over
-the GPUs with no collective on the step path), on the softbox model (the stable primary model),
-processed in per-GPU batches so that one step takes seconds, not minutes.  Weak scaling: per-GPU work fixed.
+Workload = BASELINE.json configs[2] as written: `--worlds` = 65 536 worlds IN TOTAL, sharded W/N per rank (strong
+scaling; `--weak` keeps `--worlds` per GPU instead), every world with its own stiffness U(300,1400) (ref:
+environment/manenv.py:103-109), shell damping and object-centre offset (the two extensions configs[2] names; see
+--damping-range / --offset-range), fp32 fast path, softbox model, no collective on the step path.  One "step" = one full
+squeeze episode (reset + 1 + 200*7 = 1401 physics steps, ref: create_dataset.py:14-17,33-60) of the rank's shard
+= one launch of the rollout kernel per GPU.  Other BASELINE configs: `--config 1` (4 096 worlds, fp64 verification
+build, fixed stiffness, error against the oracle), `--model softball|softcylinder|softbox_refined --tendon-damping D`.
 
 `value`   : device-timed (CUDA events on the launching stream, max over ranks), parameters resident in HBM.
-`e2e`     : the same episode through sg_batch_rollout_host with pinned HOST buffers (H2D of the stiffness
-            vector and D2H of the whole trajectory inside the timed region, wall clock, max over ranks).
+`e2e`     : the same episode through sg_batch_rollout_host_params with pinned HOST buffers (H2D of the per-world
+            parameters and D2H of the whole trajectory + status inside the timed region, wall clock, max over ranks).
 `roofline`: HBM roofline of the rollout kernel on its algorithmic bytes (the kernel is latency/issue bound on
-            the Gauss-Seidel sweep, so this fraction is tiny by construction).
-`cpu_baseline`: the fp64 oracle (a port, not libmujoco) on the host cores, bounded sample, rank 0 at N=1.
-`sensor_trace_error`: (N=1) four of the worlds just simulated against the fp64 oracle with the same stiffness; informational.
-`traj_kernels`: (N=1, outside the timed region) the HBM-bound kernels that post-process the trajectory buffer, each timed
-            alone against the HBM roof; informational, a failure there is reported in the key and never raised.
+            the Gauss-Seidel sweep, so this fraction is tiny by construction); `fp32_pipe` is the pipe view.
+`cpu_baseline`: the fp64 oracle (a port, not libmujoco; -O3 -march=native) on the host cores, bounded sample, rank 0, N=1.
+`variants`: (N=1) the same launch with stiffness-only randomisation, and with shell damping U(50,200) (below ~85 the
+            softbox volume mode is linearly unstable, SURVEY App. E: those worlds are flagged diverged and counted).
+`sensor_trace_error`: (N=1) worlds just simulated against the fp64 oracle with the same parameters.
+`traj_kernels`: (N=1, outside the timed region) the HBM-bound kernels that post-process the trajectory buffer.
 """
 import argparse
 import ctypes as C
@@ -133,6 +136,26 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------
+# per-world parameters of BASELINE.json configs[2] (counter-based per GLOBAL world id: invariant to the sharding)
+# ---------------------------------------------------------------------------------------------
+def world_params(args, ids, it, mode=None):
+    """(stiffness[W], damping[W] | None, objoff[W,3] | None) of step `it` for the global world ids `ids`."""
+    batched = importlib.import_module("soft-grip_b200.batched")
+    mode = mode or args.randomise
+    if args.fixed_stiffness is not None:
+        k = np.full(len(ids), float(args.fixed_stiffness))
+    else:
+        k = batched.world_uniform(args.seed, ids, 300, 1400, stream=it)            # ref: manenv.py:103-109
+    if mode == "stiffness":
+        return k, None, None
+    lo, hi = (50.0, 200.0) if mode == "all_damping_50_200" else args.damping_range
+    d = batched.world_uniform(args.seed, ids, lo, hi, stream=100000 + it)
+    r = args.offset_range
+    off = np.stack([batched.world_uniform(args.seed, ids, -r, r, stream=200000 + 3 * it + c) for c in range(3)], axis=1)
+    return k, d, np.ascontiguousarray(off)
+
+
+# ---------------------------------------------------------------------------------------------
 # CPU path (oracle port): used as cpu_baseline and as the --impl reference arm
 # ---------------------------------------------------------------------------------------------
 _W = {}
@@ -140,107 +163,165 @@ _W = {}
 
 def _cpu_init(blob_path, tendon_damping=None):
     from oracle import sgoracle as so
+    so.use_native()                                  # -O3 -march=native, built on the box this runs on
     blob = open(blob_path, "rb").read()
     _W["m"] = so.OracleModel(blob)
     _W["w"] = so.OracleWorld(_W["m"])
+    _W["blob"] = blob_path
     if tendon_damping is not None:
         _W["w"].set_tendon_damping(0, float(tendon_damping))
 
 
-def _cpu_episodes(ks):
+def _oracle_apply(w, model_info, k, d, off):
+    """One world's parameters on the oracle, the way sg_batch_set_params applies them on the device: stiffness -> joints
+    11..63 + tendon 0 (ref: manenv.py:12-13,103-109), damping -> every shell slider, offset -> the object's centre body."""
+    w.set_stiffness(float(k))
+    nfd, nv, obj_body, pos0 = model_info
+    if d is not None:
+        for i in range(nfd, nv):
+            w.set_dof_damping(i, float(d))
+    if off is not None:
+        w.set_body_pos(obj_body, pos0 + np.asarray(off, dtype=np.float64))
+
+
+def _model_info(blob_path):
+    """(finger dofs, nv, body id of the composite's centre body, its model position) from the compiled blob."""
+    mjcf = importlib.import_module("soft-grip_b200.mjcf")
+    A = mjcf.load_blob(blob_path).arrays
+    jt, jb = np.asarray(A["jnt_type"]), np.asarray(A["jnt_bodyid"])
+    slide = np.nonzero(jt == 2)[0]                               # mjJNT_SLIDE: the composite's shell sliders
+    obj_body = int(np.asarray(A["body_parentid"])[jb[slide[0]]])
+    pos0 = np.asarray(A["body_pos"], dtype=np.float64).reshape(-1, 3)[obj_body].copy()
+    nv = int(np.asarray(A["dof_bodyid"]).shape[0])
+    return nv - len(slide), nv, obj_body, pos0
+
+
+def _cpu_episodes(job):
+    ks, ds, offs = job
     w = _W["w"]
-    chk, flops, n = 0.0, 0.0, 0
-    for k in ks:
-        w.set_stiffness(float(k))
+    if "info" not in _W:
+        _W["info"] = _model_info(_W["blob"])
+    chk, n = 0.0, 0
+    w.flops(reset=True)
+    for i, k in enumerate(ks):
+        _oracle_apply(w, _W["info"], k, None if ds is None else ds[i], None if offs is None else offs[i])
         rows, touch, st = w.episode()
         chk += float(np.abs(rows).sum())
-        flops += w.last_step_flops()
         n += 1
-    return chk, flops / max(1, n)
+    f = w.flops(reset=True)
+    return chk, f
 
 
-def cpu_throughput(blob_path, episodes_per_core, repeats=1, cores=None, seed=0, tendon_damping=None, model="softbox"):
-    """world-steps/s of the oracle with one process per host core; returns (value, cores, seconds, sample text)."""
+def _cpu_jobs(args, cores, per_core, it, mode=None):
+    ids = np.arange(cores * per_core)
+    k, d, off = world_params(args, ids, it, mode)
+    return [(list(k[i::cores]), None if d is None else list(d[i::cores]), None if off is None else list(off[i::cores])) for i in range(cores)]
+
+
+def cpu_throughput(args, blob_path, episodes_per_core, repeats=1, cores=None):
+    """world-steps/s of the oracle with one process per host core on the bench's own workload; returns
+    (value, cores, seconds, sample text, flops per world-step (PGS, all stages))."""
     from concurrent.futures import ProcessPoolExecutor
-    batched = importlib.import_module("soft-grip_b200.batched")
+    from oracle import sgoracle as so
+    so.build_native(force=True)                      # once, here, for the host this runs on; the workers only load it
     cores = cores or len(os.sched_getaffinity(0))
     best = None
-    with ProcessPoolExecutor(cores, initializer=_cpu_init, initargs=(blob_path, tendon_damping)) as ex:
-        list(ex.map(_cpu_episodes, [[700.0][:0]] * cores))      # spin the workers up (model load excluded)
+    with ProcessPoolExecutor(cores, initializer=_cpu_init, initargs=(blob_path, args.tendon_damping)) as ex:
+        list(ex.map(_cpu_episodes, [([], None, None)] * cores))      # spin the workers up (model load excluded)
         for rep in range(repeats):
-            ks = batched.world_uniform(seed + rep, np.arange(cores * episodes_per_core), 300, 1400)
-            chunks = [list(ks[i::cores]) for i in range(cores)]
+            jobs = _cpu_jobs(args, cores, episodes_per_core, 500000 + rep)
             t0 = time.perf_counter()
-            res = list(ex.map(_cpu_episodes, chunks))
+            res = list(ex.map(_cpu_episodes, jobs))
             dt = time.perf_counter() - t0
             val = cores * episodes_per_core * STEPS_PER_EPISODE / dt
             if best is None or val > best[0]:
-                best = (val, dt, res[0][1])
-    sample = "%d processes x %d full squeeze episodes (%s, stiffness U(300,1400), fp64 oracle port)" % (cores, episodes_per_core, model)
+                f = np.sum([r[1] for r in res], axis=0)
+                best = (val, dt, (float(f[1] / max(1.0, f[0])), float(f[2] / max(1.0, f[0]))))
+    sample = "%d processes x %d full squeeze episodes (%s, randomise=%s, fp64 oracle port, gcc -O3 -march=native)" % (
+        cores, episodes_per_core, args.model, args.randomise)
     return best[0], cores, best[1], sample, best[2]
 
 
-def sensor_trace_error(blob_path, rows, ks, tendon_damping=None):
-    """The metric's second half ("sensor-trace error"), informational: the sensor traces the bench just produced for a few
-    worlds against the fp64 oracle run on the host with the same stiffness (the oracle as the checker, inside the
-    cpu_baseline leg).  Relative to each channel's peak; the settle rows are contact-free and must agree tightly, over the
-    squeeze contact make/break events amplify round-off, so the median row is reported (tests/test_gpu.py holds the bars)."""
+def sensor_trace_error(args, blob_path, rows, params):
+    """The metric's second half ("sensor-trace error"): the sensor traces the bench just produced for a few worlds against
+    the fp64 oracle run on the host with the same per-world parameters (the oracle as the checker, inside the cpu_baseline
+    leg).  Relative to each channel's peak.  The 40 settle rows are contact-free and must agree tightly; over the squeeze
+    contact make/break events amplify round-off (the oracle run against itself from a 1e-7
+    perturbation deviates as much), so the median row is the horizon statistic; tests/test_gpu.py asserts the same numbers."""
     try:
-        _cpu_init(blob_path, tendon_damping)
+        _cpu_init(blob_path, args.tendon_damping)
         w = _W["w"]
+        info = _model_info(blob_path)
         settle, med, worst = 0.0, [], 0.0
-        for r, k in zip(rows, ks):
-            w.set_stiffness(float(k))
+        ks, ds, offs = params
+        for i, r in enumerate(rows):
+            _oracle_apply(w, info, ks[i], None if ds is None else ds[i], None if offs is None else offs[i])
             want, _, st = w.episode()
             scale = np.abs(want).max(axis=0) + 1e-12
             err = (np.abs(np.asarray(r, dtype=np.float64) - want) / scale).max(axis=1)
             settle = max(settle, float(err[:40].max()))
             med.append(float(np.median(err)))
             worst = max(worst, float(err.max()))
-        return {"worlds": len(med), "settle_rows_max_rel": settle, "row_median_rel": float(np.median(med)), "row_max_rel": worst,
-                "against": "fp64 oracle port on the host (not libmujoco), same stiffness, relative to each channel's peak",
-                "stated_fp32_tolerance": {"settle_rows": 1e-4, "row_median": 5e-3}}
+        return {"worlds": len(med), "settle_rows_max_rel": settle, "row_median_rel": float(np.median(med)),
+                "row_median_rel_worst_world": float(np.max(med)), "row_max_rel": worst,
+                "against": "fp64 oracle port on the host (not libmujoco), same per-world parameters, relative to each channel's peak",
+                "stated_tolerance": TRACE_TOLERANCE}
     except Exception as e:                                   # noqa: BLE001 -- informational key only
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
+# stated tolerances of the fast path against the fp64 oracle over the full horizon (DESIGN.md section 4; asserted by
+# tests/test_gpu.py::test_fp32_trace_error_against_the_oracle on the same statistic)
+TRACE_TOLERANCE = {"fp32": {"settle_rows_max_rel": 1e-4, "row_median_rel": 5e-2}, "fp64": {"settle_rows_max_rel": 1e-9, "row_median_rel": 5e-2}}
+
+
 # ---------------------------------------------------------------------------------------------
 def run_reference_arm(args, rank):
+    """The reference's own CPU implementation of the path = the oracle port (MuJoCo is not installable here), with all the
+    host threads it can use, on this arm's config; each step a bounded sample (cores x --ref-episodes-per-core episodes)."""
     if rank != 0:
         return
     blob = os.path.join(ROOT, "tests", "golden", args.model + ".sgm")
     from oracle import sgoracle as so
     so.build()
+    so.build_native(force=True)                      # once, here, for the host this runs on; the workers only load it
     cores = len(os.sched_getaffinity(0))
     from concurrent.futures import ProcessPoolExecutor
-    batched = importlib.import_module("soft-grip_b200.batched")
     times = []
     with ProcessPoolExecutor(cores, initializer=_cpu_init, initargs=(blob, args.tendon_damping)) as ex:
-        list(ex.map(_cpu_episodes, [[]] * cores))
+        list(ex.map(_cpu_episodes, [([], None, None)] * cores))
         for it in range(args.warmup + args.steps):
-            ks = batched.world_uniform(args.seed + it, np.arange(cores * args.ref_episodes_per_core), 300, 1400)
+            jobs = _cpu_jobs(args, cores, args.ref_episodes_per_core, it)
             t0 = time.perf_counter()
-            list(ex.map(_cpu_episodes, [list(ks[i::cores]) for i in range(cores)]))
+            list(ex.map(_cpu_episodes, jobs))
             dt = time.perf_counter() - t0
             if it >= args.warmup:
                 times.append(dt)
     total = sum(times)
     value = args.steps * cores * args.ref_episodes_per_core * STEPS_PER_EPISODE / total
-    sample = "%d processes x %d episodes per step" % (cores, args.ref_episodes_per_core)
+    sample = "%d processes x %d full squeeze episodes per step (gcc -O3 -march=native)" % (cores, args.ref_episodes_per_core)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "world-steps/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, per_gpu=cores * args.ref_episodes_per_core, note="CPU path: fp64 oracle port of the MuJoCo step (not libmujoco), host cores only"),
+            "config": workload_config(args, worlds_total=None, per_gpu=cores * args.ref_episodes_per_core,
+                                      note="CPU path: fp64 oracle port of the MuJoCo step (not libmujoco), host cores only; each step is a bounded sample of the workload"),
             "cpu_baseline": {"value": value, "unit": "world-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, per_gpu, note=None):
-    cfg = {"workload": "BASELINE.json configs[2]: %s model, randomised stiffness U(300,1400) on joints 11..63 + tendon 0, fp32 fast path, "
-                       "full squeeze horizon (1401 physics steps, 200 sensor rows x 12 channels per world), worlds sharded over the GPUs" % args.model,
-           "model": args.model, "worlds_per_gpu_per_step": per_gpu, "physics_steps_per_world_per_step": STEPS_PER_EPISODE,
+def workload_config(args, worlds_total, per_gpu, note=None):
+    rand = {"stiffness": "stiffness U(300,1400) on joints 11..63 + tendon 0",
+            "all": "stiffness U(300,1400) on joints 11..63 + tendon 0, shell damping U(%g,%g), object-centre offset U(+-%g) m per axis"
+                   % (args.damping_range[0], args.damping_range[1], args.offset_range)}[args.randomise]
+    if args.fixed_stiffness is not None:
+        rand = "fixed stiffness %g" % args.fixed_stiffness + ("" if args.randomise == "stiffness" else "; " + rand.split(", ", 1)[1])
+    cfg = {"workload": "BASELINE.json configs[%d]: %s model, %s, %s, full squeeze horizon (1401 physics steps, 200 sensor rows x 12 "
+                       "channels per world), worlds sharded over the GPUs" % (args.config, args.model, rand,
+                                                                             "fp32 fast path" if args.precision == 32 else "fp64 verification build"),
+           "model": args.model, "worlds_total": worlds_total, "worlds_per_gpu_per_step": per_gpu,
+           "physics_steps_per_world_per_step": STEPS_PER_EPISODE, "randomise": args.randomise,
            "sim_step": 7, "sim_start": 1, "rows": 200, "parallelism": "independent world shards, no collective on the step path",
            "l2": "256 MiB scratch buffer written between timed steps (L2 flush); kernel inputs are tiny, state lives in shared memory"}
     if getattr(args, "tendon_damping", None) is not None:
@@ -294,17 +375,39 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="softgrip", choices=["softgrip", "reference"])
-    ap.add_argument("--model", default="softbox")
-    ap.add_argument("--worlds-per-gpu", type=int, default=18944)   # 2 x (148 SMs x 64 resident worlds)
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 4],
+                    help="BASELINE.json configs index: 2 (default) = 65 536 worlds, everything randomised, fp32; 1 = 4 096 worlds, fixed "
+                         "stiffness 700, fp64 verification build; 4 = stress (refined composite; give --worlds)")
+    ap.add_argument("--model", default=None)
+    ap.add_argument("--worlds", type=int, default=None, help="worlds in total (sharded W/N per rank); with --weak: per GPU")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --worlds per GPU instead of in total")
+    ap.add_argument("--precision", type=int, default=None, choices=[32, 64])
+    ap.add_argument("--randomise", default=None, choices=["stiffness", "all"])
+    ap.add_argument("--fixed-stiffness", type=float, default=None)
+    ap.add_argument("--damping-range", type=float, nargs=2, default=[100.0, 200.0],
+                    help="shell damping U(lo,hi): from the committed model value 100 to the reference's unused DEFAULT_DAMPING 200 "
+                         "(ref: manenv.py:5); below ~85 the softbox volume mode is linearly unstable (SURVEY App. E)")
+    ap.add_argument("--offset-range", type=float, default=0.05, help="object-centre offset U(+-r) m per axis")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--tendon-damping", type=float, default=None,
                     help="override the composite's volume-tendon damper for every world (softball / softcylinder: 50 is stable)")
-    ap.add_argument("--cpu-episodes-per-core", type=int, default=24)
-    ap.add_argument("--ref-episodes-per-core", type=int, default=1)
+    ap.add_argument("--cpu-episodes-per-core", type=int, default=16)
+    ap.add_argument("--ref-episodes-per-core", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--trace-worlds", type=int, default=8)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3                      # timing rules: W >= 3
+    defaults = {2: ("softbox", 65536, 32, "all", None), 1: ("softbox", 4096, 64, "stiffness", 700.0), 4: ("softbox_refined", 16384, 32, "all", None)}[args.config]
+    args.model = args.model or defaults[0]
+    args.worlds = args.worlds or defaults[1]
+    args.precision = args.precision or defaults[2]
+    args.randomise = args.randomise or defaults[3]
+    if args.fixed_stiffness is None:
+        args.fixed_stiffness = defaults[4]
+    if args.config == 4 and args.tendon_damping is None and args.model == "softbox_refined":
+        args.tendon_damping = 20.0
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -326,26 +429,35 @@ def main():
     from importlib import import_module
     lib = import_module("soft-grip_b200._lib")
 
-    Wg = args.worlds_per_gpu
+    # ---- sharding: contiguous blocks of global world ids, no collective on the step path ----
+    if args.weak:
+        W_total, lo = args.worlds * world, rank * args.worlds
+        hi = lo + args.worlds
+    else:
+        W_total = args.worlds
+        lo, hi = shard_range(W_total, rank, world)
+    Wg = hi - lo
+    tdtype = torch.float32 if args.precision == 32 else torch.float64
+    esize = 4 if args.precision == 32 else 8
     blob = os.path.join(ROOT, "tests", "golden", args.model + ".sgm")
-    env = batched.BatchedManEnv(blob, Wg, device=dev, dtype=torch.float32, seed=args.seed, world_offset=rank * Wg)
-    if args.tendon_damping is not None:
-        env.set_params(tendon_damping=np.full(Wg, args.tendon_damping))
+    env = batched.BatchedManEnv(blob, Wg, device=dev, dtype=tdtype, seed=args.seed, world_offset=lo)
     ev, val = batched.default_schedule(env.nu)
     T = ev.shape[0]
     sc = lib.SgSchedule(1, 7, T, ev.ctypes.data_as(C.POINTER(C.c_int)), val.ctypes.data_as(C.POINTER(C.c_double)))
-    traj = torch.empty((Wg, T, env.nsd), dtype=torch.float32, device=dev)
-    ids = np.arange(rank * Wg, (rank + 1) * Wg)
+    traj = torch.empty((Wg, T, env.nsd), dtype=tdtype, device=dev)
+    ids = np.arange(lo, hi)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
+    tdamp = None if args.tendon_damping is None else np.full(Wg, args.tendon_damping)
 
-    def stiffness_for(it):
-        return torch.from_numpy(batched.world_uniform(args.seed, ids, 300, 1400, stream=it)).to(dev)
+    def push_params(it, mode=None):
+        k, d, off = world_params(args, ids, it, mode)
+        env.stiffness = torch.from_numpy(k).to(dev)
+        env.set_params(damping=d, tendon_damping=tdamp, object_offset=off)     # resident in HBM before the timed region
+        return k, d, off
 
-    def one_step(it, timed):
-        k = stiffness_for(it)                           # resident in HBM before the timed region
-        env.stiffness = k
-        env._push_params()
+    def one_step(it, timed, mode=None):
+        push_params(it, mode)
         flush.fill_(it & 255)                           # L2 flush
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -361,6 +473,7 @@ def main():
     torch.cuda.synchronize(dev)
     barrier()
     launches0 = env.launch_count()
+    env.status(clear=True)
     with ClockSampler(local_rank) as clk:
         evs = [one_step(args.warmup + it, True) for it in range(args.steps)]
         torch.cuda.synchronize(dev)
@@ -372,18 +485,29 @@ def main():
     ndiv = sum_over_ranks(float(((st & batched.ST_DIVERGED) != 0).sum()), dev)
     nfull = sum_over_ranks(float(((st & (batched.ST_CON_FULL | batched.ST_UNSUPPORTED)) != 0).sum()), dev)
     finite = bool(torch.isfinite(traj).all().item())
-    world_steps = float(world) * Wg * STEPS_PER_EPISODE * args.steps
+    world_steps = float(W_total) * STEPS_PER_EPISODE * args.steps
     value = world_steps / (ms_total * 1e-3)
+    last = args.warmup + args.steps - 1                  # `traj` still holds the last timed step
+    pick = sorted(set(int(x) for x in np.linspace(0, Wg - 1, max(1, args.trace_worlds))))
+    traj_pick = traj[pick].double().cpu().numpy()
 
     # ---- end to end through the C-ABI with pinned HOST buffers ----
     k_host = torch.empty(Wg, dtype=torch.float64).pin_memory()
-    traj_host = torch.empty((Wg, T, env.nsd), dtype=torch.float32).pin_memory()
+    d_host = torch.empty(Wg, dtype=torch.float64).pin_memory() if args.randomise == "all" else None
+    o_host = torch.empty((Wg, 3), dtype=torch.float64).pin_memory() if args.randomise == "all" else None
+    traj_host = torch.empty((Wg, T, env.nsd), dtype=tdtype).pin_memory()
     status_host = np.zeros(Wg, dtype=np.int32)
+    hp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    h2d = Wg * 8 * (1 + (4 if args.randomise == "all" else 0))
+    d2h = Wg * (T * env.nsd * esize + 4)
 
     def e2e_step(it):
-        k_host.copy_(torch.from_numpy(batched.world_uniform(args.seed, ids, 300, 1400, stream=1000 + it)))
-        lib.check(env.L.sg_batch_rollout_host(env.h, C.byref(sc), C.c_void_p(k_host.data_ptr()), C.c_void_p(traj_host.data_ptr()), None,
-                                              status_host.ctypes.data_as(C.c_void_p)))
+        k, d, off = world_params(args, ids, 1000 + it)
+        k_host.copy_(torch.from_numpy(k))
+        if d_host is not None:
+            d_host.copy_(torch.from_numpy(d)); o_host.copy_(torch.from_numpy(off))
+        lib.check(env.L.sg_batch_rollout_host_params(env.h, C.byref(sc), hp(k_host), hp(d_host), None, hp(o_host), hp(traj_host), None,
+                                                     status_host.ctypes.data_as(C.c_void_p)))
     e2e_step(0)
     torch.cuda.synchronize(dev)
     barrier()
@@ -394,6 +518,24 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
     barrier()
     e2e_value = world_steps / e2e_s
+    e2e_launches = args.steps
+
+    # ---- variants (N = 1): what the randomisation costs / does ----
+    variants = None
+    if world == 1 and not args.no_variants and args.randomise == "all":
+        variants = {}
+        for name, mode in (("stiffness_only", "stiffness"), ("damping_50_200_and_offset", "all_damping_50_200")):
+            one_step(2000, False, mode)
+            torch.cuda.synchronize(dev)
+            env.status(clear=True)
+            e0, e1 = one_step(2001, True, mode)
+            torch.cuda.synchronize(dev)
+            stv = env.status(clear=True)
+            ms = e0.elapsed_time(e1)
+            variants[name] = {"value": Wg * STEPS_PER_EPISODE / (ms * 1e-3), "unit": "world-steps/s", "ms_per_step": ms, "steps": 1,
+                              "worlds_diverged": int(((stv & batched.ST_DIVERGED) != 0).sum()),
+                              "worlds_capacity_or_unsupported": int(((stv & (batched.ST_CON_FULL | batched.ST_UNSUPPORTED)) != 0).sum())}
+        push_params(last)
 
     if rank != 0:
         if world > 1:
@@ -401,53 +543,62 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the rollout kernel (HBM; algorithmic bytes = stiffness in + trajectory + status out) ----
+    # ---- roofline of the rollout kernel (HBM; algorithmic bytes = parameters in + trajectory + status out) ----
     peaks, which = measured_peaks()
-    bytes_per_world = 8 + T * env.nsd * 4 + 4
+    bytes_per_world = 8 * (1 + (4 if args.randomise == "all" else 0)) + T * env.nsd * esize + 4
     launch_s = (ms_local * 1e-3) / args.steps
     achieved = Wg * bytes_per_world / launch_s / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            # measured per launch of `worlds_per_launch` worlds under ncu --set full; scaled to this launch's world count
+            traffic = tj.get("dram_bytes_per_launch")
+            if traffic is not None and tj.get("worlds_per_launch"):
+                traffic = traffic * Wg / float(tj["worlds_per_launch"])
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": traffic, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback 6650 GB/s",
-                "kernel": "sg_step_kernel2<float, 8> (rollout mode)", "algorithmic_bytes_per_world_episode": bytes_per_world,
-                "note": "latency/issue-bound Gauss-Seidel kernel: state stays in shared memory for the whole episode, so the HBM fraction is tiny by design"}
+                "kernel": "sg_step_kernel2<%s, %d> (rollout mode)" % ("float" if args.precision == 32 else "double", env.config()["lanes_per_world"]),
+                "algorithmic_bytes_per_world_episode": bytes_per_world,
+                "note": "latency/issue-bound Gauss-Seidel kernel: state stays in shared memory for the whole episode, so the HBM fraction is tiny by design; see fp32_pipe"}
 
     cpu = None
-    pgs_flops = None
+    flops = None
     trace_err = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import sgoracle as so
         so.build()
-        last = args.warmup + args.steps - 1                  # `traj` still holds the last timed step
-        k_last = batched.world_uniform(args.seed, ids, 300, 1400, stream=last)
-        pick = [0, Wg // 3, (2 * Wg) // 3, Wg - 1]
-        try:
-            trace_err = sensor_trace_error(blob, traj[pick].double().cpu().numpy(), k_last[pick], args.tendon_damping)
-        except Exception as e:                               # noqa: BLE001 -- informational key only
-            trace_err = {"error": "%s: %s" % (type(e).__name__, e)}
-        v, cores, secs, sample, pgs_flops = cpu_throughput(blob, args.cpu_episodes_per_core, seed=args.seed, tendon_damping=args.tendon_damping, model=args.model)
+        k_l, d_l, o_l = world_params(args, ids, last)
+        sel = (k_l[pick], None if d_l is None else d_l[pick], None if o_l is None else o_l[pick])
+        trace_err = sensor_trace_error(args, blob, traj_pick, sel)
+        v, cores, secs, sample, flops = cpu_throughput(args, blob, args.cpu_episodes_per_core)
         cpu = {"value": v, "unit": "world-steps/s", "cores": cores, "kind": "port", "sample": sample + ", %.1f s" % secs}
 
     traj_kernels = None
-    if world == 1:
+    if world == 1 and args.precision == 32:
         traj_kernels = measure_traj_kernels(torch, traj, flush, peaks["hbm_gbs"])
 
     line = {"metric": METRIC, "value": value, "unit": "world-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args, Wg),
-            "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": Wg * 8, "d2h_bytes_per_step": Wg * (T * env.nsd * 4 + 4)},
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+            "dtype": "f32" if args.precision == 32 else "f64",
+            "data": "synthetic", "config": workload_config(args, W_total, Wg),
+            "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
             "launch_geometry": env.config(), "worlds_diverged": int(ndiv), "worlds_capacity_or_unsupported": int(nfull), "trajectory_finite": finite}
-    if pgs_flops:
-        fp32_peak = 148 * 128 * 2 * (line["clocks"]["sm_mhz"] or 1965.0) * 1e6 / 1e12
-        line["fp32_pipe"] = {"pgs_flops_per_world_step_last": pgs_flops, "achieved_tflops": value / world * pgs_flops / 1e12,
-                             "peak_tflops_at_sampled_clock": fp32_peak}
+    if flops:
+        clock = (line["clocks"]["sm_mhz"] or 1965.0)
+        peak = 148 * 128 * 2 * clock * 1e6 / 1e12 / (1 if args.precision == 32 else 64)     # fp64: 1/64 rate on B200
+        line["fp32_pipe" if args.precision == 32 else "fp64_pipe"] = {
+            "flops_per_world_step_all_stages": flops[1], "flops_per_world_step_pgs": flops[0],
+            "count": "episode average over the cpu_baseline sample: PGS counted per executed row / block update by the oracle's op counter, "
+                     "other stages by the closed-form count of SURVEY section 8d (oracle/sg_oracle.c sgo_flops_get)",
+            "achieved_tflops": value / world * flops[1] / 1e12, "peak_tflops_at_sampled_clock": peak,
+            "frac": value / world * flops[1] / 1e12 / peak}
+    if variants is not None:
+        line["variants"] = variants
     if traj_kernels is not None:
         line["traj_kernels"] = traj_kernels
     if trace_err is not None:

@@ -111,6 +111,19 @@ int sg_batch_rollout(sg_batch* b, const sg_schedule* s, void* traj_out, int* tou
 int sg_batch_rollout_host(sg_batch* b, const sg_schedule* s, const double* stiffness_host,
                           void* traj_host, int* touch_host, int* status_host);
 
+/* the same with every per-world parameter of sg_batch_set_params coming from HOST memory (fp64, [W]; objoff [W][3];
+ * NULL keeps what the batch holds): BASELINE.json configs[2] randomises stiffness, damping and object pose per world */
+int sg_batch_rollout_host_params(sg_batch* b, const sg_schedule* s, const double* stiffness_host,
+                                 const double* damping_host, const double* tdamping_host, const double* objoff_host,
+                                 void* traj_host, int* touch_host, int* status_host);
+/* trajectory layout written by sg_batch_rollout (the host variants always return the world-major one):
+ * SG_TRAJ_WORLD_MAJOR [W][nrows][nsensordata] -- one world's rows are contiguous = the reference's (T,12) sample
+ * (ref: create_dataset.py:62-63), each row written as 128-bit vectors;
+ * SG_TRAJ_SOA [nrows][nsensordata][W] -- structure of arrays, world index fastest (SURVEY section 8b `rollout`). */
+#define SG_TRAJ_WORLD_MAJOR 0
+#define SG_TRAJ_SOA 1
+int sg_batch_set_traj_layout(sg_batch* b, int layout);
+
 /* state access for parity tests on identical initial states (host fp64, synchronous).
  * qpos,qvel,qacc_warmstart: [W][nv]; act: [W][nu]; any pointer may be NULL. */
 int sg_batch_get_state(sg_batch* b, double* qpos, double* qvel, double* act, double* qacc_warmstart);

@@ -263,7 +263,9 @@ struct sgo_world {
   double* efc_A;     /* 3 per row: diagonal block of AR */
   int* mark;         /* nv   */
   int status, step_status, touch_mask, solver_iter, dense;
-  double flops;
+  double flops;            /* PGS op count of the last forward */
+  double flops_total, flops_pgs_total; long steps_total;   /* accumulated over every forward since the last sgo_flops_reset */
+  int ncand;               /* geom pairs that reached the narrowphase in the last forward */
 };
 
 static double* dalloc(size_t n) { return (double*)calloc(n ? n : 1, sizeof(double)); }
@@ -337,6 +339,11 @@ void sgo_set_dense_solver(sgo_world* d, int on) { d->dense = on; }
 void sgo_set_geom_mask(sgo_world* d, const int* mask) { memcpy(d->geom_mask, mask, sizeof(int) * d->m->ngeom); }
 int sgo_status(const sgo_world* d) { return d->status; }
 double sgo_last_step_flops(const sgo_world* d) { return d->flops; }
+/* op counts accumulated over every mj_forward since the last reset: out[0] = forwards, out[1] = PGS flops (counted per
+ * executed row / block update in solve_pgs), out[2] = all stages (PGS + the closed-form count of the other stages of
+ * 60 nv + 20 neq + 400 narrowphase pairs + 100 per contact row block + 3000 for the finger chains) */
+void sgo_flops_get(const sgo_world* d, double* out) { out[0] = (double)d->steps_total; out[1] = d->flops_pgs_total; out[2] = d->flops_total; }
+void sgo_flops_reset(sgo_world* d) { d->steps_total = 0; d->flops_pgs_total = 0; d->flops_total = 0; }
 
 /* mj_resetData: qpos=qpos0, everything else 0 (ref: manenv.py:57 sim.reset()) */
 void sgo_reset(sgo_world* d) {
@@ -745,7 +752,7 @@ static void make_frame(double* f) {
 /* mj_collision over the statically filtered pair list */
 static void collision(sgo_world* d) {
   const sgo_model* m = d->m;
-  d->ncon = 0; d->touch_mask = 0;
+  d->ncon = 0; d->touch_mask = 0; d->ncand = 0;
   for (int p = 0; p < m->npair; p++) {
     int g1 = m->pair_g1[p], g2 = m->pair_g2[p];
     int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
@@ -762,6 +769,7 @@ static void collision(sgo_world* d) {
       if (dot3(dif, dif) > bound * bound) continue;
     }
     rawcon rc[4]; int n = 0;
+    d->ncand++;
     if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) n = plane_capsule(rc, margin, p1, R1, p2, R2, m->geom_size + 3 * g2);
     else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) n = sphere_box(rc, margin, p1, m->geom_size[3 * g1], p2, R2, m->geom_size + 3 * g2);
     else if (t1 == GEOM_CAPSULE && t2 == GEOM_BOX) n = capsule_box(rc, margin, p1, R1, m->geom_size + 3 * g1, p2, R2, m->geom_size + 3 * g2);
@@ -1285,6 +1293,8 @@ void sgo_forward(sgo_world* d) {
   /* sensorAcc */
   rne(d, 1, NULL);
   sensors(d, 1);
+  d->steps_total++; d->flops_pgs_total += d->flops;
+  d->flops_total += d->flops + 60.0 * nv + 20.0 * m->neq + 400.0 * d->ncand + 100.0 * d->ncon + 3000.0;
 }
 
 /* mj_Euler with implicit joint damping */

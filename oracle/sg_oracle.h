@@ -59,6 +59,9 @@ int sgo_episode(sgo_world* w, int sim_start, int sim_step, int n_settle, int n_i
 
 /* op counter (algorithmic flop estimate of the last step, counted in the PGS and its setup) */
 double sgo_last_step_flops(const sgo_world* w);
+/* accumulated since the last reset: out[0] forwards, out[1] PGS flops, out[2] all-stage flops (see sg_oracle.c) */
+void sgo_flops_get(const sgo_world* w, double* out);
+void sgo_flops_reset(sgo_world* w);
 
 #ifdef __cplusplus
 }

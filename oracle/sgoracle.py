@@ -26,10 +26,34 @@ def build(force=False):
     return so
 
 
+def build_native(force=False):
+    """-O3 -march=native build for the CPU arm of bench.py, compiled on the box it runs on (falls back to the portable
+    build when the compiler is missing); same arithmetic, same results.  The parent process builds it once (force=True)
+    before it starts its workers; the workers only load it."""
+    so = os.path.join(_HERE, "_native", "libsgoracle_native.so")
+    src = os.path.join(_HERE, "sg_oracle.c")
+    try:
+        if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "_native/libsgoracle_native.so"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return so
+    except Exception:
+        return build()
+
+
+def use_native(force=False):
+    """Switch this process to the native build (call before the first lib())."""
+    global _LIB, _NATIVE
+    if _LIB is None:
+        _NATIVE = build_native(force)
+
+
+_NATIVE = None
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        L = C.CDLL(build())
+        L = C.CDLL(_NATIVE or build())
         P, D, I = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
         L.sgo_model_load.restype = P
         L.sgo_model_load.argtypes = [C.c_char_p, C.c_size_t]
@@ -57,6 +81,8 @@ def lib():
         L.sgo_episode.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, D, I]
         L.sgo_last_step_flops.restype = C.c_double
         L.sgo_last_step_flops.argtypes = [P]
+        L.sgo_flops_get.argtypes = [P, D]
+        L.sgo_flops_reset.argtypes = [P]
         L.sgo_test_capsule_box.argtypes = [D, D, D, D, D, D, D]
         L.sgo_test_sphere_box.argtypes = [D, C.c_double, D, D, D, D]
         L.sgo_test_qcqp2.argtypes = [D, D, D, C.c_double, D]
@@ -163,6 +189,14 @@ class OracleWorld:
         return out[:n]
 
     def last_step_flops(self): return self._L.sgo_last_step_flops(self.h)
+
+    def flops(self, reset=False):
+        """(forwards, PGS flops, all-stage flops) accumulated since the last reset."""
+        out = np.zeros(3)
+        self._L.sgo_flops_get(self.h, _dp(out))
+        if reset:
+            self._L.sgo_flops_reset(self.h)
+        return out
 
     def episode(self, sim_start=1, sim_step=7, n_settle=40, n_iter=160, open_close_div=80, ctrl_mag=0.2):
         """create_dataset.log_into_file's episode (ref: create_dataset.py:33-60) -> (rows[T,12], touch[T], status)."""

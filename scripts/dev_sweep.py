@@ -16,7 +16,7 @@ ref = None
 for cfg in cfgs:
     parts = {x[0]: int(x[1:]) for x in cfg.split(":")}
     k, l, a = parts.get("k", 2), parts.get("l", 8), parts.get("a", 0)
-    os.environ["SOFTGRIP_KERNEL"] = str(k); os.environ["SOFTGRIP_LPW"] = str(l); os.environ.pop("SOFTGRIP_AUX_SMEM", None)
+    os.environ["SOFTGRIP_LPW"] = str(l); os.environ.pop("SOFTGRIP_AUX_SMEM", None)
     os.environ.pop("SOFTGRIP_QV_SMEM", None)
     os.environ.pop("SOFTGRIP_TEAM", None)
     if parts.get("b", 1) == 0: os.environ["SOFTGRIP_NO_BANK_SCHEDULE"] = "1"

@@ -50,6 +50,8 @@ SIGNATURES = {
     "sg_batch_step": (C.c_int, [P, C.c_int, V, V, V]),
     "sg_batch_rollout": (C.c_int, [P, C.POINTER(SgSchedule), V, V, V]),
     "sg_batch_rollout_host": (C.c_int, [P, C.POINTER(SgSchedule), V, V, V, V]),
+    "sg_batch_rollout_host_params": (C.c_int, [P, C.POINTER(SgSchedule), V, V, V, V, V, V, V]),
+    "sg_batch_set_traj_layout": (C.c_int, [P, C.c_int]),
     "sg_batch_get_state": (C.c_int, [P, D, D, D, D]),
     "sg_batch_set_state": (C.c_int, [P, D, D, D, D]),
     "sg_batch_status": (C.c_int, [P, I, C.c_int]),

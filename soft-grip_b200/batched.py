@@ -261,10 +261,14 @@ class BatchedManEnv:
         check(self.L.sg_batch_status(self.h, out.ctypes.data_as(C.POINTER(C.c_int)), int(clear)))
         return out
 
-    def rollout(self, schedule=None, stiffness=None, return_touch=False):
+    def rollout(self, schedule=None, stiffness=None, return_touch=False, layout="WTC"):
         """Whole episode(s) on-chip: reset + ``sim_start`` steps, then one recorded row per env-step.
-        Returns (traj[W,T,12], stiffness[W], status[W] int32[, touch[W,T]])."""
+        Returns (traj, stiffness[W], status[W] int32[, touch[W,T]]).  ``layout="WTC"``: traj[W,T,12], one world's (T,12)
+        sample contiguous (the reference's sample shape, ref: create_dataset.py:62-63); ``layout="TCW"``: traj[T,12,W],
+        structure of arrays with the world index fastest."""
         torch = self.torch
+        if layout not in ("WTC", "TCW"):
+            raise ValueError("layout must be 'WTC' or 'TCW'")
         k = self.set_new_stiffness(stiffness=stiffness)
         self.episode += 1
         ev, val = schedule if schedule is not None else default_schedule(self.nu)
@@ -273,10 +277,15 @@ class BatchedManEnv:
         T = ev.shape[0]
         sc = SgSchedule(self.sim_start, self.sim_step, T, ev.ctypes.data_as(C.POINTER(C.c_int)),
                         val.ctypes.data_as(C.POINTER(C.c_double)))
-        traj = torch.empty((self.W, T, self.nsd), dtype=self.dtype, device=self.device)
+        shape = (self.W, T, self.nsd) if layout == "WTC" else (T, self.nsd, self.W)
+        traj = torch.empty(shape, dtype=self.dtype, device=self.device)
         touch = torch.empty((self.W, T), dtype=torch.int32, device=self.device) if return_touch else None
         self.status(clear=True)
-        check(self.L.sg_batch_rollout(self.h, C.byref(sc), self._ptr(traj), self._ptr(touch), self._stream()))
+        check(self.L.sg_batch_set_traj_layout(self.h, 0 if layout == "WTC" else 1))
+        try:
+            check(self.L.sg_batch_rollout(self.h, C.byref(sc), self._ptr(traj), self._ptr(touch), self._stream()))
+        finally:
+            check(self.L.sg_batch_set_traj_layout(self.h, 0))
         st = torch.from_numpy(self.status()).to(self.device)
         return (traj, k, st, touch) if return_touch else (traj, k, st)
 

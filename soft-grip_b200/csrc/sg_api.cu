@@ -1,5 +1,5 @@
 // sg_api.cu -- C-ABI of libsoftgrip.so (include/softgrip.h): model/plan upload, batch state in HBM,
-// kernel launches.  Host logic only; all physics is in sg_kernels.cuh.  There is no CPU fallback: every
+// kernel launches.  Host logic only; all physics is in sg_kernels2.cuh.  There is no CPU fallback: every
 // entry point that would compute needs a CUDA device and fails with an error otherwise.
 #include "sg_rt.hpp"
 
@@ -14,9 +14,6 @@
 #include "sg_plan.hpp"
 #define SG_ST_CON_FULL_BIT 2
 #define SG_ST_UNSUPPORTED_BIT 8
-#ifndef SG_SIMT_EMU
-#include "sg_kernels.cuh"      // first-generation kernel (one warp per world), kept for A/B runs: SOFTGRIP_KERNEL=1
-#endif
 #include "sg_launch.hpp"
 #include "sg_traj.cuh"
 
@@ -36,10 +33,7 @@ struct sg_batch {
   PlanDims D;                 // with per-batch capacities and masks folded in
   int W, device, precision;
   size_t esize;
-#ifndef SG_SIMT_EMU
-  SmemLayout L;
-#endif
-  int kernel = 2;             // 2: sub-warp worlds (sg_kernels2.cuh); 1: one warp per world (sg_kernels.cuh)
+  int kernel = 2;             // kernel generation (sg_kernels2.cuh: sub-warp worlds); the first-generation kernel is gone
   int lpw = 8;                // lanes per world of kernel 2
   int nwarp = 16;             // warps per CTA of kernel 2
   size_t smem2 = 0;           // dynamic shared memory per CTA of kernel 2
@@ -59,6 +53,7 @@ struct sg_batch {
   void* stage_traj = nullptr; size_t stage_traj_bytes = 0;   // device staging for rollout_host
   int* stage_touch = nullptr; size_t stage_touch_bytes = 0;
   long long launches = 0;
+  int traj_soa = 0;           // trajectory layout of sg_batch_rollout: 0 = [W][T][C], 1 = [T][C][W]
   unsigned long long* prof = nullptr; size_t prof_n = 0;   // SOFTGRIP_PROF=1: phase clocks of kernel 2 (development aid)
   int max_ctas = 0, per_sm = 0;
 };
@@ -202,7 +197,6 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   // kernel selection (environment overrides are development knobs; the defaults are the measured best)
   b->kernel = 2; b->lpw = 8; b->nwarp = 16;
   int aux_in_smem = 0;
-  if (const char* e = std::getenv("SOFTGRIP_KERNEL")) b->kernel = std::atoi(e);
   if (const char* e = std::getenv("SOFTGRIP_LPW")) b->lpw = std::atoi(e);
   if (const char* e = std::getenv("SOFTGRIP_NW")) b->nwarp = std::atoi(e);
   int qv_in_smem = 0;
@@ -212,10 +206,6 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
     delete b;
     return fail("SOFTGRIP_AUX_SMEM / SOFTGRIP_QV_SMEM: the shared-memory placement of the once-per-step data was removed from kernel 2 (measured slower; a single address space lets the compiler emit global loads)");
   }
-#ifdef SG_SIMT_EMU
-  b->kernel = 2;
-#endif
-  if (b->kernel != 1 && b->kernel != 2) { delete b; return fail("SOFTGRIP_KERNEL must be 1 or 2"); }
   if (b->nwarp < 1 || b->nwarp > SG_MAX_WARPS) { delete b; return fail("SOFTGRIP_NW must be 1..16"); }
   if (b->lpw != 4 && b->lpw != 8 && b->lpw != 16 && b->lpw != 32) { delete b; return fail("SOFTGRIP_LPW must be 4, 8, 16 or 32"); }
   if (b->kernel == 2) {
@@ -278,24 +268,6 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       CUDA_OK(cudaMemset(b->scratch, 0, (size_t)slots * cta_worlds * (size_t)b->L2.gs_stride));
     }
   }
-#ifndef SG_SIMT_EMU
-  else {
-    b->L = precision == 32 ? make_layout<float>(b->D) : make_layout<double>(b->D);
-    if ((size_t)b->L.bytes > prop.sharedMemPerBlockOptin) { sg_batch_destroy(b); return fail("sg_batch_create: world does not fit in shared memory"); }
-    // resident CTAs: one warp per world, limited by shared memory
-    if (precision == 32) {
-      CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.bytes));
-      CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_step_kernel<float>, 32, b->L.bytes));
-    } else {
-      CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->L.bytes));
-      CUDA_OK(cudaFuncSetAttribute(sg_step_kernel<double>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_step_kernel<double>, 32, b->L.bytes));
-    }
-    if (per_sm < 1) per_sm = 1;
-    b->max_ctas = per_sm * prop.multiProcessorCount; b->per_sm = per_sm;
-  }
-#endif
   *out = b;
   return sg_batch_reset(b, nullptr);
 }
@@ -339,10 +311,10 @@ extern "C" int sg_batch_set_params(sg_batch* b, const double* stiffness, const d
   CUDA_OK(cudaSetDevice(b->device));
   cudaStream_t s = (cudaStream_t)stream;
   b->has_stiff = stiffness != nullptr; b->has_damp = damping != nullptr; b->has_tdamp = tdamping != nullptr; b->has_objoff = objoff != nullptr;
-  if (stiffness) CUDA_OK(cudaMemcpyAsync(b->p_stiff, stiffness, sizeof(double) * b->W, cudaMemcpyDefault, s));
-  if (damping) CUDA_OK(cudaMemcpyAsync(b->p_damp, damping, sizeof(double) * b->W, cudaMemcpyDefault, s));
-  if (tdamping) CUDA_OK(cudaMemcpyAsync(b->p_tdamp, tdamping, sizeof(double) * b->W, cudaMemcpyDefault, s));
-  if (objoff) CUDA_OK(cudaMemcpyAsync(b->p_objoff, objoff, sizeof(double) * 3 * b->W, cudaMemcpyDefault, s));
+  if (stiffness && stiffness != b->p_stiff) CUDA_OK(cudaMemcpyAsync(b->p_stiff, stiffness, sizeof(double) * b->W, cudaMemcpyDefault, s));
+  if (damping && damping != b->p_damp) CUDA_OK(cudaMemcpyAsync(b->p_damp, damping, sizeof(double) * b->W, cudaMemcpyDefault, s));
+  if (tdamping && tdamping != b->p_tdamp) CUDA_OK(cudaMemcpyAsync(b->p_tdamp, tdamping, sizeof(double) * b->W, cudaMemcpyDefault, s));
+  if (objoff && objoff != b->p_objoff) CUDA_OK(cudaMemcpyAsync(b->p_objoff, objoff, sizeof(double) * 3 * b->W, cudaMemcpyDefault, s));
   return 0;
 }
 
@@ -418,30 +390,6 @@ struct LaunchSpec {
   int* touch_out = nullptr;
 };
 
-#ifndef SG_SIMT_EMU
-template <typename T>
-static int launch_v1(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
-  KArgs<T> K{};
-  K.D = b->D; K.L = b->L;
-  // fold the (possibly updated) model-level masks / stiffness targets into this launch
-  K.D.stiff_tendon0 = b->model->plan.d.stiff_tendon0;
-  K.D.cap_mask = b->model->plan.d.cap_mask; K.D.sph_mask = b->model->plan.d.sph_mask;
-  K.tab = (const T*)b->tab; K.itab = b->itab; K.nworlds = b->W;
-  K.qpos = (T*)b->qpos; K.qvel = (T*)b->qvel; K.warm = (T*)b->warm; K.act = (T*)b->act; K.ctrl = (T*)b->ctrl;
-  K.p_stiff = b->has_stiff ? b->p_stiff : nullptr; K.p_damp = b->has_damp ? b->p_damp : nullptr;
-  K.p_tdamp = b->has_tdamp ? b->p_tdamp : nullptr; K.p_objoff = b->has_objoff ? b->p_objoff : nullptr;
-  K.status = b->status;
-  K.debug_world = b->debug_world; K.debug_out = b->debug_out; K.debug_cap = b->debug_cap;
-  K.nsub = sp.nsub; K.integrate = sp.integrate; K.sens_out = (T*)sp.sens_out; K.touch_out = sp.touch_out;
-  K.rollout = sp.rollout; K.sim_start = sp.sim_start; K.sim_step = sp.sim_step; K.nrows = sp.nrows;
-  K.ctrl_event = b->d_ctrl_event; K.ctrl_value = b->d_ctrl_value;
-  int grid = b->W;
-  if (grid > b->max_ctas) grid = b->max_ctas;   // persistent: each CTA walks worlds w, w+grid, ...
-  sg_step_kernel<T><<<grid, 32, b->L.bytes, s>>>(K);
-  CUDA_OK(cudaGetLastError());
-  return 0;
-}
-#endif
 
 template <typename T>
 static int launch_v2(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
@@ -463,6 +411,7 @@ static int launch_v2(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
   K.prof = b->prof;
   K.nsub = sp.nsub; K.integrate = sp.integrate; K.sens_out = (T*)sp.sens_out; K.touch_out = sp.touch_out;
   K.rollout = sp.rollout; K.sim_start = sp.sim_start; K.sim_step = sp.sim_step; K.nrows = sp.nrows;
+  K.traj_soa = sp.rollout ? b->traj_soa : 0;
   K.ctrl_event = b->d_ctrl_event; K.ctrl_value = b->d_ctrl_value;
   const int cta_worlds = (32 / b->lpw) * b->nwarp;
   int grid = (b->W + cta_worlds - 1) / cta_worlds;
@@ -476,9 +425,6 @@ static int launch_any(sg_batch* b, const LaunchSpec& sp, void* stream) {
   CUDA_OK(cudaSetDevice(b->device));
   cudaStream_t s = (cudaStream_t)stream;
   b->launches++;
-#ifndef SG_SIMT_EMU
-  if (b->kernel == 1) return b->precision == 32 ? launch_v1<float>(b, sp, s) : launch_v1<double>(b, sp, s);
-#endif
   return b->precision == 32 ? launch_v2<float>(b, sp, s) : launch_v2<double>(b, sp, s);
 }
 
@@ -528,14 +474,34 @@ extern "C" int sg_batch_rollout(sg_batch* b, const sg_schedule* sc, void* traj_o
   return launch_any(b, sp, stream);
 }
 
+extern "C" int sg_batch_set_traj_layout(sg_batch* b, int layout) {
+  if (!b) return fail("sg_batch_set_traj_layout: null batch");
+  if (layout != SG_TRAJ_WORLD_MAJOR && layout != SG_TRAJ_SOA) return fail("sg_batch_set_traj_layout: layout must be SG_TRAJ_WORLD_MAJOR or SG_TRAJ_SOA");
+  b->traj_soa = layout == SG_TRAJ_SOA;
+  return 0;
+}
+
 extern "C" int sg_batch_rollout_host(sg_batch* b, const sg_schedule* sc, const double* stiffness_host, void* traj_host,
                                      int* touch_host, int* status_host) {
+  return sg_batch_rollout_host_params(b, sc, stiffness_host, nullptr, nullptr, nullptr, traj_host, touch_host, status_host);
+}
+
+extern "C" int sg_batch_rollout_host_params(sg_batch* b, const sg_schedule* sc, const double* stiffness_host, const double* damping_host,
+                                            const double* tdamping_host, const double* objoff_host, void* traj_host,
+                                            int* touch_host, int* status_host) {
   if (!b || !sc || !traj_host) return fail("sg_batch_rollout_host: null argument");
   CUDA_OK(cudaSetDevice(b->device));
   const size_t tb = b->esize * (size_t)b->W * sc->nrows * b->D.nsd, ub = sizeof(int) * (size_t)b->W * sc->nrows;
   if (tb > b->stage_traj_bytes) { if (b->stage_traj) cudaFree(b->stage_traj); CUDA_OK(cudaMalloc(&b->stage_traj, tb)); b->stage_traj_bytes = tb; }
   if (touch_host && ub > b->stage_touch_bytes) { if (b->stage_touch) cudaFree(b->stage_touch); CUDA_OK(cudaMalloc((void**)&b->stage_touch, ub)); b->stage_touch_bytes = ub; }
-  if (stiffness_host) { int rc = sg_batch_set_params(b, stiffness_host, nullptr, nullptr, nullptr, nullptr); if (rc) return rc; }
+  if (stiffness_host || damping_host || tdamping_host || objoff_host) {
+    // host -> device copies of the per-world parameters (parameters that are not given keep what the batch already holds)
+    int rc = sg_batch_set_params(b, stiffness_host ? stiffness_host : (b->has_stiff ? b->p_stiff : nullptr),
+                                 damping_host ? damping_host : (b->has_damp ? b->p_damp : nullptr),
+                                 tdamping_host ? tdamping_host : (b->has_tdamp ? b->p_tdamp : nullptr),
+                                 objoff_host ? objoff_host : (b->has_objoff ? b->p_objoff : nullptr), nullptr);
+    if (rc) return rc;
+  }
   CUDA_OK(cudaMemsetAsync(b->status, 0, sizeof(int) * b->W, 0));
   int rc = sg_batch_rollout(b, sc, b->stage_traj, touch_host ? b->stage_touch : nullptr, nullptr);
   if (rc) return rc;

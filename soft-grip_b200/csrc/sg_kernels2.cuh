@@ -186,8 +186,9 @@ struct KArgs2 {
   T *qpos, *qvel, *warm, *act, *ctrl;
   const double *p_stiff, *p_damp, *p_tdamp, *p_objoff;
   int* status;
-  T* sens_out;          // step: [W][nsd]; rollout: [W][nrows][nsd]
+  T* sens_out;          // step: [W][nsd]; rollout: [W][nrows][nsd] (traj_soa = 0) or [nrows][nsd][W] (traj_soa = 1)
   int* touch_out;       // step: [W];      rollout: [W][nrows]
+  int traj_soa;         // rollout only: 1 = structure-of-arrays trajectory, world index fastest
   int nsub, integrate;
   int rollout, sim_start, sim_step, nrows;
   const int* ctrl_event;
@@ -1759,7 +1760,17 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
       }
       W.step(K.rollout || K.integrate);
       if (t >= 0 && phase == K.sim_step - 1 && valid) {
-        for (int i = sl; i < D.nsd; i += LPW) K.sens_out[((size_t)w * K.nrows + t) * D.nsd + i] = aux[L.sens + i];
+        // sensor row of this env-step (ref: manenv.py:85 np.copy(sensordata)).  World-major: one world's row is 12
+        // consecutive values, written as 128-bit vectors by the first lanes of the world; SoA: channel-major planes with
+        // the world index fastest, the worlds of a warp / CTA land in the same 32-byte sectors.
+        if (K.traj_soa) {
+          for (int i = sl; i < D.nsd; i += LPW) K.sens_out[((size_t)t * D.nsd + i) * K.nworlds + w] = aux[L.sens + i];
+        } else if ((D.nsd & 3) == 0) {
+          T* row = K.sens_out + ((size_t)w * K.nrows + t) * D.nsd;
+          for (int i = 4 * sl; i < D.nsd; i += 4 * LPW) { T x[4]; ld4(aux + L.sens + i, x); st4(row + i, x[0], x[1], x[2], x[3]); }
+        } else {
+          for (int i = sl; i < D.nsd; i += LPW) K.sens_out[((size_t)w * K.nrows + t) * D.nsd + i] = aux[L.sens + i];
+        }
         if (K.touch_out && sl == 0) K.touch_out[(size_t)w * K.nrows + t] = W.misc(M2_TOUCH);
       }
     }

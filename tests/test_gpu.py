@@ -16,6 +16,15 @@ FP32_TOL = {"q": 5e-5, "v": 3e-3, "qacc": 3e-3, "sens": 1e-2}
 FP64_TOL = 1e-9
 
 
+def _note(text):
+    """Measured values behind the asserted bounds, kept next to the run's other outputs (gpurun_out/ travels back)."""
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "test_gpu_measured.txt"), "a") as f:
+            f.write(text + "\n")
+    print(text)
+
+
 def rel(a, b):
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-12, np.abs(b).max()))
 
@@ -96,7 +105,10 @@ def test_full_horizon_rollout_fp64_vs_oracle(torch_cuda, batched, make_world, k)
     # amplified by make/break events; the drift stays bounded and most rows still agree tightly
     row_err = err.max(axis=1)
     print("k=%g full-horizon drift: max %.2e  median %.2e  rows>1e-5: %d" % (k, row_err.max(), np.median(row_err), int((row_err > 1e-5).sum())))
-    assert row_err.max() < 0.2 and np.median(row_err) < 5e-3
+    _note("fp64 full horizon k=%g: row max %.3e median %.3e rows>1e-5 %d" % (k, row_err.max(), np.median(row_err), int((row_err > 1e-5).sum())))
+    # bounds from the oracle's own sensitivity (tests/test_oracle.py::test_oracle_sensitivity_bounds_the_horizon_tolerances:
+    # a 1e-12 relative perturbation of one parameter moves its own traces by up to 3e-4 of a channel's peak, median 1e-7)
+    assert row_err.max() < 2e-2 and np.median(row_err) < 1e-5
     tg = touch[0].cpu().numpy()
     assert (tg != otouch).sum() <= 4
     q, v, a, qacc = env.get_state()
@@ -104,7 +116,8 @@ def test_full_horizon_rollout_fp64_vs_oracle(torch_cuda, batched, make_world, k)
     # the final state sits after ~700 contact-rich steps of chaotic amplification: the filter state `act` is
     # contact-free and must agree tightly; qpos is held to a drift bound (median over dofs), not to parity
     assert rel(a[0], oa) < 1e-9
-    assert float(np.median(np.abs(q[0] - oq))) / np.abs(oq).max() < 1e-2 and rel(q[0], oq) < 1.0
+    _note("fp64 full horizon k=%g: final qpos median %.3e max %.3e" % (k, float(np.median(np.abs(q[0] - oq))) / np.abs(oq).max(), rel(q[0], oq)))
+    assert float(np.median(np.abs(q[0] - oq))) / np.abs(oq).max() < 1e-5 and rel(q[0], oq) < 5e-2
     if k == 700.0:
         gold = np.load(os.path.join(GOLDEN, "softbox_episode_k700.npz"))
         assert (np.abs(g - gold["rows"]) / scale)[:40].max() < 1e-9
@@ -152,6 +165,49 @@ def test_fp32_drift_and_feature_statistics(torch_cuda, batched):
     for x, y in zip(sa, sb):
         np.testing.assert_allclose(x["mean"], y["mean"], rtol=0.05)
         np.testing.assert_allclose(x["std"], y["std"], rtol=0.15)
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_trace_error_statistic_of_the_bench_against_the_oracle(torch_cuda, batched, prec):
+    """The metric's second half, asserted: the statistic bench.py prints as `sensor_trace_error` (CUDA path vs the fp64
+    ORACLE with the same per-world stiffness / damping / object offset of BASELINE configs[2], relative to each channel's
+    peak) stays inside bench.TRACE_TOLERANCE.  The horizon bound is set by the dynamics, not by the arithmetic: the
+    oracle run against itself from a 1e-6 relative parameter perturbation deviates by a median of up to 3e-2
+    (tests/test_oracle.py::test_oracle_sensitivity_bounds_the_horizon_tolerances)."""
+    torch = torch_cuda
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    args = argparse.Namespace(randomise="all", fixed_stiffness=None, seed=11, damping_range=[100.0, 200.0], offset_range=0.05,
+                              tendon_damping=None)
+    W = 12
+    ids = np.arange(1000, 1000 + W)
+    k, d, off = bench.world_params(args, ids, 0)
+    env = make_env(batched, torch, W=W, dtype=torch.float32 if prec == "f32" else torch.float64)
+    env.set_params(damping=d, object_offset=off)
+    traj, _, st = env.rollout(stiffness=k)
+    assert int((st != 0).sum()) == 0
+    out = bench.sensor_trace_error(args, blob_path("softbox"), traj.double().cpu().numpy(), (k, d, off))
+    _note("trace error %s: %s" % (prec, {kk: vv for kk, vv in out.items() if isinstance(vv, float)}))
+    tol = bench.TRACE_TOLERANCE["fp32" if prec == "f32" else "fp64"]
+    assert "error" not in out, out
+    assert out["settle_rows_max_rel"] <= tol["settle_rows_max_rel"], out
+    assert out["row_median_rel"] <= tol["row_median_rel"], out
+    assert out["row_median_rel_worst_world"] <= 4 * tol["row_median_rel"], out
+
+
+def test_rollout_soa_layout_equals_world_major(torch_cuda, batched):
+    """north-star item (5): the SoA trajectory [T,12,W] (world index fastest) holds the same values as the world-major
+    [W,T,12] sample layout, bit for bit, in both precisions."""
+    torch = torch_cuda
+    sched = batched.default_schedule(2, n_settle=2, n_iter=10, open_close_div=5)
+    for dtype in (torch.float32, torch.float64):
+        env = make_env(batched, torch, W=70, dtype=dtype)
+        k = np.linspace(300, 1400, 70)
+        a, _, _ = env.rollout(schedule=sched, stiffness=k)
+        b, _, _ = env.rollout(schedule=sched, stiffness=k, layout="TCW")
+        assert tuple(b.shape) == (12, 12, 70) and tuple(a.shape) == (70, 12, 12)
+        np.testing.assert_array_equal(b.permute(2, 0, 1).cpu().numpy(), a.cpu().numpy())
 
 
 def test_per_world_parameters_parity(torch_cuda, batched, states, make_world):

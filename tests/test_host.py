@@ -289,18 +289,46 @@ def test_two_rank_dataset_regeneration_with_gloo(tmp_path):
 
 
 def test_bench_sensor_trace_error_against_the_oracle(oracle):
-    """bench.py's informational sensor_trace_error: zero for the oracle's own traces, the perturbation otherwise, and an
-    error key (never an exception) when it cannot run."""
+    """bench.py's sensor_trace_error: zero for the oracle's own traces (with every per-world parameter of BASELINE configs[2]:
+    stiffness, shell damping, object offset), the perturbation otherwise, and an error key (never an exception) when it
+    cannot run."""
     sys.path.insert(0, ROOT)
+    import argparse
     import bench
+    args = argparse.Namespace(tendon_damping=None)
+    info = bench._model_info(blob_path("softbox"))
+    assert info[:3] == (8, 118, 10) and np.allclose(info[3], [1.7, 0.0, 1.0])
     w = oracle.OracleWorld(oracle.OracleModel(open(blob_path("softbox"), "rb").read()))
+    ks, ds, offs = [400.0, 900.0], [120.0, 180.0], [[0.01, -0.02, 0.03], [0.0, 0.04, -0.05]]
     rows = []
-    for k in (400.0, 900.0):
+    for k, d, off in zip(ks, ds, offs):
         w.set_stiffness(k)
+        for dof in range(8, 118):
+            w.set_dof_damping(dof, d)
+        w.set_body_pos(10, np.array([1.7, 0, 1.0]) + off)
         rows.append(w.episode()[0])
-    out = bench.sensor_trace_error(blob_path("softbox"), np.array(rows), [400.0, 900.0])
+    out = bench.sensor_trace_error(args, blob_path("softbox"), np.array(rows), (ks, ds, offs))
     assert out["worlds"] == 2 and out["settle_rows_max_rel"] == 0.0 and out["row_max_rel"] == 0.0
+    plain = bench.sensor_trace_error(args, blob_path("softbox"), np.array(rows), (ks, None, None))
+    assert plain["row_max_rel"] > 1e-3                       # the damping / offset really change the traces
     bumped = np.array(rows) * (1 + 1e-3)
-    out = bench.sensor_trace_error(blob_path("softbox"), bumped, [400.0, 900.0])
+    out = bench.sensor_trace_error(args, blob_path("softbox"), bumped, (ks, ds, offs))
     assert 5e-4 < out["row_max_rel"] < 2e-3 and 0 < out["settle_rows_max_rel"] < 2e-3
-    assert "error" in bench.sensor_trace_error("/nonexistent.sgm", bumped, [400.0, 900.0])
+    assert "error" in bench.sensor_trace_error(args, "/nonexistent.sgm", bumped, (ks, ds, offs))
+
+
+def test_bench_world_params_do_not_depend_on_the_sharding():
+    """BASELINE configs[2] parameters are functions of (seed, step, global world id): any shard draws the same values."""
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    args = argparse.Namespace(randomise="all", fixed_stiffness=None, seed=3, damping_range=[100.0, 200.0], offset_range=0.05)
+    k, d, off = bench.world_params(args, np.arange(0, 64), 5)
+    k2, d2, off2 = bench.world_params(args, np.arange(32, 64), 5)
+    assert np.array_equal(k[32:], k2) and np.array_equal(d[32:], d2) and np.array_equal(off[32:], off2)
+    assert 300 <= k.min() and k.max() <= 1400 and 100 <= d.min() and d.max() <= 200 and np.abs(off).max() <= 0.05 and off.shape == (64, 3)
+    assert not np.array_equal(k, bench.world_params(args, np.arange(0, 64), 6)[0])
+    ks, ds, offs = bench.world_params(args, np.arange(8), 0, "stiffness")
+    assert ds is None and offs is None
+    args.fixed_stiffness = 700.0
+    assert np.all(bench.world_params(args, np.arange(8), 0)[0] == 700.0)

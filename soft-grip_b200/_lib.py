@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsoftgrip.so")
+# SOFTGRIP_LIB: development knob for A/B runs of kernel variants (csrc/Makefile `variant`); never set by tests/ or bench.py
+LIB_PATH = os.environ.get("SOFTGRIP_LIB") or os.path.join(_HERE, "libsoftgrip.so")
 _LIB = None
 
 

@@ -162,7 +162,11 @@ static int upload_tables(sg_batch* b, bool allocate) {
 }
 
 // (precision, lanes-per-world) -> instantiation; the list must match the Makefile's SG_INSTANCES
+#ifdef SG_SMALL_BUILD
+#define SG_K2_CASES(X) X(float, 8) X(double, 8)
+#else
 #define SG_K2_CASES(X) X(float, 4) X(float, 8) X(float, 16) X(float, 32) X(double, 4) X(double, 8) X(double, 16) X(double, 32)
+#endif
 static int k2_dispatch_configure(int precision, int lpw, int block, size_t smem, int* per_sm) {
 #define X(T, N) if ((precision == 32) == (sizeof(T) == 4) && lpw == N) return k2_configure<T, N>(block, smem, per_sm);
   SG_K2_CASES(X)
@@ -244,6 +248,17 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       if (b->smem2 <= prop.sharedMemPerBlockOptin || b->nwarp == 1) break;
       b->nwarp -= 1;                       // largest CTA that fits
     }
+#if SG_SLOT8
+    {
+      // the 8-byte step slots and the unit-coefficient tendon row assume what every MuJoCo composite has: one element mass
+      // and coefficient 1 for every slider of the volume tendon
+      const Plan& P = m->plan;
+      bool uniform = true;
+      for (int e = 0; e < b->D.ns; e++)
+        if (P.tab[b->D.o_sl_m + e] != P.tab[b->D.o_sl_m] || P.tab[b->D.o_sl_tc + e] != 1.0) uniform = false;
+      if (!uniform) { sg_batch_destroy(b); return fail("sg_batch_create: shell elements with different masses or tendon coefficients are not supported by this build (SG_SLOT8)"); }
+    }
+#endif
     if (b->D.nrow >= 0xfff || b->D.ns >= 0xfff) { sg_batch_destroy(b); return fail("sg_batch_create: too many equality rows or shell joints for the packed warm-start table"); }
     if (b->L2.cand_cap < 16) { sg_batch_destroy(b); return fail("sg_batch_create: the collision scratch (the equality-row pairs of one world) is too small for this model"); }
     if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) != 0) { sg_batch_destroy(b); return fail("SOFTGRIP_TEAM: team mode was removed from kernel 2 (measured slower, profiles/r01b_*, r01g_*)"); } }

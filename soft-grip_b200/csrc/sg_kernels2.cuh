@@ -34,6 +34,16 @@
 
 namespace sg {
 
+// software-pipelined contact records on the fp32 fast path (see chain_phase)
+#ifndef SG_PIPE_REC
+#define SG_PIPE_REC 1
+#endif
+
+// 8-byte step slots / unit tendon coefficients for shells with uniform element mass (checked by the host, sg_api.cu)
+#ifndef SG_SLOT8
+#define SG_SLOT8 1
+#endif
+
 #ifndef SG_ST_CON_FULL_BIT
 #define SG_ST_CON_FULL_BIT 2
 #define SG_ST_UNSUPPORTED_BIT 8
@@ -134,7 +144,7 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw
   }
   // CTA-shared tables: step slots | tendon coefficients, coefficient / mass, 1 / mass (ns each) | slider axes (3 ns) |
   // collider table | broadphase runs | row -> sliders
-  L.smem_tables = (int)(((size_t)(D.nstep + 1) * lpw * (8 + 2 * sizeof(T)) + (6 * (size_t)D.ns + (size_t)MAXCOLL * CO_STRIDE) * sizeof(T) +
+  L.smem_tables = (int)(((size_t)(D.nstep + 1) * lpw * (SG_SLOT8 ? 8 : 8 + 2 * sizeof(T)) + (6 * (size_t)D.ns + (size_t)MAXCOLL * CO_STRIDE) * sizeof(T) +
                          (4 * (size_t)D.nrun + (size_t)D.nrow) * sizeof(int) + 127) & ~(size_t)127);
   return L;
 }
@@ -379,9 +389,15 @@ template <> __device__ __forceinline__ void ldg2<double>(const double* p, double
 static_assert(MAXCD == 4, "finger chain blocks are loaded as 4-vectors");
 
 // one slot of the level-sweep step tables in shared memory (host encoding: sg_plan.hpp build_step_tables)
+#if SG_SLOT8
+// uniform shell (every slider has the same mass and tendon coefficient 1, as every MuJoCo composite has): the slot is the
+// 8-byte descriptor alone -- one 64-bit shared-memory load, two wavefronts per warp instead of four
+template <typename T> struct alignas(8) Slot { unsigned x, y; };
+#else
 template <typename T> struct Slot;
 template <> struct alignas(16) Slot<float> { unsigned x, y; float iw1, iw2; };      // one 128-bit shared-memory load
 template <> struct alignas(8) Slot<double> { unsigned x, y; double iw1, iw2; };
+#endif
 template <typename T> __device__ __forceinline__ Slot<T> ld_slot(const Slot<T>* p) { return *p; }
 
 // ---------------------------------------------------------------------------------------------
@@ -1289,16 +1305,24 @@ struct World2 {
     f1 = vv[0]; f2 = vv[1];
   }
   // one elliptic contact block (mj_solPGS inner body, dim 3) on the lane that owns its chain
+  // the 32 words of one contact record in registers
+  struct Rec { T jg[12], w1[4], w2[4], Aw[8], w3[4]; };
+  __device__ __forceinline__ void load_rec(Rec& x, const T* r) const {
+    ld4(r + CR_JG, x.jg); ld4(r + CR_JG + 4, x.jg + 4); ld4(r + CR_JG + 8, x.jg + 8);
+    ld4(r + CR_NS, x.w1);          // ns0 ns1 ns2 iwe
+    ld4(r + CR_AREF, x.w2);        // aref0 aref1 aref2 R0
+    ld4(r + CR_A, x.Aw); ld4(r + CR_A + 4, x.Aw + 4);   // A00 A01 A02 A11 | A12 A22 R1 e
+    ld4(r + CR_F, x.w3);           // f0 f1 f2, friction multiplier of the previous sweep
+  }
   __device__ __forceinline__ T contact_block(T* r, int e, T* ag, bool has_chain, const T* mv) {
+    Rec x; load_rec(x, r);
+    return contact_block(x, r, e, ag, has_chain, mv);
+  }
+  __device__ __forceinline__ T contact_block(const Rec& x, T* r, int e, T* ag, bool has_chain, const T* mv) {
     const int nfd = D.nfd;
     T ae = 0;
     if (e >= 0) ae = a()[nfd + e];
-    T jg[12], w1[4], w2[4], w3[4];
-    ld4(r + CR_JG, jg); ld4(r + CR_JG + 4, jg + 4); ld4(r + CR_JG + 8, jg + 8);
-    ld4(r + CR_NS, w1);          // ns0 ns1 ns2 iwe
-    ld4(r + CR_AREF, w2);        // aref0 aref1 aref2 R0
-    T Aw[8]; ld4(r + CR_A, Aw); ld4(r + CR_A + 4, Aw + 4);   // A00 A01 A02 A11 | A12 A22 R1 e
-    ld4(r + CR_F, w3);           // f0 f1 f2 -
+    const T* jg = x.jg; const T* w1 = x.w1; const T* w2 = x.w2; const T* Aw = x.Aw; const T* w3 = x.w3;
     const T A00 = Aw[0], A01 = Aw[1], A02 = Aw[2], A11 = Aw[3], A12 = Aw[4], A22 = Aw[5];
     const T R0 = w2[3], R1 = Aw[6];
     const T old0 = w3[0], old1 = w3[1], old2 = w3[2];
@@ -1401,6 +1425,11 @@ struct World2 {
     if (cnt > 1) entB = order[1];
     if (cnt > 2) entC = order[2];
     const int ent0 = entA;
+#if SG_PIPE_REC
+    Rec cur;
+    if (sizeof(T) == 4) { if (cnt > 0) load_rec(cur, crec(entA & 0xff)); }
+    else
+#endif
     if (cnt > 1 && !L.aux_in_smem) prefetch_l1(crec(entB & 0xff));
     if (cs.chain_lane && !done) {
 #pragma unroll
@@ -1424,6 +1453,28 @@ struct World2 {
       }
     }
     int k = 0;
+#if SG_PIPE_REC
+    if (sizeof(T) == 4) {
+      // fp32 fast path: the record of the lane's NEXT block is loaded into registers while the current block runs (32 words
+      // in flight per lane), so a block never waits for the L2 round trip of its own record; the first record of a sweep
+      // was requested before the limit rows above
+      for (int t = 1; t <= tmaxw; t++) {
+        if (k < cnt && ((entA >> 8) & 0xff) == t) {
+          T* r = crec(entA & 0xff);
+          const int e = (entA >> 16) - 1;
+          k++;
+          entA = entB; entB = entC;
+          const bool more = k < cnt;
+          Rec nxt;
+          if (more) load_rec(nxt, crec(entA & 0xff));
+          if (k + 2 < cnt) entC = order[k + 2];
+          impr -= contact_block(cur, r, e, cs.ag, cs.chain_lane, cs.mv);
+          if (more) cur = nxt;
+        }
+        __syncwarp();
+      }
+    } else
+#endif
     for (int t = 1; t <= tmaxw; t++) {
       if (k < cnt && ((entA >> 8) & 0xff) == t) {
         T* r = crec(entA & 0xff);
@@ -1460,6 +1511,9 @@ struct World2 {
     char* avb = reinterpret_cast<char*>(a() + D.nfd);
     char* rwb = reinterpret_cast<char*>(hot);     // Layout2::row2 == 0 (make_layout2)
     T acc = 0;                                   // sum of res * dl = -2 * cost improvement
+#if SG_SLOT8
+    const T iwu = stim[0];                       // 1 / element mass, the same for every slider
+#endif
     // one row per lane per step, a warp barrier where the schedule asks for one.  The next step's slot is fetched
     // before the barrier so that its latency overlaps this step's arithmetic.
     Slot<T> sn = ld_slot<T>(slots);
@@ -1479,7 +1533,11 @@ struct World2 {
       if (GATED) n = done ? T(0) : n;
       const T dl = res * n;
       acc += dl * res;
+#if SG_SLOT8
+      a1 += iwu * dl; a2 -= (has2 ? iwu : T(0)) * dl;        // fix rows have no second slider
+#else
       a1 += sc.iw1 * dl; a2 -= sc.iw2 * dl;
+#endif
       T un = a2 - a1;
       if (GATED) un = done ? u : un;
       if (valid) { *pr = un; *pa1 = a1; }
@@ -1499,13 +1557,24 @@ struct World2 {
     // volume-tendon row: dense over the shell, sub-warp shuffle reduction
     {
       T s = 0;
+#if SG_SLOT8
+#pragma unroll 4
+      for (int e = sl; e < ns; e += LPW) s += av[e];            // tendon coefficients are all 1
+#else
       for (int e = sl; e < ns; e += LPW) s += stc[e] * av[e];
+#endif
       s = gsum(s);
       const T res = s + tn.u;
       const T dl = done ? T(0) : res * tn.nA;
       if (sl == 0) impr -= T(0.5) * dl * res;
       tn.u += tn.R * dl;
+#if SG_SLOT8
+      const T da = stim[0] * dl;
+#pragma unroll 4
+      for (int e = sl; e < ns; e += LPW) av[e] += da;
+#else
       for (int e = sl; e < ns; e += LPW) av[e] += stciw[e] * dl;
+#endif
       __syncwarp();
     }
     return impr;
@@ -1714,7 +1783,9 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
     const int nslot = (D.nstep + 1) * LPW;
     for (int i = threadIdx.x; i < nslot; i += blockDim.x) {
       Slot<T> t; t.x = (unsigned)K.itab[D.io_step_d + 2 * i]; t.y = (unsigned)K.itab[D.io_step_d + 2 * i + 1];
+#if !SG_SLOT8
       t.iw1 = K.tab[D.o_step_iw + 2 * i]; t.iw2 = K.tab[D.o_step_iw + 2 * i + 1];
+#endif
       ss[i] = t;
     }
     T* tc = reinterpret_cast<T*>(smem_raw + (size_t)nslot * sizeof(Slot<T>));

@@ -36,7 +36,8 @@ for cfg in cfgs:
         for rep in range(3):
             torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            traj, kk, st = env.rollout(schedule=(ev, val))
+            # u1: every world gets the same stiffness (how much do unequal worlds in a warp / CTA cost?)
+            traj, kk, st = env.rollout(schedule=(ev, val), stiffness=([700.0] * W if parts.get("u", 0) else None))
             e1.record(); torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1) / 1e3)
         t = traj.double().cpu().numpy()

@@ -182,8 +182,17 @@ static int k2_dispatch_launch(int lpw, const KArgs2<T>& K, int grid, int block, 
 }
 
 extern "C" void sg_batch_destroy(sg_batch* b);
+static int batch_create_body(const sg_model* m, int nworlds, int device, int precision, sg_batch*& b);
 extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int precision, sg_batch** out) {
   if (!m || !out) return fail("sg_batch_create: null argument");
+  *out = nullptr;
+  sg_batch* b = nullptr;
+  const int rc = batch_create_body(m, nworlds, device, precision, b);
+  if (rc) { if (b) sg_batch_destroy(b); return rc; }      // every failure path frees the handle and what it already owns
+  *out = b;
+  return 0;
+}
+static int batch_create_body(const sg_model* m, int nworlds, int device, int precision, sg_batch*& b) {
   if (nworlds < 1) return fail("sg_batch_create: nworlds must be >= 1");
   if (precision != 32 && precision != 64) return fail("sg_batch_create: precision must be 32 or 64");
   int ndev = 0;
@@ -191,7 +200,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   if (e != cudaSuccess || ndev == 0) return fail("sg_batch_create: no CUDA device available (libsoftgrip has no CPU path)");
   if (device < 0 || device >= ndev) return fail("sg_batch_create: bad device index");
   CUDA_OK(cudaSetDevice(device));
-  sg_batch* b = new sg_batch();
+  b = new sg_batch();
   b->model = m; b->W = nworlds; b->device = device; b->precision = precision;
   b->esize = precision == 32 ? 4 : 8;
   b->D = m->plan.d;
@@ -207,11 +216,10 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   if (const char* e = std::getenv("SOFTGRIP_QV_SMEM")) qv_in_smem = std::atoi(e);
   if (const char* e = std::getenv("SOFTGRIP_AUX_SMEM")) aux_in_smem = std::atoi(e);
   if (b->kernel == 2 && (aux_in_smem || qv_in_smem)) {
-    delete b;
     return fail("SOFTGRIP_AUX_SMEM / SOFTGRIP_QV_SMEM: the shared-memory placement of the once-per-step data was removed from kernel 2 (measured slower; a single address space lets the compiler emit global loads)");
   }
-  if (b->nwarp < 1 || b->nwarp > SG_MAX_WARPS) { delete b; return fail("SOFTGRIP_NW must be 1..16"); }
-  if (b->lpw != 4 && b->lpw != 8 && b->lpw != 16 && b->lpw != 32) { delete b; return fail("SOFTGRIP_LPW must be 4, 8, 16 or 32"); }
+  if (b->nwarp < 1 || b->nwarp > SG_MAX_WARPS) { return fail("SOFTGRIP_NW must be 1..16"); }
+  if (b->lpw != 4 && b->lpw != 8 && b->lpw != 16 && b->lpw != 32) { return fail("SOFTGRIP_LPW must be 4, 8, 16 or 32"); }
   if (b->kernel == 2) {
     const Plan& P = m->plan;
     build_step_tables(b->D, P.tab, P.itab, b->lpw, (int)b->esize, b->step_d, b->step_iw, b->row_perm, std::getenv("SOFTGRIP_NO_BANK_SCHEDULE") == nullptr);
@@ -220,7 +228,7 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
     b->D.io_step_d = (int)((P.itab.size() + 3) / 4 * 4);
   }
   int rc = upload_tables(b, true);
-  if (rc) { sg_batch_destroy(b); return rc; }
+  if (rc) { return rc; }
   const size_t nv = b->D.nv, nu = b->D.nu > 0 ? b->D.nu : 1;
   CUDA_OK(cudaMalloc(&b->qpos, b->esize * nv * nworlds));
   CUDA_OK(cudaMalloc(&b->qvel, b->esize * nv * nworlds));
@@ -238,16 +246,36 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
   int per_sm = 0;
   if (b->kernel == 2) {
     const int wpw = 32 / b->lpw;
-    if (!std::getenv("SOFTGRIP_NW")) {
-      // small batches: smaller CTAs, so that every SM gets work
-      while (b->nwarp > 1 && (nworlds + b->nwarp * wpw - 1) / (b->nwarp * wpw) < prop.multiProcessorCount) b->nwarp /= 2;
+    // Launch geometry.  Warps never exchange data, and the kernel is bound by the dependent-issue latency of each warp
+    // (profiles/r02c_phase_scan.txt: 1.05e6 cycles per warp-step with one warp per SM, 1.58e6 with sixteen), so what
+    // counts is (i) every SM busy and (ii) as few passes over the batch list as possible.  Among the CTA sizes that fit,
+    // take the one with the smallest modelled time  passes * (1 + 0.035 (resident warps - 1));  several small CTAs per SM
+    // are penalised: their warps do not share the per-step barrier, which costs instruction-cache locality
+    // (profiles/r01s_*).  E.g. 8 192 worlds (BASELINE configs[2] on 8 GPUs) run as 147 CTAs of 56 worlds instead of
+    // 128 CTAs of 64 on 148 SMs.
+    const bool nw_forced = std::getenv("SOFTGRIP_NW") != nullptr;
+    int best_nw = 0; double best_cost = 0;
+    for (int nw = nw_forced ? b->nwarp : SG_MAX_WARPS; nw >= (nw_forced ? b->nwarp : 1); nw--) {
+      const Layout2 L = precision == 32 ? make_layout2<float>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem) : make_layout2<double>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem);
+      const size_t smem = (size_t)L.smem_tables + (size_t)L.smem_stride * wpw * nw;
+      if (smem > prop.sharedMemPerBlockOptin) continue;
+      int ps = 0;
+      const int e = k2_dispatch_configure(precision, b->lpw, 32 * nw, smem, &ps);
+      if (e == -12345) { return fail("SOFTGRIP_LPW: this lanes-per-world value is not compiled in"); }
+      if (e) { return fail(std::string("kernel configuration failed: ") + cudaGetErrorString((cudaError_t)e)); }
+      if (ps < 1) continue;
+      const long ctas = ((long)nworlds + nw * wpw - 1) / (nw * wpw);
+      const long resident = (long)ps * prop.multiProcessorCount;
+      const long passes = (ctas + resident - 1) / resident;
+      const long per_sm_used = ctas < resident ? (ctas + prop.multiProcessorCount - 1) / prop.multiProcessorCount : ps;
+      double cost = (double)passes * (1.0 + 0.035 * (double)(per_sm_used * nw - 1));
+      if (per_sm_used > 1) cost *= 1.3;
+      if (!best_nw || cost < best_cost * (1.0 - 1e-9)) { best_nw = nw; best_cost = cost; }
     }
-    for (;;) {
-      b->L2 = precision == 32 ? make_layout2<float>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem) : make_layout2<double>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem);
-      b->smem2 = (size_t)b->L2.smem_tables + (size_t)b->L2.smem_stride * wpw * b->nwarp;
-      if (b->smem2 <= prop.sharedMemPerBlockOptin || b->nwarp == 1) break;
-      b->nwarp -= 1;                       // largest CTA that fits
-    }
+    if (!best_nw) { return fail("sg_batch_create: worlds of one warp do not fit in shared memory (use more lanes per world)"); }
+    b->nwarp = best_nw;
+    b->L2 = precision == 32 ? make_layout2<float>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem) : make_layout2<double>(b->D, aux_in_smem, wpw, b->lpw, qv_in_smem);
+    b->smem2 = (size_t)b->L2.smem_tables + (size_t)b->L2.smem_stride * wpw * b->nwarp;
 #if SG_SLOT8
     {
       // the 8-byte step slots and the unit-coefficient tendon row assume what every MuJoCo composite has: one element mass
@@ -256,16 +284,16 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       bool uniform = true;
       for (int e = 0; e < b->D.ns; e++)
         if (P.tab[b->D.o_sl_m + e] != P.tab[b->D.o_sl_m] || P.tab[b->D.o_sl_tc + e] != 1.0) uniform = false;
-      if (!uniform) { sg_batch_destroy(b); return fail("sg_batch_create: shell elements with different masses or tendon coefficients are not supported by this build (SG_SLOT8)"); }
+      if (!uniform) { return fail("sg_batch_create: shell elements with different masses or tendon coefficients are not supported by this build (SG_SLOT8)"); }
     }
 #endif
-    if (b->D.nrow >= 0xfff || b->D.ns >= 0xfff) { sg_batch_destroy(b); return fail("sg_batch_create: too many equality rows or shell joints for the packed warm-start table"); }
-    if (b->L2.cand_cap < 16) { sg_batch_destroy(b); return fail("sg_batch_create: the collision scratch (the equality-row pairs of one world) is too small for this model"); }
-    if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) != 0) { sg_batch_destroy(b); return fail("SOFTGRIP_TEAM: team mode was removed from kernel 2 (measured slower, profiles/r01b_*, r01g_*)"); } }
-    if (b->smem2 > prop.sharedMemPerBlockOptin) { sg_batch_destroy(b); return fail("sg_batch_create: worlds of one warp do not fit in shared memory (use more lanes per world or SOFTGRIP_AUX_SMEM=0)"); }
+    if (b->D.nrow >= 0xfff || b->D.ns >= 0xfff) { return fail("sg_batch_create: too many equality rows or shell joints for the packed warm-start table"); }
+    if (b->L2.cand_cap < 16) { return fail("sg_batch_create: the collision scratch (the equality-row pairs of one world) is too small for this model"); }
+    if (const char* e = std::getenv("SOFTGRIP_TEAM")) { if (std::atoi(e) != 0) { return fail("SOFTGRIP_TEAM: team mode was removed from kernel 2 (measured slower, profiles/r01b_*, r01g_*)"); } }
+    if (b->smem2 > prop.sharedMemPerBlockOptin) { return fail("sg_batch_create: worlds of one warp do not fit in shared memory (use more lanes per world or SOFTGRIP_AUX_SMEM=0)"); }
     int e = k2_dispatch_configure(precision, b->lpw, 32 * b->nwarp, b->smem2, &per_sm);
-    if (e == -12345) { sg_batch_destroy(b); return fail("SOFTGRIP_LPW: this lanes-per-world value is not compiled in"); }
-    if (e) { sg_batch_destroy(b); return fail(std::string("kernel configuration failed: ") + cudaGetErrorString((cudaError_t)e)); }
+    if (e == -12345) { return fail("SOFTGRIP_LPW: this lanes-per-world value is not compiled in"); }
+    if (e) { return fail(std::string("kernel configuration failed: ") + cudaGetErrorString((cudaError_t)e)); }
     if (per_sm < 1) per_sm = 1;
     b->max_ctas = per_sm * prop.multiProcessorCount; b->per_sm = per_sm;
     const int cta_worlds = wpw * b->nwarp;
@@ -283,7 +311,6 @@ extern "C" int sg_batch_create(const sg_model* m, int nworlds, int device, int p
       CUDA_OK(cudaMemset(b->scratch, 0, (size_t)slots * cta_worlds * (size_t)b->L2.gs_stride));
     }
   }
-  *out = b;
   return sg_batch_reset(b, nullptr);
 }
 

@@ -34,9 +34,29 @@
 
 namespace sg {
 
-// software-pipelined contact records on the fp32 fast path (see chain_phase)
+// software-pipelined contact records on the fp32 fast path (see chain_phase).  Measured slower (profiles/r02b_sweep.txt:
+// 1.006e7 against 1.141e7 world-steps/s): the second record costs 32 registers, the kernel spills 1.1 KB and every block
+// pays 32 register moves.  Off; kept as an A/B switch.
 #ifndef SG_PIPE_REC
-#define SG_PIPE_REC 1
+#define SG_PIPE_REC 0
+#endif
+
+// lean chain phase: record pointers from one byte base kept in registers, unconditional force updates, no run-time
+// placement tests (the once-per-step data always lives in the global scratch)
+#ifndef SG_LEAN_CHAIN
+#define SG_LEAN_CHAIN 1
+#endif
+
+// broadphase: runs of the pair list whose collider(s) cannot reach the bounding box of the capsule centres are skipped
+#ifndef SG_BP_CULL
+#define SG_BP_CULL 1
+#endif
+
+// contact block without data-dependent branches outside the friction solve (selects instead), the same code for chain and
+// static lanes (a static contact has a zero finger Jacobian and a zero chain acceleration), slider-less contacts go
+// through the dummy slider: two large basic blocks around the Newton loop, which the scheduler can overlap freely
+#ifndef SG_BF_BLOCK
+#define SG_BF_BLOCK 1
 #endif
 
 // 8-byte step slots / unit tendon coefficients for shells with uniform element mass (checked by the host, sg_api.cu)
@@ -328,8 +348,11 @@ __device__ __forceinline__ void friction_fast(float& f1, float& f2, float& la_io
   // (the tangent of the convex function lands left of the root, from where the iterates rise monotonically)
   float la = fmaxf(lo, la_io);
   float w1 = 0, w2 = 0, rdet = 0, N2 = 0;
+#ifndef SG_X_FRIC_MAXIT
+#define SG_X_FRIC_MAXIT 8          // (timing experiments only: a lower cap changes the results)
+#endif
 #pragma unroll 1
-  for (int iter = 0; iter < 8; iter++) {
+  for (int iter = 0; iter < SG_X_FRIC_MAXIT; iter++) {
     const float c11 = a22 + la, c22 = a11 + la;
     const float det = c11 * c22 - a12 * a12;
     w1 = c11 * b1 - a12 * b2; w2 = c22 * b2 - a12 * b1;
@@ -867,6 +890,9 @@ struct World2 {
   __device__ void collide() {
     const bool dbg = valid && (w == K.debug_world);
     // ---- capsule centres into the scratch (the sliders only move along their axes) ----
+#if SG_BP_CULL
+    T blo[3] = {T(SG_MAXVAL), T(SG_MAXVAL), T(SG_MAXVAL)}, bhi[3] = {-T(SG_MAXVAL), -T(SG_MAXVAL), -T(SG_MAXVAL)};
+#endif
     {
       const T* __restrict__ qsl = q() + D.nfd;
       const T* __restrict__ c0 = tab(D.o_sl_cap0);
@@ -875,8 +901,25 @@ struct World2 {
       for (int e = sl; e < D.ns; e += LPW) {
         const T qe = qsl[e];
 #pragma unroll
-        for (int k = 0; k < 3; k++) cen[3 * e + k] = off[k] + c0[3 * e + k] + sax[3 * e + k] * qe;
+        for (int k = 0; k < 3; k++) {
+          const T ck = off[k] + c0[3 * e + k] + sax[3 * e + k] * qe;
+          cen[3 * e + k] = ck;
+#if SG_BP_CULL
+          blo[k] = ck < blo[k] ? ck : blo[k]; bhi[k] = ck > bhi[k] ? ck : bhi[k];     // a NaN centre leaves the bounds alone
+          if (!(ck == ck)) { blo[k] = -T(SG_MAXVAL); bhi[k] = T(SG_MAXVAL); }          // ... so it opens them explicitly
+#endif
+        }
       }
+#if SG_BP_CULL
+      // bounding box of the capsule centres of this world (sub-warp min / max)
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int o = LPW / 2; o > 0; o >>= 1) {
+          const T l2 = __shfl_xor_sync(FULLMASK, blo[k], o), h2 = __shfl_xor_sync(FULLMASK, bhi[k], o);
+          blo[k] = l2 < blo[k] ? l2 : blo[k]; bhi[k] = h2 > bhi[k] ? h2 : bhi[k];
+        }
+#endif
       __syncwarp();
     }
     // ---- broadphase: bounding spheres, candidates compacted in pair order.  The pair list is walked by runs
@@ -891,6 +934,34 @@ struct World2 {
       int pa = a0;
       const T* co = scoll + pa * CO_STRIDE;
       T c1[3], rot1[9];
+#if SG_BP_CULL
+      if (pt == PAIR_PLANE_CAPSULE || pt == PAIR_BOX_CAPSULE) {
+        // Can any capsule of the shell pass the bounding-sphere test against a collider of this run?  The test below is
+        // |centre - c1|^2 <= (rb1 + rb2)^2 (plane: signed distance <= rb2); every centre lies in [blo, bhi], so a collider
+        // whose distance to that box exceeds the bound (with a relative margin for rounding) rejects every pair of the run.
+        bool reach = false;
+        const T rb2 = C.cap_r + C.cap_hl;
+        for (int i = 0; i < na; i++) {
+          const T* ci = scoll + (a0 + i) * CO_STRIDE;
+          T cc[3], rr[9];
+          collider_pose(a0 + i, cc, rr);
+          if ((int)ci[CO_TYPE] == GEOM_PLANE) {
+            T dmin = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { const T n = rr[3 * k + 2], a = n * (blo[k] - cc[k]), b = n * (bhi[k] - cc[k]); dmin += a < b ? a : b; }
+            if (!(dmin > rb2 + T(1e-4) * (tabs(dmin) + rb2))) reach = true;
+          } else {
+            T d2 = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { const T x = cc[k] < blo[k] ? blo[k] - cc[k] : (cc[k] > bhi[k] ? cc[k] - bhi[k] : T(0)); d2 += x * x; }
+            const T bound = ci[CO_RBOUND] + rb2;
+            if (!(d2 > bound * bound * T(1.0001))) reach = true;
+          }
+        }
+        // the loop below is full of warp collectives (the worlds of a warp ballot together): warp-uniform decision
+        if (!__any_sync(FULLMASK, reach)) continue;
+      }
+#endif
       if (one) collider_pose(pa, c1, rot1);
       for (int base = 0; base < total; base += LPW) {
         const int j = base + sl;
@@ -1318,6 +1389,70 @@ struct World2 {
     Rec x; load_rec(x, r);
     return contact_block(x, r, e, ag, has_chain, mv);
   }
+#if SG_BF_BLOCK
+  __device__ __forceinline__ T contact_block(const Rec& x, T* r, int e, T* ag, bool has_chain, const T* mv) {
+    (void)has_chain;
+    // a contact without a slider (centre sphere) reads and writes the dummy slider: its ns and 1/m words are zero
+    T* const pae = a() + D.nfd + (e >= 0 ? e : D.ns);
+    const T ae = *pae;
+    const T* jg = x.jg; const T* w1 = x.w1; const T* w2 = x.w2; const T* Aw = x.Aw; const T* w3 = x.w3;
+    const T A00 = Aw[0], A01 = Aw[1], A02 = Aw[2], A11 = Aw[3], A12 = Aw[4], A22 = Aw[5];
+    const T R0 = w2[3], R1 = Aw[6];
+    const T old0 = w3[0], old1 = w3[1], old2 = w3[2];
+    T la = w3[3];
+    T res[3];
+    const T Rr[3] = {R0, R1, R1};
+    const T fo[3] = {old0, old1, old2};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      T s = Rr[k] * fo[k] - w2[k];
+#pragma unroll
+      for (int jj = 0; jj < MAXCD; jj++) s += jg[4 * k + jj] * ag[jj];
+      res[k] = s + w1[k] * ae;
+    }
+    // normal force: plain update of an inactive contact, ray update of an active one (mj_solPGS)
+    const bool active = !(old0 < T(SG_MINVAL));
+    const T x0 = A00 * old0 + A01 * old1 + A02 * old2, x1 = A01 * old0 + A11 * old1 + A12 * old2, x2 = A02 * old0 + A12 * old1 + A22 * old2;
+    const T denom = old0 * x0 + old1 * x1 + old2 * x2;
+    const bool okden = denom >= T(SG_MINVAL);
+    T xr = -tdiv(old0 * res[0] + old1 * res[1] + old2 * res[2], okden ? denom : T(1));
+    if (old0 + xr * old0 < T(0)) xr = T(-1);
+    xr = okden ? xr : T(0);
+    T f0n = old0 - tdiv(res[0], A00);
+    f0n = f0n < T(0) ? T(0) : f0n;
+    T f0 = active ? old0 + xr * old0 : f0n;
+    T f1 = active ? old1 + xr * old1 : T(0);
+    T f2 = active ? old2 + xr * old2 : T(0);
+    // friction update with the normal force fixed
+    {
+      T bc[2];
+      bc[0] = res[1] - (A11 * old1 + A12 * old2) + A01 * (f0 - old0);
+      bc[1] = res[2] - (A12 * old1 + A22 * old2) + A02 * (f0 - old0);
+      if (f0 < T(SG_MINVAL)) { f1 = 0; f2 = 0; la = 0; }
+      else friction(f1, f2, la, A11, A12, A22, bc, C.con_fr, f0);
+    }
+    // cost change, revert if positive
+    T d0f = f0 - old0, d1f = f1 - old1, d2f = f2 - old2;
+    T change = T(0.5) * (d0f * (A00 * d0f + A01 * d1f + A02 * d2f) + d1f * (A01 * d0f + A11 * d1f + A12 * d2f) + d2f * (A02 * d0f + A12 * d1f + A22 * d2f))
+             + d0f * res[0] + d1f * res[1] + d2f * res[2];
+    const bool revert = change > T(1e-10);
+    f0 = revert ? old0 : f0; f1 = revert ? old1 : f1; f2 = revert ? old2 : f2;
+    d0f = revert ? T(0) : d0f; d1f = revert ? T(0) : d1f; d2f = revert ? T(0) : d2f;
+    change = revert ? T(0) : change;
+    st4(r + CR_F, f0, f1, f2, la);
+    // qacc += M^-1 J^T delta: unconditionally (a zero change adds exact zeros)
+    *pae = ae + (w1[0] * d0f + w1[1] * d1f + w1[2] * d2f) * w1[3];
+    T gv[MAXCD];
+#pragma unroll
+    for (int jj = 0; jj < MAXCD; jj++) gv[jj] = jg[jj] * d0f + jg[4 + jj] * d1f + jg[8 + jj] * d2f;
+#pragma unroll
+    for (int ii = 0; ii < MAXCD; ii++) {
+      T m4[4]; ld4(mv + 4 * ii, m4);
+      ag[ii] += m4[0] * gv[0] + m4[1] * gv[1] + m4[2] * gv[2] + m4[3] * gv[3];
+    }
+    return change;
+  }
+#else
   __device__ __forceinline__ T contact_block(const Rec& x, T* r, int e, T* ag, bool has_chain, const T* mv) {
     const int nfd = D.nfd;
     T ae = 0;
@@ -1368,8 +1503,8 @@ struct World2 {
              + d0f * res[0] + d1f * res[1] + d2f * res[2];
     if (change > T(1e-10)) { f0 = old0; f1 = old1; f2 = old2; d0f = d1f = d2f = 0; change = 0; }
     st4(r + CR_F, f0, f1, f2, la);
-    // qacc += M^-1 J^T delta
-    if (d0f != T(0) || d1f != T(0) || d2f != T(0)) {
+    // qacc += M^-1 J^T delta (lean: unconditionally -- a zero change adds exact zeros)
+    if (SG_LEAN_CHAIN || d0f != T(0) || d1f != T(0) || d2f != T(0)) {
       if (e >= 0) a()[nfd + e] = ae + (w1[0] * d0f + w1[1] * d1f + w1[2] * d2f) * w1[3];
       if (has_chain) {
         T gv[MAXCD];
@@ -1384,6 +1519,8 @@ struct World2 {
     }
     return change;
   }
+
+#endif
 
   // ---- limit / contact rows: swept by the lane that owns the finger chain (plus a share of the static contacts) ----
   struct ChainState {
@@ -1475,6 +1612,25 @@ struct World2 {
       }
     } else
 #endif
+#if SG_LEAN_CHAIN
+    {
+      // one byte base for the records of this world; an entry's record is base + index * 128 (CR_STRIDE reals)
+      unsigned char* const recb = reinterpret_cast<unsigned char*>(aux + L.crec);
+      constexpr unsigned RB = CR_STRIDE * sizeof(T);
+      for (int t = 1; t <= tmaxw; t++) {
+        if (k < cnt && ((entA >> 8) & 0xff) == t) {
+          T* r = reinterpret_cast<T*>(recb + (size_t)((unsigned)(entA & 0xff) * RB));
+          const int e = (entA >> 16) - 1;
+          k++;
+          if (k + 1 < cnt) prefetch_l1(recb + (size_t)((unsigned)(entC & 0xff) * RB));   // two blocks ahead, as the entries
+          const int entD = (k + 2 < cnt) ? order[k + 2] : 0;
+          impr -= contact_block(r, e, cs.ag, cs.chain_lane, cs.mv);
+          entA = entB; entB = entC; entC = entD;
+        }
+        __syncwarp();
+      }
+    }
+#else
     for (int t = 1; t <= tmaxw; t++) {
       if (k < cnt && ((entA >> 8) & 0xff) == t) {
         T* r = crec(entA & 0xff);
@@ -1487,6 +1643,7 @@ struct World2 {
       }
       __syncwarp();
     }
+#endif
     // next sweep's first entries and record: towards L1 while the equality block is swept
     if (cnt > 0 && !L.aux_in_smem) { prefetch_l1(order); prefetch_l1(crec(ent0 & 0xff)); }
     return impr;
@@ -1522,6 +1679,15 @@ struct World2 {
       const Slot<T> sc = sn;
       sn = ld_slot<T>(slots + (st + 1) * LPW);   // the table carries one empty step past the end
       const unsigned o2 = sc.x >> 16;
+#if SG_EQ_NOPRED && SG_SLOT8
+      // unpredicated: padding slots and the second slider of fix rows address dummies that stay 0 (sg_plan.hpp emit)
+      const bool valid = true, has2 = o2 != (unsigned)(D.ns * sizeof(T));
+      T* pa1 = reinterpret_cast<T*>(avb + (sc.x & 0xffffu));
+      T* pa2 = reinterpret_cast<T*>(avb + o2);
+      T* pr = reinterpret_cast<T*>(rwb + (sc.y & 0x3fffffffu));
+      T a1 = *pa1, a2 = *pa2, u, n;
+      ld2(pr, u, n);
+#else
       const bool valid = (sc.y & 0x40000000u) != 0u, has2 = o2 != 0xffffu;     // padding slot / fix row: predicated off
       T* pa1 = reinterpret_cast<T*>(avb + (sc.x & 0xffffu));
       T* pa2 = reinterpret_cast<T*>(avb + o2);
@@ -1529,6 +1695,7 @@ struct World2 {
       T a1 = 0, a2 = 0, u = 0, n = 0;
       if (valid) { a1 = *pa1; ld2(pr, u, n); }
       if (has2) a2 = *pa2;
+#endif
       const T res = (a1 - a2) + u;
       if (GATED) n = done ? T(0) : n;
       const T dl = res * n;
@@ -1540,8 +1707,12 @@ struct World2 {
 #endif
       T un = a2 - a1;
       if (GATED) un = done ? u : un;
+#if SG_EQ_NOPRED && SG_SLOT8
+      *pr = un; *pa1 = a1; *pa2 = a2;
+#else
       if (valid) { *pr = un; *pa1 = a1; }
       if (has2) *pa2 = a2;
+#endif
       // nearly every step of the 8-lane schedules ends a dependency level: an unconditional barrier is cheaper than
       // testing the flag; narrower worlds have runs of independent steps that are allowed to overlap
       if (LPW >= 8 || (int)sc.y < 0) __syncwarp();

@@ -6,6 +6,10 @@
 // It replaces what mj_loadXML/mj_makeData hand to mj_step in the reference (ref: environment/manenv.py:27-28).
 // Anything outside that model family is rejected with an error -- there is no generic/CPU fallback.
 #pragma once
+// unpredicated equality sweep (see sg_kernels2.cuh equality_rows); needs SG_SLOT8
+#ifndef SG_EQ_NOPRED
+#define SG_EQ_NOPRED 0
+#endif
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -234,13 +238,22 @@ inline int build_step_tables_for(const PlanDims& D, const std::vector<double>& t
   } else for (int p = 0; p < nrow; p++) perm[p] = p;
   auto emit = [&](int p, int fl) {
     unsigned x = 0xffffffffu, y = (unsigned)fl << 31; double iw1 = 0, iw2 = 0;
+#if SG_EQ_NOPRED
+    // unpredicated sweep: padding slots address the dummy slider (index ns, always 0) twice and the dummy row pair
+    // (position nrow: u = 0, n = -1); the missing second slider of a fix row is the dummy slider as well
+    const unsigned dummy = (unsigned)(D.ns * esize);
+    x = dummy | (dummy << 16); y = (unsigned)(nrow * 2 * esize);
+#endif
     if (p >= 0) {
       const int d1 = itab[D.io_row_d1 + p], d2 = itab[D.io_row_d2 + p];
       iw1 = 1.0 / tab[D.o_sl_m + d1];
       unsigned o2 = 0xffffu;
+#if SG_EQ_NOPRED
+      o2 = dummy;
+#endif
       if (d2 >= 0) { o2 = (unsigned)(d2 * esize); iw2 = 1.0 / tab[D.o_sl_m + d2]; }
       x = (unsigned)(d1 * esize) | (o2 << 16);
-      y |= (unsigned)(perm[p] * 2 * esize) | (1u << 30);
+      y = ((unsigned)fl << 31) | (unsigned)(perm[p] * 2 * esize) | (1u << 30);
     }
     step_d.push_back((int)x); step_d.push_back((int)y); step_iw.push_back(iw1); step_iw.push_back(iw2);
   };
@@ -272,7 +285,7 @@ inline long sweep_wavefronts(const std::vector<int>& step_d, int lpw, int esize)
       for (int k = 0; k < lpw; k++) {
         const unsigned x = (unsigned)step_d[2 * (s * lpw + k)], y = (unsigned)step_d[2 * (s * lpw + k) + 1];
         const long goff = (long)slot * lpw + 4096L * slot;   // worlds sit lpw banks apart (plus whole multiples of 32 words)
-        const bool valid = (y >> 30) & 1, has2 = (x >> 16) != 0xffffu;
+        const bool valid = (y >> 30) & 1, has2 = (x >> 16) != 0xffffu;   // (the unpredicated variant also touches the dummies: not modelled)
         a1.push_back(valid ? goff + (x & 0xffff) / 4 : -1); a2.push_back(valid && has2 ? goff + (x >> 16) / 4 : -1);
         rw.push_back(valid ? goff + (y & 0x3fffffffu) / 4 : -1);
       }

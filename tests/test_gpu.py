@@ -106,9 +106,23 @@ def test_full_horizon_rollout_fp64_vs_oracle(torch_cuda, batched, make_world, k)
     row_err = err.max(axis=1)
     print("k=%g full-horizon drift: max %.2e  median %.2e  rows>1e-5: %d" % (k, row_err.max(), np.median(row_err), int((row_err > 1e-5).sum())))
     _note("fp64 full horizon k=%g: row max %.3e median %.3e rows>1e-5 %d" % (k, row_err.max(), np.median(row_err), int((row_err > 1e-5).sum())))
-    # bounds from the oracle's own sensitivity (tests/test_oracle.py::test_oracle_sensitivity_bounds_the_horizon_tolerances:
-    # a 1e-12 relative perturbation of one parameter moves its own traces by up to 3e-4 of a channel's peak, median 1e-7)
-    assert row_err.max() < 2e-2 and np.median(row_err) < 1e-5
+    # Bound = the oracle's OWN sensitivity at this stiffness: the same episode re-run on the host with the stiffness moved by
+    # +-1e-12 and +-3e-13 relative (what a different summation order does in fp64).  Where the oracle is well conditioned
+    # (k = 300, 1000: worst row 2e-6) the kernel has to agree that tightly; where a make/break event bifurcates (k = 1400:
+    # the -1e-12 run moves the oracle's own worst row by 4e-2 and its median row by 3e-4) no fp64 implementation can do
+    # better than that envelope.  Rows before the oracle's first sensitive row must agree to 1e-5 regardless.
+    env_max, env_med, first, env_q = 0.0, 0.0, rows.shape[0], 0.0
+    oq = w.get_state()[0]
+    for eps in (1e-12, -1e-12, 3e-13, -3e-13):
+        w2 = make_world("softbox", k=k * (1.0 + eps))
+        e2 = (np.abs(w2.episode()[0] - rows) / scale).max(axis=1)
+        env_q = max(env_q, rel(w2.get_state()[0], oq))
+        env_max = max(env_max, float(e2.max())); env_med = max(env_med, float(np.median(e2)))
+        if (e2 > 1e-6).any(): first = min(first, int(np.argmax(e2 > 1e-6)))
+    _note("fp64 full horizon k=%g: oracle self-sensitivity envelope (+-1e-12): row max %.3e median %.3e first sensitive row %d" % (k, env_max, env_med, first))
+    assert row_err[:max(40, first - 5)].max() < 1e-5
+    assert row_err.max() < max(1e-5, 3.0 * env_max) and np.median(row_err) < max(1e-8, 3.0 * env_med), (row_err.max(), env_max, np.median(row_err), env_med)
+    assert row_err.max() < 0.2
     tg = touch[0].cpu().numpy()
     assert (tg != otouch).sum() <= 4
     q, v, a, qacc = env.get_state()
@@ -117,7 +131,7 @@ def test_full_horizon_rollout_fp64_vs_oracle(torch_cuda, batched, make_world, k)
     # contact-free and must agree tightly; qpos is held to a drift bound (median over dofs), not to parity
     assert rel(a[0], oa) < 1e-9
     _note("fp64 full horizon k=%g: final qpos median %.3e max %.3e" % (k, float(np.median(np.abs(q[0] - oq))) / np.abs(oq).max(), rel(q[0], oq)))
-    assert float(np.median(np.abs(q[0] - oq))) / np.abs(oq).max() < 1e-5 and rel(q[0], oq) < 5e-2
+    assert float(np.median(np.abs(q[0] - oq))) / np.abs(oq).max() < 1e-5 and rel(q[0], oq) < max(1e-4, 3.0 * env_q)
     if k == 700.0:
         gold = np.load(os.path.join(GOLDEN, "softbox_episode_k700.npz"))
         assert (np.abs(g - gold["rows"]) / scale)[:40].max() < 1e-9

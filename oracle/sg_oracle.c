@@ -262,7 +262,7 @@ struct sgo_world {
   double* cfrc;      /* 6*nbody */
   double* efc_A;     /* 3 per row: diagonal block of AR */
   int* mark;         /* nv   */
-  int status, step_status, touch_mask, solver_iter, dense;
+  int status, step_status, touch_mask, solver_iter, dense, cb_single;
   double flops;            /* PGS op count of the last forward */
   double flops_total, flops_pgs_total; long steps_total;   /* accumulated over every forward since the last sgo_flops_reset */
   int ncand;               /* geom pairs that reached the narrowphase in the last forward */
@@ -336,6 +336,7 @@ void sgo_set_tendon_damping(sgo_world* d, int t, double v) { if (t >= 0 && t < d
 void sgo_set_body_pos(sgo_world* d, int b, const double* p) { if (b > 0 && b < d->m->nbody) memcpy(d->body_pos + 3 * b, p, 3 * sizeof(double)); }
 void sgo_set_ctrl(sgo_world* d, const double* c) { memcpy(d->ctrl, c, sizeof(double) * d->m->nu); }
 void sgo_set_dense_solver(sgo_world* d, int on) { d->dense = on; }
+void sgo_set_capsule_box_single(sgo_world* d, int on) { d->cb_single = on; }
 void sgo_set_geom_mask(sgo_world* d, const int* mask) { memcpy(d->geom_mask, mask, sizeof(int) * d->m->ngeom); }
 int sgo_status(const sgo_world* d) { return d->status; }
 double sgo_last_step_flops(const sgo_world* d) { return d->flops; }
@@ -646,8 +647,16 @@ static double seg_box_grad(const double* c, const double* h, const double* s, do
 
 /* capsule-box, DEFINED HERE (see file header): contact at the segment point of minimal signed
  * distance to the box; a second contact at the far end of the segment if that end is within margin. */
+static int capsule_box_mode(rawcon* con, double margin, const double* cpos, const double* cmat, const double* csize,
+                            const double* bpos, const double* bmat, const double* bsize, int second);
 static int capsule_box(rawcon* con, double margin, const double* cpos, const double* cmat, const double* csize,
                        const double* bpos, const double* bmat, const double* bsize) {
+  return capsule_box_mode(con, margin, cpos, cmat, csize, bpos, bmat, bsize, 1);
+}
+/* second = 0 drops the second contact (sensitivity study of the one rule of this narrowphase that is a choice rather than
+ * geometry, tests/test_oracle.py::test_second_capsule_box_contact_is_immaterial); the product and every parity test use 1 */
+static int capsule_box_mode(rawcon* con, double margin, const double* cpos, const double* cmat, const double* csize,
+                            const double* bpos, const double* bmat, const double* bsize, int second) {
   double radius = csize[0], hl = csize[1];
   double axis_w[3] = {cmat[2], cmat[5], cmat[8]};
   double tmp[3], c[3], ax[3], h[3];
@@ -700,6 +709,7 @@ static int capsule_box(rawcon* con, double margin, const double* cpos, const dou
   int n = 0; double sp[3];
   for (int k = 0; k < 3; k++) sp[k] = cpos[k] + axis_w[k] * (tstar * hl);
   n += sphere_box(con + n, margin, sp, radius, bpos, bmat, bsize);
+  if (!second) return n;
   double t2 = (tstar >= 0) ? -1.0 : 1.0;
   for (int k = 0; k < 3; k++) sp[k] = cpos[k] + axis_w[k] * (t2 * hl);
   n += sphere_box(con + n, margin, sp, radius, bpos, bmat, bsize);
@@ -772,7 +782,7 @@ static void collision(sgo_world* d) {
     d->ncand++;
     if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) n = plane_capsule(rc, margin, p1, R1, p2, R2, m->geom_size + 3 * g2);
     else if (t1 == GEOM_SPHERE && t2 == GEOM_BOX) n = sphere_box(rc, margin, p1, m->geom_size[3 * g1], p2, R2, m->geom_size + 3 * g2);
-    else if (t1 == GEOM_CAPSULE && t2 == GEOM_BOX) n = capsule_box(rc, margin, p1, R1, m->geom_size + 3 * g1, p2, R2, m->geom_size + 3 * g2);
+    else if (t1 == GEOM_CAPSULE && t2 == GEOM_BOX) n = capsule_box_mode(rc, margin, p1, R1, m->geom_size + 3 * g1, p2, R2, m->geom_size + 3 * g2, !d->cb_single);
     else if (t1 == GEOM_BOX && t2 == GEOM_BOX) { if (box_box_overlap(p1, R1, m->geom_size + 3 * g1, p2, R2, m->geom_size + 3 * g2)) d->step_status |= SGO_ST_BOXBOX; }
     else d->step_status |= SGO_ST_BOXBOX; /* unsupported pair reached the narrowphase (e.g. plane-box) */
     for (int i = 0; i < n; i++) {

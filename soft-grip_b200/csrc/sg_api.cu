@@ -712,8 +712,10 @@ static int traj_noise_launch(const void* in, void* out, long long nrows, long lo
   const int block = 256;
   const long long nquad = A.nelem / 4;
   long long grid = (nquad + block - 1) / block;
-  if (grid > (long long)sms * 8) grid = (long long)sms * 8;     // 8 x 256 threads resident per SM, grid-stride beyond that
   auto kp = sg_traj_noise_kernel<T>;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kp, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (grid > (long long)sms * per_sm) grid = (long long)sms * per_sm;   // exactly one resident wave, grid-stride beyond that
   SG_LAUNCH(kp, (int)grid, block, 0, (cudaStream_t)stream, A);
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -745,11 +747,17 @@ static int traj_stats_block(int nchan) {           // a multiple of 32 and of nc
   return block;
 }
 
-static int traj_stats_grid(int nchan, long long nrows, int sms) {
+// one resident wave of pass-1 CTAs (the occupancy the hardware reports for this instantiation), never more CTAs than quads
+static int traj_stats_grid(int nchan, long long nrows, int sms, int precision) {
   const int block = traj_stats_block(nchan);
   const long long nquad = nrows * (nchan / 4);
   long long grid = (nquad + block - 1) / block;
-  const long long cap = (long long)sms * (1536 / block);
+  int per_sm = 0;
+  const size_t smem = (size_t)block * 8 * sizeof(double);
+  const cudaError_t e = precision == 32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_traj_stats_partial_kernel<float>, block, smem)
+                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_traj_stats_partial_kernel<double>, block, smem);
+  if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+  const long long cap = (long long)sms * per_sm;
   if (grid > cap) grid = cap;
   return (int)(grid < 1 ? 1 : grid);
 }
@@ -758,7 +766,10 @@ extern "C" long long sg_traj_stats_workspace_bytes(long long nrows, int nchan, i
   if (nrows < 0 || nchan < 4 || nchan % 4 != 0 || nchan > TRAJ_STATS_MAX_CHAN) return fail("sg_traj_stats_workspace_bytes: bad shape");
   int sms = 0;
   if (int rc = traj_sm_count(device, &sms)) return rc;
-  return (long long)traj_stats_grid(nchan, nrows, sms) * 2 * nchan * (long long)sizeof(double);
+  if (cudaSetDevice(device) != cudaSuccess) return fail("sg_traj_stats_workspace_bytes: cudaSetDevice failed");
+  // (sized for either precision: the larger of the two grids)
+  const int g32 = traj_stats_grid(nchan, nrows, sms, 32), g64 = traj_stats_grid(nchan, nrows, sms, 64);
+  return (long long)(g32 > g64 ? g32 : g64) * 2 * nchan * (long long)sizeof(double);
 }
 
 template <typename T>
@@ -766,12 +777,12 @@ static int traj_stats_launch(const void* in, long long nrows, int nchan, double*
   TrajStatsArgs<T> A;
   A.in = (const T*)in; A.nrows = nrows; A.nchan = nchan; A.partial = (double*)ws; A.mean = mean; A.stdev = stdev;
   const int block = traj_stats_block(nchan);
-  A.nblocks = traj_stats_grid(nchan, nrows, sms);
+  A.nblocks = traj_stats_grid(nchan, nrows, sms, sizeof(T) == 4 ? 32 : 64);
   auto k1 = sg_traj_stats_partial_kernel<T>;
   SG_LAUNCH(k1, A.nblocks, block, (size_t)block * 8 * sizeof(double), (cudaStream_t)stream, A);
   CUDA_OK(cudaGetLastError());
   auto k2 = sg_traj_stats_final_kernel<T>;
-  SG_LAUNCH(k2, 1, 64, 0, (cudaStream_t)stream, A);
+  SG_LAUNCH(k2, 1, TRAJ_STATS_FINAL_THREADS, (size_t)(TRAJ_STATS_FINAL_THREADS / (2 * nchan)) * 2 * nchan * sizeof(double), (cudaStream_t)stream, A);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

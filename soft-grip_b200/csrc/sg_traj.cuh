@@ -46,23 +46,37 @@ __device__ __forceinline__ Philox4 philox4x32_10(Philox4 c, uint32_t k0, uint32_
 // uniform in (0, 1]: never 0, so the logarithm below is finite (x * 2^-32 is exact in fp32, so fma or mul+add agree)
 __device__ __forceinline__ float u01(uint32_t x) { return (float)x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }
 
-// two standard normals from two words
+// two standard normals from two words: Box-Muller, z0 = r cos(2 pi ub), z1 = r sin(2 pi ub), r = sqrt(-2 ln ua).
+// Default: the special-function unit, arranged so that the absolute error on z stays below 8e-6 for every input (typically
+// 1e-6; the oracle evaluates the same formula in float64 from the same fp32 uniforms):
+//   * ln ua by lg2.approx (relative error 2^-22 below 0.5, absolute 2^-22 above) except within 2^-5 of 1, where the relative
+//     error of a logarithm near zero would blow up: there 1 - ua is exact in fp32 and -ln(1 - t) is its series to t^5
+//     (truncation t^5 / 6 < 5e-9 relative);
+//   * sqrt.approx (2^-23 relative);
+//   * the angle is taken in (-pi, pi] (cos and sin of 2 pi u are minus those of 2 pi (u - 0.5), and u - 0.5 is exact above
+//     0.25), where sin.approx / cos.approx are good to 2^-20.9 absolute.
+// About 50 instructions per pair instead of ~170 with the FFMA polynomials of logf / sincospif: the kernel is bound by
+// HBM instead of by issue slots.  -DSG_TRAJ_ACCURATE_NORMALS keeps the libdevice version for A/B runs.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-#ifdef SG_TRAJ_FAST_NORMALS
-  // A/B build only (make NVCCFLAGS+=-DSG_TRAJ_FAST_NORMALS, never the default and not what the parity tests pin): the
-  // special-function unit instead of the FFMA polynomials of logf / sincospif -- ~140 instead of ~260 instructions per
-  // quad, at ~3e-6 absolute error on the normal (up to 8e-4 in the 1e-6-probability corner u -> 1).  See DESIGN.md 3b.
-  const float r = sqrtf(-2.0f * __logf(u01(a)));
-  float s, c;
-  __sincosf(6.2831853071795865f * (u01(b) - 0.5f), &s, &c);      // angle in (-pi, pi]: the intrinsic's accurate range
-  z0 = -r * c;
-  z1 = -r * s;
-#else
+#if defined(SG_TRAJ_ACCURATE_NORMALS) || !defined(__CUDA_ARCH__)
   const float r = sqrtf(-2.0f * logf(u01(a)));
   float s, c;
   sincospif(2.0f * u01(b), &s, &c);
   z0 = r * c;
   z1 = r * s;
+#else
+  const float ua = u01(a), t = 1.0f - ua;
+  float lg, L, r, s, c;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(ua));
+  L = -1.3862943611198906f * lg;                                       // -2 ln 2 * log2(ua)
+  const float ser = 2.0f * t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 0.2f, 0.25f), 0.33333334f), 0.5f), 1.0f);
+  L = t < 0.03125f ? ser : L;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(L));
+  const float th = 6.2831853071795865f * (u01(b) - 0.5f);
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
+  z0 = -r * c;
+  z1 = -r * s;
 #endif
 }
 
@@ -92,30 +106,44 @@ struct TrajNoiseArgs {
 };
 
 template <typename T>
+__device__ __forceinline__ void traj_noise_quad(const TrajNoiseArgs<T>& A, Vec4<T>& v, long long q, int g) {
+  const unsigned long long ctr = A.first_quad + (unsigned long long)q;
+  const Philox4 r = philox4x32_10(Philox4{(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, A.k0, A.k1);
+  float z[4];
+  box_muller(r.x, r.y, z[0], z[1]);
+  box_muller(r.z, r.w, z[2], z[3]);
+  const int c0 = g * 4;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int c = c0 + j;
+    T x = v.v[j] + (T)(c < A.nacc ? A.sigma_acc : A.sigma_gyro) * (T)z[j];
+    if (A.mean) x = (x - (T)A.mean[c]) / (T)A.stdev[c];
+    v.v[j] = x;
+  }
+}
+
+// Two quads per thread and iteration, both loads issued before any arithmetic: with 2 048 resident threads per SM that is
+// 64 KB of reads in flight per SM, enough to cover the HBM latency at the measured bandwidth.
+template <typename T>
 __global__ void __launch_bounds__(256) sg_traj_noise_kernel(const __grid_constant__ TrajNoiseArgs<T> A) {
   const long long nquad = A.nelem >> 2, stride = (long long)gridDim.x * blockDim.x;
   const int qpr = A.nchan >> 2;
   const long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int g = (int)(q0 % qpr);                               // channel group of q, carried along instead of a 64-bit modulo per quad
   const int gstep = (int)(stride % qpr);
-  for (long long q = q0; q < nquad; q += stride) {
-    Vec4<T> v = load4(A.in + 4 * q);
-    const unsigned long long ctr = A.first_quad + (unsigned long long)q;
-    const Philox4 r = philox4x32_10(Philox4{(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, A.k0, A.k1);
-    float z[4];
-    box_muller(r.x, r.y, z[0], z[1]);
-    box_muller(r.z, r.w, z[2], z[3]);
-    const int c0 = g * 4;
-    g += gstep;
+  for (long long q = q0; q < nquad; q += 2 * stride) {
+    const long long qb = q + stride;
+    const bool hb = qb < nquad;
+    Vec4<T> va = load4(A.in + 4 * q);
+    Vec4<T> vb = va;
+    if (hb) vb = load4(A.in + 4 * qb);
+    int gb = g + gstep;
+    if (gb >= qpr) gb -= qpr;
+    traj_noise_quad(A, va, q, g);
+    store4(A.out + 4 * q, va);
+    if (hb) { traj_noise_quad(A, vb, qb, gb); store4(A.out + 4 * qb, vb); }
+    g = gb + gstep;
     if (g >= qpr) g -= qpr;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int c = c0 + j;
-      T x = v.v[j] + (T)(c < A.nacc ? A.sigma_acc : A.sigma_gyro) * (T)z[j];
-      if (A.mean) x = (x - (T)A.mean[c]) / (T)A.stdev[c];
-      v.v[j] = x;
-    }
-    store4(A.out + 4 * q, v);
   }
 }
 
@@ -146,7 +174,7 @@ __global__ void __launch_bounds__(512) sg_traj_stats_partial_kernel(const __grid
   const int g = tid % qpr;                             // this thread's channel group
   const Vec4<T> sv = load4(A.in + 4 * g);
   double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-#pragma unroll 4
+#pragma unroll 8
   for (long long q = (long long)blockIdx.x * nt + tid; q < nquad; q += stride) {
     const Vec4<T> v = load4(A.in + 4 * q);
 #pragma unroll
@@ -168,19 +196,33 @@ __global__ void __launch_bounds__(512) sg_traj_stats_partial_kernel(const __grid
   }
 }
 
+// Pass 2, one CTA: thread (r, col) adds the partials of the CTAs b = r, r + R, r + 2R, ... of column col = (sum | sum of
+// squares, channel) in increasing b -- independent loads, so the L2 latency is paid once per thread and not once per
+// partial as in a single serial loop -- and the R subset sums of a column are then added in the order r = 0 .. R-1.  The
+// association is fixed by (nblocks, blockDim.x) alone: bit-reproducible.
+constexpr int TRAJ_STATS_FINAL_THREADS = 1024;
 template <typename T>
-__global__ void __launch_bounds__(64) sg_traj_stats_final_kernel(const __grid_constant__ TrajStatsArgs<T> A) {
-  const int c = threadIdx.x;
-  if (c >= A.nchan) return;
-  double s = 0, ss = 0;
-  for (int b = 0; b < A.nblocks; b++) {
-    s += A.partial[((long long)b * 2 + 0) * A.nchan + c];
-    ss += A.partial[((long long)b * 2 + 1) * A.nchan + c];
+__global__ void __launch_bounds__(TRAJ_STATS_FINAL_THREADS) sg_traj_stats_final_kernel(const __grid_constant__ TrajStatsArgs<T> A) {
+  SG_SHARED_BYTES(smem_raw);
+  double* sh = (double*)smem_raw;                      // [R][2 * nchan]
+  const int ncol = 2 * A.nchan, R = blockDim.x / ncol, tid = threadIdx.x;
+  const int r = tid / ncol, col = tid - r * ncol;
+  if (r < R) {
+    double acc = 0;
+#pragma unroll 4
+    for (int b = r; b < A.nblocks; b += R) acc += A.partial[(long long)b * ncol + col];
+    sh[r * ncol + col] = acc;
   }
-  const double n = (double)A.nrows * 1.0, m = s / n;
-  const double var = ss / n - m * m;
-  A.mean[c] = (double)A.in[c] + m;
-  A.stdev[c] = sqrt(var > 0 ? var : 0.0);
+  __syncthreads();
+  if (tid < A.nchan) {
+    const int c = tid;
+    double s = 0, ss = 0;
+    for (int q = 0; q < R; q++) { s += sh[q * ncol + c]; ss += sh[q * ncol + A.nchan + c]; }
+    const double n = (double)A.nrows * 1.0, m = s / n;
+    const double var = ss / n - m * m;
+    A.mean[c] = (double)A.in[c] + m;
+    A.stdev[c] = sqrt(var > 0 ? var : 0.0);
+  }
 }
 
 // ---- --mask-contact -------------------------------------------------------------------------------------------------

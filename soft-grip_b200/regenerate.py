@@ -84,9 +84,43 @@ class DeviceRollouts:
         `softball_testing` and `softcylinder_testing` do not share a label vector."""
         return self.seed * len(SHAPES) + SHAPES.index(shape)
 
+    def prefetch(self, files):
+        """Simulate every world a file plan needs, one shape at a time and in as few launches as `worlds_per_launch`
+        allows.  A launch is bound by the latency of one episode (about a second whether it holds 500 worlds or 9 000), so
+        six files of a few hundred to a few thousand samples cost three launches instead of nine.  `files` is the output
+        of plan_files; world ids of a shape are handed out consecutively, so [0, total) covers all its parts."""
+        import torch
+        total = {}
+        for _, parts in files:
+            for shape, first, count in parts:
+                total[shape] = max(total.get(shape, 0), first + count)
+        self._cache = {}
+        for shape, n in total.items():
+            chunks = list(self._simulate(shape, 0, n))
+            self._cache[shape] = tuple(torch.cat([c[i] for c in chunks], 0) for i in range(3))
+
     def __call__(self, shape, first, count, noise_seed=None):
         """noise_seed: also apply the trainer's noise augmentation (ref: functions/optimization.py:6-14) on the device; the
         draw of a sample depends only on (noise_seed, shape, global world id), not on launches or ranks."""
+        cache = getattr(self, "_cache", {}).get(shape)
+        if cache is not None and first + count <= cache[0].shape[0]:
+            traj, k, st = (t[first:first + count] for t in cache)
+            if noise_seed is not None:
+                traj = self._noise(traj.clone(), shape, first, noise_seed)
+            yield traj, k, st
+            return
+        for traj, k, st in self._simulate(shape, first, count):
+            if noise_seed is not None:
+                traj = self._noise(traj, shape, first, noise_seed)
+                first += int(traj.shape[0])
+            yield traj, k, st
+
+    def _noise(self, traj, shape, first, noise_seed):
+        fn = importlib.import_module(_PKG + ".functions")
+        fn.noised_modality(traj, seed=int(noise_seed) * len(SHAPES) + SHAPES.index(shape), out=traj, first_row=first * int(traj.shape[1]))
+        return traj
+
+    def _simulate(self, shape, first, count):
         import torch
         b = self.batched
         if shape not in self._dm:
@@ -102,15 +136,11 @@ class DeviceRollouts:
             if shape in self.tdamp:
                 env.set_params(tendon_damping=torch.full((n,), float(self.tdamp[shape]), dtype=torch.float64, device=self.device))
             traj, k, st, touch = env.rollout(return_touch=True)
+            if self.mask:
+                env.mask_contact(traj, touch)
             torch.cuda.synchronize(self.device)
             self.seconds["simulate"] += time.perf_counter() - t0
             self.world_steps += n * (self.sim_start + self.sim_step * int(traj.shape[1]))
-            if self.mask:
-                env.mask_contact(traj, touch)
-            if noise_seed is not None:
-                fn = importlib.import_module(_PKG + ".functions")
-                fn.noised_modality(traj, seed=int(noise_seed) * len(SHAPES) + SHAPES.index(shape), out=traj,
-                                   first_row=(first + done) * int(traj.shape[1]))
             yield traj, k, st
             done += n
             del env
@@ -308,7 +338,10 @@ def regenerate(out_dir, n_train, n_val, n_test, rollouts, shapes=SHAPES, stats_f
     dataset = importlib.import_module(_PKG + ".dataset")
     out = []
     t0 = time.perf_counter()
-    for stem, parts in plan_files(n_train, n_val, n_test, shapes):
+    files = plan_files(n_train, n_val, n_test, shapes)
+    if hasattr(rollouts, "prefetch"):
+        rollouts.prefetch(files)            # one launch per shape instead of one per file part
+    for stem, parts in files:
         kw = {"noise_seed": noise_seed} if (noise_seed is not None and stem.endswith("/train")) else {}
 
         def chunks():

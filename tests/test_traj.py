@@ -16,9 +16,11 @@ from oracle import traj_oracle as to
 
 sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
 
-# fp32 Box-Muller on the device vs float64 Box-Muller of the same uniforms in the oracle: logf/sincospif are good to ~2 ulp,
-# |z| <= 6.7, so 4e-6 absolute on the standard normal
-Z_TOL = 4e-6
+# fp32 Box-Muller on the device vs float64 Box-Muller of the same uniforms in the oracle.  The device evaluates it on the
+# special-function unit (csrc/sg_traj.cuh box_muller): sin/cos.approx 2^-20.9 = 5.1e-7 absolute on an angle that itself carries
+# <= 3e-7 of fp32 rounding, times r <= 6.76, plus the 2^-22 relative error of lg2.approx -> 8e-6 absolute on the standard
+# normal in the worst corner (r at its maximum), about 1e-6 typically.  (The emulator build runs the libm formula.)
+Z_TOL = 8e-6
 
 
 def _vp(a):

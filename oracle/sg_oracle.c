@@ -262,7 +262,7 @@ struct sgo_world {
   double* cfrc;      /* 6*nbody */
   double* efc_A;     /* 3 per row: diagonal block of AR */
   int* mark;         /* nv   */
-  int status, step_status, touch_mask, solver_iter, dense, cb_single;
+  int status, step_status, touch_mask, solver_iter, dense, cb_single, implicit_tendon;
   double flops;            /* PGS op count of the last forward */
   double flops_total, flops_pgs_total; long steps_total;   /* accumulated over every forward since the last sgo_flops_reset */
   int ncand;               /* geom pairs that reached the narrowphase in the last forward */
@@ -337,6 +337,7 @@ void sgo_set_body_pos(sgo_world* d, int b, const double* p) { if (b > 0 && b < d
 void sgo_set_ctrl(sgo_world* d, const double* c) { memcpy(d->ctrl, c, sizeof(double) * d->m->nu); }
 void sgo_set_dense_solver(sgo_world* d, int on) { d->dense = on; }
 void sgo_set_capsule_box_single(sgo_world* d, int on) { d->cb_single = on; }
+void sgo_set_implicit_tendon_damping(sgo_world* d, int on) { d->implicit_tendon = on; }
 void sgo_set_geom_mask(sgo_world* d, const int* mask) { memcpy(d->geom_mask, mask, sizeof(int) * d->m->ngeom); }
 int sgo_status(const sgo_world* d) { return d->status; }
 double sgo_last_step_flops(const sgo_world* d) { return d->flops; }
@@ -1240,7 +1241,12 @@ static void solve_pgs_dense(sgo_world* d) {
 /* mj_fwdConstraint: b, warm start, PGS, dualFinish */
 static void fwd_constraint(sgo_world* d) {
   const sgo_model* m = d->m; int nv = m->nv, nefc = d->nefc;
-  if (!nefc) { memcpy(d->qacc, d->qacc_smooth, sizeof(double) * nv); memset(d->qfrc_constraint, 0, sizeof(double) * nv); d->solver_iter = 0; return; }
+  /* mj_fwdConstraint saves the result for the next step's warm start itself (both exits), so mj_forward alone -- ManEnv.reset's
+   * sim.forward(), ref: manenv.py:57-58 -- already seeds the first step; the integrator does not touch qacc_warmstart */
+  if (!nefc) {
+    memcpy(d->qacc, d->qacc_smooth, sizeof(double) * nv); memcpy(d->qacc_warmstart, d->qacc_smooth, sizeof(double) * nv);
+    memset(d->qfrc_constraint, 0, sizeof(double) * nv); d->solver_iter = 0; return;
+  }
   for (int i = 0; i < nefc; i++) d->efc_b[i] = row_dot(d, i, d->qacc_smooth) - d->efc_aref[i];
   /* warm start: forces from qacc_warmstart, kept only if the dual cost is not positive */
   double* jar = (double*)malloc(sizeof(double) * nefc);
@@ -1267,6 +1273,7 @@ static void fwd_constraint(sgo_world* d) {
     for (int q = 0; q < d->efc_rownnz[i]; q++) { int c = d->efc_colind[adr + q]; d->qfrc_constraint[c] += d->efc_J[adr + q] * f; w[c] += d->efc_B[adr + q] * f; }
   }
   for (int i = 0; i < nv; i++) d->qacc[i] = d->qacc_smooth[i] + w[i];
+  memcpy(d->qacc_warmstart, d->qacc, sizeof(double) * nv);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1322,13 +1329,31 @@ static void euler(sgo_world* d) {
     for (int i = 0; i < nv; i++) qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
     /* solve with the temporary factor */
     double *sLD = d->qLD, *sDi = d->qLDiagInv;
-    d->qLD = LD; d->qLDiagInv = dinv; solve_ld(d, qacc); d->qLD = sLD; d->qLDiagInv = sDi;
+    d->qLD = LD; d->qLDiagInv = dinv; solve_ld(d, qacc);
+    if (d->implicit_tendon) {
+      /* HYPOTHESIS SWITCH (SURVEY App. E candidate, off by default, NOT what MuJoCo's Euler integrator is recalled to do):
+       * tendon dampers treated like joint dampers, (M + h diag(d) + h sum_t b_t J_t' J_t) qacc' = rhs, one rank-1
+       * Sherman-Morrison update per damped tendon on top of the solve above */
+      double* y = (double*)malloc(sizeof(double) * nv);
+      for (int t = 0; t < m->ntendon; t++) {
+        double b = d->tendon_damping[t];
+        if (!(b > 0)) continue;
+        const double* J = d->ten_J + (size_t)t * nv;
+        memcpy(y, J, sizeof(double) * nv);
+        solve_ld(d, y);
+        double jx = 0, jy = 0;
+        for (int i = 0; i < nv; i++) { jx += J[i] * qacc[i]; jy += J[i] * y[i]; }
+        double c = h * b * jx / (1.0 + h * b * jy);
+        for (int i = 0; i < nv; i++) qacc[i] -= c * y[i];
+      }
+      free(y);
+    }
+    d->qLD = sLD; d->qLDiagInv = sDi;
     free(MhB);
   }
   for (int u = 0; u < m->nu; u++) d->act[u] += h * d->act_dot[u];
   for (int i = 0; i < nv; i++) { d->qvel[i] += h * qacc[i]; d->qpos[i] += h * d->qvel[i]; }
   d->time += h;
-  memcpy(d->qacc_warmstart, d->qacc, sizeof(double) * nv);
 }
 
 int sgo_step(sgo_world* d) {

@@ -37,6 +37,7 @@ void sgo_set_tendon_damping(sgo_world* w, int tendon, double d);
 void sgo_set_body_pos(sgo_world* w, int body, const double* xyz);
 void sgo_set_ctrl(sgo_world* w, const double* ctrl);
 void sgo_set_capsule_box_single(sgo_world* w, int on); /* sensitivity study only: drop the second capsule-box contact */
+void sgo_set_implicit_tendon_damping(sgo_world* w, int on); /* hypothesis switch, off by default */
 void sgo_set_dense_solver(sgo_world* w, int on);   /* literal efc_AR PGS (slow; validation of the matrix-free form) */
 void sgo_set_geom_mask(sgo_world* w, const int* mask); /* per-geom name bitmask for the contact flag */
 

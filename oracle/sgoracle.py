@@ -68,6 +68,7 @@ def lib():
         L.sgo_set_ctrl.argtypes = [P, D]
         L.sgo_set_dense_solver.argtypes = [P, C.c_int]
         L.sgo_set_capsule_box_single.argtypes = [P, C.c_int]
+        L.sgo_set_implicit_tendon_damping.argtypes = [P, C.c_int]
         L.sgo_set_geom_mask.argtypes = [P, I]
         L.sgo_reset.argtypes = [P]
         L.sgo_forward.argtypes = [P]
@@ -152,6 +153,7 @@ class OracleWorld:
 
     def set_dense_solver(self, on): self._L.sgo_set_dense_solver(self.h, int(on))
     def set_capsule_box_single(self, on): self._L.sgo_set_capsule_box_single(self.h, int(on))
+    def set_implicit_tendon_damping(self, on): self._L.sgo_set_implicit_tendon_damping(self.h, int(on))
 
     def set_geom_mask(self, mask):
         a = np.ascontiguousarray(mask, dtype=np.int32)

@@ -1989,7 +1989,9 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
       __syncwarp();
     } else W.reset_if(true);     // whole episode on-chip (create_dataset.log_into_file, ref: create_dataset.py:33-60)
     const int total = K.rollout ? K.sim_start + K.nrows * K.sim_step : (K.integrate ? K.nsub : 1);
-    for (int s = 0; s < total; s++) {
+    // rollout: pass s = -1 is the mj_forward of ManEnv.reset (ref: manenv.py:57-58 sim.reset(); sim.forward()).  It moves no
+    // state but, like every mj_forward, leaves its qacc as the warm start of the first step (mj_fwdConstraint saves it).
+    for (int s = K.rollout ? -1 : 0; s < total; s++) {
       if (nwarp > 1 && K.step_barrier) __syncthreads();     // warps start each step together (instruction-cache locality, see above)
       int t = -1, phase = 0;
       if (K.rollout && s >= K.sim_start) {
@@ -2000,7 +2002,7 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
           __syncwarp();
         }
       }
-      W.step(K.rollout || K.integrate);
+      W.step(s >= 0 && (K.rollout || K.integrate));
       if (t >= 0 && phase == K.sim_step - 1 && valid) {
         // sensor row of this env-step (ref: manenv.py:85 np.copy(sensordata)).  World-major: one world's row is 12
         // consecutive values, written as 128-bit vectors by the first lanes of the world; SoA: channel-major planes with
@@ -2016,12 +2018,7 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
         if (K.touch_out && sl == 0) K.touch_out[(size_t)w * K.nrows + t] = W.misc(M2_TOUCH);
       }
     }
-    if (!K.rollout && !K.integrate) {
-      // mj_forward: sensors/contacts refreshed, nothing integrated, warm start left untouched
-      __syncwarp();
-      for (int i = sl; i < D.nv; i += LPW) W.a()[i] = K.warm[sb + i];
-      __syncwarp();
-    }
+    // (a forward-only launch stores its qacc as the next warm start as well: mj_fwdConstraint saves it on every mj_forward)
     if (valid) {
       for (int i = sl; i < D.nv; i += LPW) { K.qpos[sb + i] = W.q()[i]; K.qvel[sb + i] = W.v()[i]; K.warm[sb + i] = W.a()[i]; }
       if (!K.rollout) {

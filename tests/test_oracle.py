@@ -376,7 +376,9 @@ def test_oracle_sensitivity_bounds_the_horizon_tolerances(oracle):
     chaotic once contacts make and break.  The oracle run against ITSELF with one parameter perturbed by 1e-6 relative
     (about what fp32 rounding of the inputs alone does) moves its own traces by a median of 1e-3..3e-2 of a channel's peak
     and by O(1) on the worst row, while the 40 contact-free settle rows do not move at all; a 1e-12 perturbation (what a
-    different summation order does in fp64) stays below 1e-3 on the worst row and 1e-6 in the median."""
+    different summation order does in fp64) moves the median row by less than 1e-5, while the worst row -- one make/break event taken a step earlier or later -- can move
+    by percents (3.5e-2 here; 4e-2 at k = 1400) at these two
+    stiffnesses (tests/test_gpu.py measures the envelope per stiffness instead of assuming one)."""
     m = oracle.OracleModel(open(blob_path("softbox"), "rb").read())
 
     def run(k):
@@ -394,4 +396,80 @@ def test_oracle_sensitivity_bounds_the_horizon_tolerances(oracle):
             med.append(float(np.median(err))); mx.append(float(err.max()))
     assert max(med6) > 1e-3 and max(max6) > 0.5          # fp32-sized perturbations decorrelate the worst rows completely
     assert max(med6) < 5e-2                               # ... but the median row stays inside the stated fp32 bound
-    assert max(med12) < 1e-6 and max(max12) < 1e-3        # fp64-sized ones stay small: the fp64 bounds of tests/test_gpu.py
+    assert max(med12) < 1e-5 and max(max12) < 0.2         # fp64-sized ones: tight in the median, bifurcations on single rows
+
+
+def test_app_e_candidates_for_the_committed_ball_and_cylinder(oracle):
+    """SURVEY App. E, settled as far as it can be without MuJoCo: under the restated semantics softball / softcylinder run
+    away at their COMMITTED parameters (joint and volume-tendon damper 100, ref:
+    data/gripper/soft_experiments_softball_adjusted_for_2_fingers.xml:11-14).  Of the three recalled details App. E names,
+    (a) the tendon damper not entering (0) or entering at <= 70 and (c) an implicit treatment of the tendon damper in the
+    Euler step each make both committed files run a whole episode clean; (b) the impedance / diagApprox of the tendon row
+    cannot (dmax = 0.97 caps the attenuation at 65.7 where 109 would be needed for n = 218).  softbox
+    runs under every variant -- and (c) changes its traces too, so which variant MuJoCo 2.0 implements stays the top
+    unpinned detail of this oracle.  The product and every parity test use the default (explicit tendon damper, App. A6)."""
+    for name in ("softball", "softcylinder"):
+        m = oracle.OracleModel(open(blob_path(name), "rb").read())
+
+        def run(tendon_damping=None, implicit=False):
+            w = oracle.OracleWorld(m)
+            w.set_stiffness(700.0)
+            if tendon_damping is not None:
+                w.set_tendon_damping(0, tendon_damping)
+            w.set_implicit_tendon_damping(implicit)
+            rows, _, st = w.episode()
+            return st, float(np.abs(rows).max())
+
+        st, peak = run()
+        assert st & 1 and peak > 1e6                      # committed: diverged and reset
+        for td in (70.0, 0.0):
+            st, peak = run(tendon_damping=td)
+            assert st == 0 and peak < 1e3, (name, td, st, peak)      # (a)
+        st, peak = run(implicit=True)
+        assert st == 0 and peak < 1e3, (name, st, peak)               # (c), at the committed damper
+    m = oracle.OracleModel(open(blob_path("softbox"), "rb").read())
+    rows = []
+    for implicit in (False, True):
+        w = oracle.OracleWorld(m)
+        w.set_stiffness(700.0)
+        w.set_implicit_tendon_damping(implicit)
+        r, _, st = w.episode()
+        assert st == 0
+        rows.append(r)
+    scale = np.abs(rows[0]).max(axis=0)
+    assert (np.abs(rows[0] - rows[1]) / scale)[40:].max() > 1e-2       # ... and it matters for the headline model as well
+
+
+def test_second_capsule_box_contact_share_and_sensitivity(oracle):
+    """The one rule of the capsule-box narrowphase that is a choice rather than geometry: the first contact sits at the segment
+    point closest to the box (pinned against dense sampling above, and what any closest-feature routine returns); the second
+    contact -- here: the far end of the segment when it penetrates -- is where a restatement can differ from
+    mjc_CapsuleBox's case analysis.  It is rare (about 2 % of the softbox contacts, none on the ball) but not immaterial: in
+    a chaotic episode dropping it moves the median row by percents.  Recorded so that the claim "contact sets equal the
+    reference's" is never made on this evidence (DESIGN.md section 4)."""
+    m = oracle.OracleModel(open(blob_path("softbox"), "rb").read())
+    out = []
+    for single in (0, 1):
+        w = oracle.OracleWorld(m)
+        w.set_stiffness(700.0)
+        w.set_capsule_box_single(single)
+        w.reset(); w.forward()
+        pairs2 = total = 0
+        rows = []
+        ctrl = [0.0] * 40 + [-0.2] * 80 + [0.2] * 80
+        w.step()
+        for t in range(200):
+            w.set_ctrl([ctrl[t]] * 2)
+            for _ in range(7):
+                w.step()
+                n = w.get_int("ncon")
+                if n:
+                    g = list(zip(w.get("con_geom1").astype(int), w.get("con_geom2").astype(int)))
+                    total += n
+                    pairs2 += n - len(set(g))
+            rows.append(w.sensordata())
+        out.append((np.array(rows), pairs2, total))
+    (a, p2, tot), (b, p2s, _) = out
+    assert p2s == 0 and 0.005 < p2 / tot < 0.05
+    scale = np.abs(a).max(axis=0)
+    assert np.median((np.abs(a - b) / scale).max(axis=1)[60:]) > 1e-3

@@ -208,7 +208,10 @@ static int batch_create_body(const sg_model* m, int nworlds, int device, int pre
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
   // kernel selection (environment overrides are development knobs; the defaults are the measured best)
-  b->kernel = 2; b->lpw = 8; b->nwarp = 16;
+  // lanes per world: 8 for the committed models (measured best for softbox, softball; within 9 % for softcylinder), 32 for
+  // shells beyond 256 elements, where shared memory leaves few worlds per SM and the equality sweep is twice as long at 8
+  // lanes (softbox_refined, 434 elements: 1.11e6 / 1.48e6 / 1.72e6 world-steps/s at 8 / 16 / 32 lanes, profiles/r02a_*)
+  b->kernel = 2; b->lpw = b->D.ns > 256 ? 32 : 8; b->nwarp = 16;
   int aux_in_smem = 0;
   if (const char* e = std::getenv("SOFTGRIP_LPW")) b->lpw = std::atoi(e);
   if (const char* e = std::getenv("SOFTGRIP_NW")) b->nwarp = std::atoi(e);
@@ -222,8 +225,14 @@ static int batch_create_body(const sg_model* m, int nworlds, int device, int pre
   if (b->lpw != 4 && b->lpw != 8 && b->lpw != 16 && b->lpw != 32) { return fail("SOFTGRIP_LPW must be 4, 8, 16 or 32"); }
   if (b->kernel == 2) {
     const Plan& P = m->plan;
+#if SG_EQ2 && SG_SLOT8
+    build_step_tables2(b->D, P.itab, b->lpw, (int)b->esize, b->step_d, b->row_perm, std::getenv("SOFTGRIP_NO_BANK_SCHEDULE") == nullptr);
+    b->step_iw.clear();
+    b->D.nstep = (int)(b->step_d.size() / (4 * (size_t)b->lpw)) - 1;   // two rows per slot; without the trailing dummy step
+#else
     build_step_tables(b->D, P.tab, P.itab, b->lpw, (int)b->esize, b->step_d, b->step_iw, b->row_perm, std::getenv("SOFTGRIP_NO_BANK_SCHEDULE") == nullptr);
     b->D.nstep = (int)(b->step_d.size() / (2 * (size_t)b->lpw)) - 1;   // without the trailing dummy step
+#endif
     b->D.o_step_iw = (int)((P.tab.size() + 3) / 4 * 4);
     b->D.io_step_d = (int)((P.itab.size() + 3) / 4 * 4);
   }
@@ -640,8 +649,16 @@ extern "C" int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int
     // host-side tables of the equality sweep (no device data): [nstep, lanes per world, bytes per real, nrow, estimated
     // shared-memory wavefronts per sweep], the slot descriptors (2 ints per slot, nstep + 1 steps), then the storage
     // position of every row (plan schedule order)
-    std::vector<double> t = {(double)b->D.nstep, (double)b->lpw, (double)b->esize, (double)b->D.nrow,
-                             (double)sweep_wavefronts(b->step_d, b->lpw, (int)b->esize)};
+    // (rows per slot: 2 when the sweep takes two rows per lane and step, SG_EQ2 -- then 4 ints per slot; it rides in the
+    // upper digits of the wavefront figure so that the header keeps its five entries)
+#if SG_EQ2 && SG_SLOT8
+    const int rows_per_slot = 2;
+    const long wf = sweep_wavefronts2(b->step_d, b->lpw, (int)b->esize);
+#else
+    const int rows_per_slot = 1;
+    const long wf = sweep_wavefronts(b->step_d, b->lpw, (int)b->esize);
+#endif
+    std::vector<double> t = {(double)b->D.nstep, (double)b->lpw, (double)b->esize, (double)b->D.nrow, (double)wf + 1e9 * rows_per_slot};
     for (int v : b->step_d) t.push_back((double)(unsigned)v);
     for (int v : b->row_perm) t.push_back((double)v);
     return put(t.data(), (int)t.size());

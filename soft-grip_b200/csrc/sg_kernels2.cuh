@@ -59,6 +59,11 @@ namespace sg {
 #define SG_BF_BLOCK 1
 #endif
 
+// broadphase: specialised chunk loop for runs of one collider against a range of capsules
+#ifndef SG_BP_LEAN
+#define SG_BP_LEAN 1
+#endif
+
 // 8-byte step slots / unit tendon coefficients for shells with uniform element mass (checked by the host, sg_api.cu)
 #ifndef SG_SLOT8
 #define SG_SLOT8 1
@@ -164,7 +169,7 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw
   }
   // CTA-shared tables: step slots | tendon coefficients, coefficient / mass, 1 / mass (ns each) | slider axes (3 ns) |
   // collider table | broadphase runs | row -> sliders
-  L.smem_tables = (int)(((size_t)(D.nstep + 1) * lpw * (SG_SLOT8 ? 8 : 8 + 2 * sizeof(T)) + (6 * (size_t)D.ns + (size_t)MAXCOLL * CO_STRIDE) * sizeof(T) +
+  L.smem_tables = (int)(((size_t)(D.nstep + 1) * lpw * ((SG_EQ2 && SG_SLOT8) ? 16 : SG_SLOT8 ? 8 : 8 + 2 * sizeof(T)) + (6 * (size_t)D.ns + (size_t)MAXCOLL * CO_STRIDE) * sizeof(T) +
                          (4 * (size_t)D.nrun + (size_t)D.nrow) * sizeof(int) + 127) & ~(size_t)127);
   return L;
 }
@@ -335,7 +340,14 @@ __device__ __forceinline__ float trsqrt(float x) {
 // normalised by trace(A); with w = adj(A + la) b, v = -w / det, every step needs |w|^2, det and w' adj w only, so its
 // three special-function ops (1/det, sqrt |w|^2, 1/(Q r)) are independent of each other, and the final rescaling is one
 // more reciprocal square root:  f = -w r / |w|  when the cone is active.
+#if defined(SG_FRIC_STATS) && !defined(__CUDA_ARCH__)
+static long sg_fric_evals = 0, sg_fric_calls = 0;     // development statistics under the emulator (Newton evaluations per call)
+#endif
 __device__ __forceinline__ void friction_fast(float& f1, float& f2, float& la_io, float A11i, float A12i, float A22i, float bc0, float bc1, float frc, float f0) {
+#if defined(SG_FRIC_STATS) && !defined(__CUDA_ARCH__)
+  sg_fric_calls++;
+  if ((sg_fric_calls & 0x3ffff) == 0) fprintf(stderr, "friction_fast: %ld calls, %.3f evaluations per call\n", sg_fric_calls, (double)sg_fric_evals / (double)sg_fric_calls);
+#endif
   const float d2 = frc * frc;
   float a11 = A11i * d2, a12 = A12i * d2, a22 = A22i * d2, b1 = bc0 * frc, b2 = bc1 * frc;
   if (a11 * a22 - a12 * a12 < 1e-10f) { f1 = 0; f2 = 0; la_io = 0; return; }       // mju_QCQP2: singular -> zero, inactive
@@ -353,6 +365,9 @@ __device__ __forceinline__ void friction_fast(float& f1, float& f2, float& la_io
 #endif
 #pragma unroll 1
   for (int iter = 0; iter < SG_X_FRIC_MAXIT; iter++) {
+#if defined(SG_FRIC_STATS) && !defined(__CUDA_ARCH__)
+    sg_fric_evals++;
+#endif
     const float c11 = a22 + la, c22 = a11 + la;
     const float det = c11 * c22 - a12 * a12;
     w1 = c11 * b1 - a12 * b2; w2 = c22 * b2 - a12 * b1;
@@ -412,7 +427,10 @@ template <> __device__ __forceinline__ void ldg2<double>(const double* p, double
 static_assert(MAXCD == 4, "finger chain blocks are loaded as 4-vectors");
 
 // one slot of the level-sweep step tables in shared memory (host encoding: sg_plan.hpp build_step_tables)
-#if SG_SLOT8
+#if SG_EQ2 && SG_SLOT8
+// two rows per lane and step (sg_plan.hpp build_step_tables2): {xA, yA, xB, yB}, one 128-bit shared-memory load
+template <typename T> struct alignas(16) Slot { unsigned x, y, xb, yb; };
+#elif SG_SLOT8
 // uniform shell (every slider has the same mass and tendon coefficient 1, as every MuJoCo composite has): the slot is the
 // 8-byte descriptor alone -- one 64-bit shared-memory load, two wavefronts per warp instead of four
 template <typename T> struct alignas(8) Slot { unsigned x, y; };
@@ -963,6 +981,44 @@ struct World2 {
       }
 #endif
       if (one) collider_pose(pa, c1, rot1);
+#if SG_BP_LEAN
+      if (one && (pt == PAIR_PLANE_CAPSULE || pt == PAIR_BOX_CAPSULE)) {
+        // one collider against a range of capsules (nearly every pair of the list): everything that does not depend on
+        // the capsule is hoisted out of the chunk loop -- the same tests in the same order, a third of the instructions
+        const bool plane = pt == PAIR_PLANE_CAPSULE;
+        const T rb2 = C.cap_r + C.cap_hl;
+        const T bound = co[CO_RBOUND] + rb2, bound2 = bound * bound;
+        const T nrm[3] = {rot1[2], rot1[5], rot1[8]};
+        const T hs[3] = {co[CO_SIZE] + C.cap_r, co[CO_SIZE + 1] + C.cap_r, co[CO_SIZE + 2] + C.cap_r};
+        const T* cen = scr(L.sc_cen);
+        for (int base = 0; base < total; base += LPW) {
+          const int j = base + sl, pb = b0 + j;
+          bool pass = false;
+          if (j < total) {
+            const T dif[3] = {cen[3 * pb] - c1[0], cen[3 * pb + 1] - c1[1], cen[3 * pb + 2] - c1[2]};
+            if (plane) pass = !(dot3(dif, nrm) > rb2);
+            else {
+              pass = !(dot3(dif, dif) > bound2);
+              if (pass) {
+                // mid-phase (prunes only): the capsule's bounding box in the frame of the box must overlap the box
+                T dl[3], al[3];
+                matTvec3(dl, rot1, dif);
+                matTvec3(al, rot1, sax + 3 * pb);
+#pragma unroll
+                for (int k = 0; k < 3; k++) if (tabs(dl[k]) > hs[k] + C.cap_hl * tabs(al[k])) pass = false;
+              }
+            }
+          }
+          const unsigned m = gballot(pass);
+          if (pass) {
+            const int slot = ncand + __popc(m & ((1u << sl) - 1));
+            if (slot < cand_cap) cand[slot] = pt | (pa << 3) | (pb << 8); else flags |= SG_ST_CON_FULL_BIT;
+          }
+          ncand += __popc(m);
+        }
+        continue;
+      }
+#endif
       for (int base = 0; base < total; base += LPW) {
         const int j = base + sl;
         int pb = b0 + j;
@@ -1140,7 +1196,7 @@ struct World2 {
 #pragma unroll 4
     for (int p = sl; p < D.nrow; p += LPW) {
       const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
-      T pos = qp[d1], vel = vp[d1], diag = siwt[d1];
+      T pos = qp[d1], vel = vp[d1], diag = siwt[d1];     // (dof_invweight0 is not bit-uniform over the sliders: table loads)
       if (d2 != 0xffff) { pos -= qp[d2]; vel -= vp[d2]; diag += siwt[d2]; }
       const T imp = impedance2<T>(C.eqj_si, pos);
       const T aref = -C.eqj_B * vel - C.eqj_K * imp * pos;
@@ -1662,6 +1718,64 @@ struct World2 {
   // Per row the sweep keeps (u, n) with u = R f - aref and n = -1 / (1/m1 + 1/m2 + R): the residual is a1 - a2 + u, the
   // force change dl = res * n, and since an (unclamped) equality row has zero residual right after its own update, the
   // new u is simply a2' - a1' -- neither R nor f is needed, and there is no division in the sweep.
+#if SG_EQ2 && SG_SLOT8
+  // Two rows per lane and step: row A, then row B on the same lane -- B is either the successor of A on its dependency chain
+  // (the shared slider's new acceleration is handed over in a register: flag bits 26..29 of yb) or an independent row.
+  // All shared-memory operands of both rows are loaded up front; A's stores precede B's, so a slider both rows update ends
+  // with B's value.  Half the steps of the one-row sweep, i.e. half the load -> flops -> store -> barrier latencies.
+  template <bool GATED>
+  __device__ __forceinline__ T equality_rows(bool done) {
+    const int nstep = D.nstep;
+    char* avb = reinterpret_cast<char*>(a() + D.nfd);
+    char* rwb = reinterpret_cast<char*>(hot);
+    T acc = 0;
+    const T iwu = stim[0];
+    Slot<T> sn = ld_slot<T>(slots);
+#pragma unroll 2
+    for (int st = 0; st < nstep; st++) {
+      const Slot<T> sc = sn;
+      sn = ld_slot<T>(slots + (st + 1) * LPW);
+      const unsigned oa2 = sc.x >> 16, ob2 = sc.xb >> 16;
+      const bool va = (sc.y & 0x40000000u) != 0u, ha2 = oa2 != 0xffffu;
+      const bool vb = (sc.yb & 0x40000000u) != 0u, hb2 = ob2 != 0xffffu;
+      T* pa1 = reinterpret_cast<T*>(avb + (sc.x & 0xffffu));
+      T* pa2 = reinterpret_cast<T*>(avb + oa2);
+      T* pra = reinterpret_cast<T*>(rwb + (sc.y & 0x3ffffffu));
+      T* pb1 = reinterpret_cast<T*>(avb + (sc.xb & 0xffffu));
+      T* pb2 = reinterpret_cast<T*>(avb + ob2);
+      T* prb = reinterpret_cast<T*>(rwb + (sc.yb & 0x3ffffffu));
+      T a1 = 0, a2 = 0, u = 0, n = 0, b1 = 0, b2 = 0, ub = 0, nb = 0;
+      if (va) { a1 = *pa1; ld2(pra, u, n); }
+      if (ha2) a2 = *pa2;
+      if (vb) { ld2(prb, ub, nb); if (!(sc.yb & 0x0c000000u)) b1 = *pb1; }
+      if (hb2 && !(sc.yb & 0x30000000u)) b2 = *pb2;
+      // row A
+      const T res = (a1 - a2) + u;
+      if (GATED) n = done ? T(0) : n;
+      const T dl = res * n;
+      acc += dl * res;
+      a1 += iwu * dl; a2 -= (ha2 ? iwu : T(0)) * dl;
+      T un = a2 - a1;
+      if (GATED) un = done ? u : un;
+      // row B, with A's results where the rows share a slider
+      b1 = (sc.yb & 0x04000000u) ? a1 : b1; b1 = (sc.yb & 0x08000000u) ? a2 : b1;
+      b2 = (sc.yb & 0x10000000u) ? a1 : b2; b2 = (sc.yb & 0x20000000u) ? a2 : b2;
+      const T resb = (b1 - b2) + ub;
+      if (GATED) nb = done ? T(0) : nb;
+      const T dlb = resb * nb;
+      acc += dlb * resb;
+      b1 += iwu * dlb; b2 -= (hb2 ? iwu : T(0)) * dlb;
+      T unb = b2 - b1;
+      if (GATED) unb = done ? ub : unb;
+      if (va) { *pra = un; *pa1 = a1; }
+      if (ha2) *pa2 = a2;
+      if (vb) { *prb = unb; *pb1 = b1; }
+      if (hb2) *pb2 = b2;
+      __syncwarp();
+    }
+    return T(-0.5) * acc;
+  }
+#else
   template <bool GATED>
   __device__ __forceinline__ T equality_rows(bool done) {
     const int nstep = D.nstep;
@@ -1674,7 +1788,12 @@ struct World2 {
     // one row per lane per step, a warp barrier where the schedule asks for one.  The next step's slot is fetched
     // before the barrier so that its latency overlaps this step's arithmetic.
     Slot<T> sn = ld_slot<T>(slots);
-#pragma unroll 2
+#ifndef SG_EQ_UNROLL
+#define SG_EQ_UNROLL 4   // measured: 1.202e7 / 1.200e7 / 1.227e7 world-steps/s at 1 / 2 / 4 (profiles/r02j_sweep.log)
+#endif
+#define SG_PRAGMA_(x) _Pragma(#x)
+#define SG_PRAGMA(x) SG_PRAGMA_(x)
+    SG_PRAGMA(unroll SG_EQ_UNROLL)
     for (int st = 0; st < nstep; st++) {
       const Slot<T> sc = sn;
       sn = ld_slot<T>(slots + (st + 1) * LPW);   // the table carries one empty step past the end
@@ -1719,6 +1838,7 @@ struct World2 {
     }
     return T(-0.5) * acc;
   }
+#endif
   __device__ __forceinline__ T equality_sweep(Tendon& tn, bool done) {
     const int ns = D.ns;
     T* av = a() + D.nfd;
@@ -1953,7 +2073,12 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
     Slot<T>* ss = reinterpret_cast<Slot<T>*>(smem_raw);
     const int nslot = (D.nstep + 1) * LPW;
     for (int i = threadIdx.x; i < nslot; i += blockDim.x) {
+#if SG_EQ2 && SG_SLOT8
+      Slot<T> t; t.x = (unsigned)K.itab[D.io_step_d + 4 * i]; t.y = (unsigned)K.itab[D.io_step_d + 4 * i + 1];
+      t.xb = (unsigned)K.itab[D.io_step_d + 4 * i + 2]; t.yb = (unsigned)K.itab[D.io_step_d + 4 * i + 3];
+#else
       Slot<T> t; t.x = (unsigned)K.itab[D.io_step_d + 2 * i]; t.y = (unsigned)K.itab[D.io_step_d + 2 * i + 1];
+#endif
 #if !SG_SLOT8
       t.iw1 = K.tab[D.o_step_iw + 2 * i]; t.iw2 = K.tab[D.o_step_iw + 2 * i + 1];
 #endif

@@ -207,24 +207,30 @@ def test_emulated_other_models_first_steps(emu, make_world, name):
 
 
 def _decode_schedule(env):
+    """-> nstep, lanes, bytes per real, nrow, modelled wavefronts, rows per slot (1 or 2), slots [nstep+1][lanes][2*rps], perm."""
     t = env.debug("sweep_schedule")
     nstep, lpw, esize, nrow = (int(x) for x in t[:4])
-    wavefronts = int(t[4])
-    sd = t[5:5 + 2 * (nstep + 1) * lpw].astype(np.uint64).reshape(nstep + 1, lpw, 2)
-    perm = t[5 + 2 * (nstep + 1) * lpw:].astype(int)
-    return nstep, lpw, esize, nrow, wavefronts, sd, perm
+    rps = int(t[4] // 1e9)
+    wavefronts = int(t[4] - 1e9 * rps)
+    n = 2 * rps * (nstep + 1) * lpw
+    sd = t[5:5 + n].astype(np.uint64).reshape(nstep + 1, lpw, 2 * rps)
+    perm = t[5 + n:].astype(int)
+    return nstep, lpw, esize, nrow, wavefronts, rps, sd, perm
 
 
-@pytest.mark.parametrize("model,lpw,prec", [("softbox", 8, 32), ("softbox", 4, 32), ("softbox", 16, 64), ("softball", 8, 32), ("softcylinder", 8, 64)])
+@pytest.mark.parametrize("model,lpw,prec", [("softbox", 8, 32), ("softbox", 4, 32), ("softbox", 16, 64), ("softball", 8, 32), ("softcylinder", 8, 64),
+                                            ("softbox_refined", 32, 32)])
 def test_equality_sweep_schedule_is_a_valid_gauss_seidel_order(emu, model, lpw, prec):
-    """Host logic of the equality sweep (sg_plan.hpp build_step_tables): every row is swept exactly once, rows of one step
-    share no slider, rows that share a slider keep MuJoCo's order with a barrier in between, the storage positions are a
-    permutation, and the conflict-aware schedule costs no more shared-memory wavefronts than the plain list schedule."""
+    """Host logic of the equality sweep (sg_plan.hpp build_step_tables / build_step_tables2): every row is swept exactly
+    once; within a step different lanes share no slider; a lane's second row (two rows per slot) may share sliders with its
+    own first row only, with the hand-over flags saying so; rows that share a slider keep MuJoCo's order (an earlier step,
+    or first / second row of one lane); the storage positions are a permutation; and the conflict-aware schedule costs no
+    more modelled shared-memory wavefronts than the plain list schedule."""
     import importlib
     mjcf = importlib.import_module("soft-grip_b200.mjcf")
     A = mjcf.load_blob(blob_path(model)).arrays
     env = emu.EmuBatch(blob_path(model), 2, prec=prec, lpw=lpw)
-    nstep, lpw_, esize, nrow, wavefronts, sd, perm = _decode_schedule(env)
+    nstep, lpw_, esize, nrow, wavefronts, rps, sd, perm = _decode_schedule(env)
     assert lpw_ == lpw and esize == prec // 8 and nrow == len(A["eq_obj1id"]) - 1
     assert sorted(perm.tolist()) == list(range(nrow))
     nfd = int((A["jnt_type"] == 3).sum())                      # hinge joints of the fingers come first
@@ -233,48 +239,56 @@ def test_equality_sweep_schedule_is_a_valid_gauss_seidel_order(emu, model, lpw, 
         d1, d2 = int(A["eq_obj1id"][r]) - nfd, int(A["eq_obj2id"][r])
         key_to_eq[(d1, d2 - nfd if d2 >= 0 else -1)] = r
     assert len(key_to_eq) == nrow
-    step_of, seen_pos, flags = {}, set(), []
+    posmask = 0x3fffffff if rps == 1 else 0x3ffffff
+    when, seen_pos = {}, set()                                 # row -> (step, lane, half)
     for s in range(nstep):
-        used = set()
-        flags.append(int(sd[s, 0, 1]) >> 31)
+        owner = {}                                             # slider -> lane that touches it in this step
         for k in range(lpw):
-            x, y = int(sd[s, k, 0]), int(sd[s, k, 1])
-            assert (y >> 31) == flags[-1]                      # the barrier flag is uniform over the step
-            if not (y >> 30) & 1:
-                continue
-            d1 = (x & 0xffff) // esize
-            d2 = (x >> 16) // esize if (x >> 16) != 0xffff else -1
-            pos = (y & 0x3fffffff) // (2 * esize)
-            assert pos not in seen_pos and 0 <= pos < nrow
-            seen_pos.add(pos)
-            assert d1 not in used and d2 not in used           # rows of a step touch disjoint sliders
-            used.add(d1)
-            if d2 >= 0:
-                used.add(d2)
-            r = key_to_eq[(d1, d2)]
-            assert r not in step_of
-            step_of[r] = s
-    assert len(step_of) == nrow and flags[-1] == 1
-    # the empty step past the end only pads the descriptor prefetch
-    assert all(not (int(sd[nstep, k, 1]) >> 30) & 1 for k in range(lpw))
+            first = None
+            for half in range(rps):
+                x, y = int(sd[s, k, 2 * half]), int(sd[s, k, 2 * half + 1])
+                if not (y >> 30) & 1:
+                    assert half == 0 or (y >> 26) == 0
+                    continue
+                assert half == 0 or first is not None         # a second row only behind a first one
+                d1 = (x & 0xffff) // esize
+                d2 = (x >> 16) // esize if (x >> 16) != 0xffff else -1
+                pos = (y & posmask) // (2 * esize)
+                assert pos not in seen_pos and 0 <= pos < nrow
+                seen_pos.add(pos)
+                for d in (d1, d2):
+                    if d >= 0:
+                        assert owner.setdefault(d, k) == k     # different lanes of a step touch disjoint sliders
+                if half == 1:
+                    fl = (y >> 26) & 15
+                    want = (1 if d1 == first[0] else 2 if d1 == first[1] else 0) | ((4 if d2 == first[0] else 8 if d2 == first[1] else 0) if d2 >= 0 else 0)
+                    assert fl == want, (s, k, fl, want)        # the hand-over flags name exactly the shared sliders
+                else:
+                    first = (d1, d2 if d2 >= 0 else -2)
+                r = key_to_eq[(d1, d2)]
+                assert r not in when
+                when[r] = (s, k, half)
+    assert len(when) == nrow
+    assert all(not (int(sd[nstep, k, 2 * h + 1]) >> 30) & 1 for k in range(lpw) for h in range(rps))   # padding step
     last = {}
     for r in range(nrow):                                      # MuJoCo's sequential order
         for d in (int(A["eq_obj1id"][r]) - nfd, int(A["eq_obj2id"][r]) - nfd if A["eq_obj2id"][r] >= 0 else None):
             if d is None:
                 continue
             if d in last:
-                q = last[d]
-                assert step_of[q] < step_of[r]
-                assert any(flags[s] for s in range(step_of[q], step_of[r]))
+                (sq, kq, hq), (sr, kr, hr) = when[last[d]], when[r]
+                assert sq < sr or (sq == sr and kq == kr and hq < hr)
             last[d] = r
     os.environ["SOFTGRIP_NO_BANK_SCHEDULE"] = "1"
     try:
         plain = emu.EmuBatch(blob_path(model), 2, prec=prec, lpw=lpw)
-        nstep0, _, _, _, wavefronts0, _, perm0 = _decode_schedule(plain)
+        nstep0, _, _, _, wavefronts0, _, _, perm0 = _decode_schedule(plain)
     finally:
         del os.environ["SOFTGRIP_NO_BANK_SCHEDULE"]
     assert perm0.tolist() == list(range(nrow))
-    assert wavefronts + 6 * nstep <= wavefronts0 + 6 * nstep0
+    assert wavefronts + (10 if rps == 2 else 6) * nstep <= wavefronts0 + (10 if rps == 2 else 6) * nstep0
+    if rps == 2 and model == "softbox" and lpw == 8:
+        assert nstep <= 36                                     # 53 dependency levels in about half the steps
 
 
 def test_removed_placement_options_fail_loudly(emu):
@@ -454,7 +468,7 @@ def test_emulated_larger_models_at_more_lanes_per_world(emu, make_world, name, l
         assert rel(q1[-1], oq) < 1e-8 and rel(v1[-1], ov) < 1e-8 and rel(qacc[-1], oacc) < 1e-8
         steps[lanes] = int(env.debug("sweep_schedule")[0])
         env.close()
-    assert steps[lpw] < 0.7 * steps[8], steps
+    assert steps[lpw] < 0.8 * steps[8], steps        # (two rows per slot: softball 55 -> 42 steps, refined 99 -> 63 / 56)
 
 
 def test_emulated_step_kernel_is_clean_under_asan(tmp_path):
@@ -479,3 +493,29 @@ def test_emulated_step_kernel_is_clean_under_asan(tmp_path):
                          capture_output=True, text=True, env=env, timeout=1200)
     assert out.returncode == 0 and "ASAN DRIVE DONE" in out.stdout, (out.stdout[-500:], out.stderr[-3000:])
     assert "ERROR: AddressSanitizer" not in out.stderr
+
+
+def test_launch_geometry_fills_every_sm_in_one_pass(emu):
+    """sg_batch_create picks the CTA size from the batch size: the emulated device has 2 SMs, so
+    112 softbox worlds run as 2 CTAs of 56 worlds (14 warps) in one pass rather than as 64 + 48, a batch that needs
+    several passes takes the largest CTA, a handful of worlds takes one small CTA -- and the bits do not depend on it."""
+    import ctypes as C
+
+    def geometry(W, nw=None):
+        env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=8, nw=nw)
+        out = (C.c_int * 8)()
+        assert env.L.sg_batch_config(env.b, out) == 0
+        return env, {"warps_per_cta": out[1], "worlds_per_cta": out[2]}
+
+    env, g = geometry(112)
+    assert g == {"warps_per_cta": 14, "worlds_per_cta": 56}
+    env.close()
+    env, g = geometry(1000)
+    assert g["warps_per_cta"] == 16
+    env.close()
+    env, g = geometry(3)
+    assert g["warps_per_cta"] == 1
+    env.close()
+    env, g = geometry(112, nw=16)                       # the development override still wins
+    assert g["warps_per_cta"] == 16
+    env.close()

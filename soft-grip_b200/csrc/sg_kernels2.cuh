@@ -34,34 +34,11 @@
 
 namespace sg {
 
-// software-pipelined contact records on the fp32 fast path (see chain_phase).  Measured slower (profiles/r02b_sweep.txt:
-// 1.006e7 against 1.141e7 world-steps/s): the second record costs 32 registers, the kernel spills 1.1 KB and every block
-// pays 32 register moves.  Off; kept as an A/B switch.
-#ifndef SG_PIPE_REC
-#define SG_PIPE_REC 0
-#endif
 
-// lean chain phase: record pointers from one byte base kept in registers, unconditional force updates, no run-time
-// placement tests (the once-per-step data always lives in the global scratch)
-#ifndef SG_LEAN_CHAIN
-#define SG_LEAN_CHAIN 1
-#endif
-
-// broadphase: runs of the pair list whose collider(s) cannot reach the bounding box of the capsule centres are skipped
-#ifndef SG_BP_CULL
-#define SG_BP_CULL 1
-#endif
-
-// contact block without data-dependent branches outside the friction solve (selects instead), the same code for chain and
-// static lanes (a static contact has a zero finger Jacobian and a zero chain acceleration), slider-less contacts go
-// through the dummy slider: two large basic blocks around the Newton loop, which the scheduler can overlap freely
-#ifndef SG_BF_BLOCK
-#define SG_BF_BLOCK 1
-#endif
-
-// broadphase: specialised chunk loop for runs of one collider against a range of capsules
-#ifndef SG_BP_LEAN
-#define SG_BP_LEAN 1
+// how many blocks ahead a chain lane prefetches its contact records into L1.  The L1 left beside 228 KB of shared memory
+// is 28 KB; 16 warps x 8 lanes x 128 B are 16 KB of records in flight per block of look-ahead.
+#ifndef SG_PF_DIST
+#define SG_PF_DIST 2      // 1 and 2 measure the same (profiles/r02o_sweep.log: 1.216e7 / 1.223e7)
 #endif
 
 // 8-byte step slots / unit tendon coefficients for shells with uniform element mass (checked by the host, sg_api.cu)
@@ -353,6 +330,9 @@ __device__ __forceinline__ void friction_fast(float& f1, float& f2, float& la_io
   if (a11 * a22 - a12 * a12 < 1e-10f) { f1 = 0; f2 = 0; la_io = 0; return; }       // mju_QCQP2: singular -> zero, inactive
   const float sc = trcp<float>(a11 + a22), rr = trcp<float>(f0);
   a11 *= sc; a12 *= sc; a22 *= sc; b1 *= sc; b2 *= sc;
+#ifndef SG_X_FRIC_MAXIT
+#define SG_X_FRIC_MAXIT 8          // (timing experiments only: a lower cap changes the results)
+#endif
   float lo = tfsqrt<float>(b1 * b1 + b2 * b2) * rr - 1.0f;               // lower bound |b|/r - trace of the root
   if (!(lo > 0.0f)) lo = 0.0f;
   // start from the root of the previous sweep (la_io, in the same normalised units; 0 on the first sweep) when it lies
@@ -360,9 +340,6 @@ __device__ __forceinline__ void friction_fast(float& f1, float& f2, float& la_io
   // (the tangent of the convex function lands left of the root, from where the iterates rise monotonically)
   float la = fmaxf(lo, la_io);
   float w1 = 0, w2 = 0, rdet = 0, N2 = 0;
-#ifndef SG_X_FRIC_MAXIT
-#define SG_X_FRIC_MAXIT 8          // (timing experiments only: a lower cap changes the results)
-#endif
 #pragma unroll 1
   for (int iter = 0; iter < SG_X_FRIC_MAXIT; iter++) {
 #if defined(SG_FRIC_STATS) && !defined(__CUDA_ARCH__)
@@ -908,9 +885,7 @@ struct World2 {
   __device__ void collide() {
     const bool dbg = valid && (w == K.debug_world);
     // ---- capsule centres into the scratch (the sliders only move along their axes) ----
-#if SG_BP_CULL
     T blo[3] = {T(SG_MAXVAL), T(SG_MAXVAL), T(SG_MAXVAL)}, bhi[3] = {-T(SG_MAXVAL), -T(SG_MAXVAL), -T(SG_MAXVAL)};
-#endif
     {
       const T* __restrict__ qsl = q() + D.nfd;
       const T* __restrict__ c0 = tab(D.o_sl_cap0);
@@ -922,13 +897,10 @@ struct World2 {
         for (int k = 0; k < 3; k++) {
           const T ck = off[k] + c0[3 * e + k] + sax[3 * e + k] * qe;
           cen[3 * e + k] = ck;
-#if SG_BP_CULL
           blo[k] = ck < blo[k] ? ck : blo[k]; bhi[k] = ck > bhi[k] ? ck : bhi[k];     // a NaN centre leaves the bounds alone
           if (!(ck == ck)) { blo[k] = -T(SG_MAXVAL); bhi[k] = T(SG_MAXVAL); }          // ... so it opens them explicitly
-#endif
         }
       }
-#if SG_BP_CULL
       // bounding box of the capsule centres of this world (sub-warp min / max)
 #pragma unroll
       for (int k = 0; k < 3; k++)
@@ -937,7 +909,6 @@ struct World2 {
           const T l2 = __shfl_xor_sync(FULLMASK, blo[k], o), h2 = __shfl_xor_sync(FULLMASK, bhi[k], o);
           blo[k] = l2 < blo[k] ? l2 : blo[k]; bhi[k] = h2 > bhi[k] ? h2 : bhi[k];
         }
-#endif
       __syncwarp();
     }
     // ---- broadphase: bounding spheres, candidates compacted in pair order.  The pair list is walked by runs
@@ -952,7 +923,6 @@ struct World2 {
       int pa = a0;
       const T* co = scoll + pa * CO_STRIDE;
       T c1[3], rot1[9];
-#if SG_BP_CULL
       if (pt == PAIR_PLANE_CAPSULE || pt == PAIR_BOX_CAPSULE) {
         // Can any capsule of the shell pass the bounding-sphere test against a collider of this run?  The test below is
         // |centre - c1|^2 <= (rb1 + rb2)^2 (plane: signed distance <= rb2); every centre lies in [blo, bhi], so a collider
@@ -979,9 +949,7 @@ struct World2 {
         // the loop below is full of warp collectives (the worlds of a warp ballot together): warp-uniform decision
         if (!__any_sync(FULLMASK, reach)) continue;
       }
-#endif
       if (one) collider_pose(pa, c1, rot1);
-#if SG_BP_LEAN
       if (one && (pt == PAIR_PLANE_CAPSULE || pt == PAIR_BOX_CAPSULE)) {
         // one collider against a range of capsules (nearly every pair of the list): everything that does not depend on
         // the capsule is hoisted out of the chunk loop -- the same tests in the same order, a third of the instructions
@@ -1018,7 +986,6 @@ struct World2 {
         }
         continue;
       }
-#endif
       for (int base = 0; base < total; base += LPW) {
         const int j = base + sl;
         int pb = b0 + j;
@@ -1431,9 +1398,12 @@ struct World2 {
     }
     f1 = vv[0]; f2 = vv[1];
   }
-  // one elliptic contact block (mj_solPGS inner body, dim 3) on the lane that owns its chain
-  // the 32 words of one contact record in registers
-  struct Rec { T jg[12], w1[4], w2[4], Aw[8], w3[4]; };
+  // One elliptic contact block (mj_solPGS inner body, dim 3) on the lane that owns its finger chain, or on one of the other
+  // lanes for a contact against a static collider.  No data-dependent branch outside the friction solve (selects instead),
+  // and one code path for both kinds of lane: a static contact has a zero finger Jacobian and the lane a zero chain
+  // acceleration, a contact without a slider goes through the dummy slider.  That leaves two large basic blocks around the
+  // Newton loop of the friction solve for the scheduler to interleave (profiles/r02e_sweep.txt: 1.193e7 -> 1.223e7).
+  struct Rec { T jg[12], w1[4], w2[4], Aw[8], w3[4]; };      // the 32 words of one contact record in registers
   __device__ __forceinline__ void load_rec(Rec& x, const T* r) const {
     ld4(r + CR_JG, x.jg); ld4(r + CR_JG + 4, x.jg + 4); ld4(r + CR_JG + 8, x.jg + 8);
     ld4(r + CR_NS, x.w1);          // ns0 ns1 ns2 iwe
@@ -1441,13 +1411,8 @@ struct World2 {
     ld4(r + CR_A, x.Aw); ld4(r + CR_A + 4, x.Aw + 4);   // A00 A01 A02 A11 | A12 A22 R1 e
     ld4(r + CR_F, x.w3);           // f0 f1 f2, friction multiplier of the previous sweep
   }
-  __device__ __forceinline__ T contact_block(T* r, int e, T* ag, bool has_chain, const T* mv) {
+  __device__ __forceinline__ T contact_block(T* r, int e, T* ag, const T* mv) {
     Rec x; load_rec(x, r);
-    return contact_block(x, r, e, ag, has_chain, mv);
-  }
-#if SG_BF_BLOCK
-  __device__ __forceinline__ T contact_block(const Rec& x, T* r, int e, T* ag, bool has_chain, const T* mv) {
-    (void)has_chain;
     // a contact without a slider (centre sphere) reads and writes the dummy slider: its ns and 1/m words are zero
     T* const pae = a() + D.nfd + (e >= 0 ? e : D.ns);
     const T ae = *pae;
@@ -1508,75 +1473,6 @@ struct World2 {
     }
     return change;
   }
-#else
-  __device__ __forceinline__ T contact_block(const Rec& x, T* r, int e, T* ag, bool has_chain, const T* mv) {
-    const int nfd = D.nfd;
-    T ae = 0;
-    if (e >= 0) ae = a()[nfd + e];
-    const T* jg = x.jg; const T* w1 = x.w1; const T* w2 = x.w2; const T* Aw = x.Aw; const T* w3 = x.w3;
-    const T A00 = Aw[0], A01 = Aw[1], A02 = Aw[2], A11 = Aw[3], A12 = Aw[4], A22 = Aw[5];
-    const T R0 = w2[3], R1 = Aw[6];
-    const T old0 = w3[0], old1 = w3[1], old2 = w3[2];
-    T la = w3[3];                // friction multiplier of the previous sweep (fp32 fast path's warm start)
-    T res[3];
-    const T Rr[3] = {R0, R1, R1};
-    const T fo[3] = {old0, old1, old2};
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      T s = Rr[k] * fo[k] - w2[k];
-      if (has_chain) {
-#pragma unroll
-        for (int jj = 0; jj < MAXCD; jj++) s += jg[4 * k + jj] * ag[jj];
-      }
-      res[k] = s + w1[k] * ae;      // the slider's acceleration arrives last (shared memory)
-    }
-    T f0 = old0, f1 = old1, f2 = old2;
-    if (f0 < T(SG_MINVAL)) {
-      f0 -= tdiv(res[0], A00);
-      if (f0 < T(0)) f0 = 0;
-      f1 = 0; f2 = 0;
-    } else {
-      const T v0 = f0, v1 = f1, v2 = f2;
-      const T x0 = A00 * v0 + A01 * v1 + A02 * v2, x1 = A01 * v0 + A11 * v1 + A12 * v2, x2 = A02 * v0 + A12 * v1 + A22 * v2;
-      const T denom = v0 * x0 + v1 * x1 + v2 * x2;
-      if (denom >= T(SG_MINVAL)) {
-        T x = -tdiv(v0 * res[0] + v1 * res[1] + v2 * res[2], denom);
-        if (f0 + x * v0 < T(0)) x = T(-1);
-        f0 += x * v0; f1 += x * v1; f2 += x * v2;
-      }
-    }
-    // friction update with the normal force fixed
-    {
-      T bc[2];
-      bc[0] = res[1] - (A11 * old1 + A12 * old2) + A01 * (f0 - old0);
-      bc[1] = res[2] - (A12 * old1 + A22 * old2) + A02 * (f0 - old0);
-      if (f0 < T(SG_MINVAL)) { f1 = 0; f2 = 0; la = 0; }
-      else friction(f1, f2, la, A11, A12, A22, bc, C.con_fr, f0);
-    }
-    // cost change, revert if positive
-    T d0f = f0 - old0, d1f = f1 - old1, d2f = f2 - old2;
-    T change = T(0.5) * (d0f * (A00 * d0f + A01 * d1f + A02 * d2f) + d1f * (A01 * d0f + A11 * d1f + A12 * d2f) + d2f * (A02 * d0f + A12 * d1f + A22 * d2f))
-             + d0f * res[0] + d1f * res[1] + d2f * res[2];
-    if (change > T(1e-10)) { f0 = old0; f1 = old1; f2 = old2; d0f = d1f = d2f = 0; change = 0; }
-    st4(r + CR_F, f0, f1, f2, la);
-    // qacc += M^-1 J^T delta (lean: unconditionally -- a zero change adds exact zeros)
-    if (SG_LEAN_CHAIN || d0f != T(0) || d1f != T(0) || d2f != T(0)) {
-      if (e >= 0) a()[nfd + e] = ae + (w1[0] * d0f + w1[1] * d1f + w1[2] * d2f) * w1[3];
-      if (has_chain) {
-        T gv[MAXCD];
-#pragma unroll
-        for (int jj = 0; jj < MAXCD; jj++) gv[jj] = jg[jj] * d0f + jg[4 + jj] * d1f + jg[8 + jj] * d2f;
-#pragma unroll
-        for (int ii = 0; ii < MAXCD; ii++) {
-          T m4[4]; ld4(mv + 4 * ii, m4);
-          ag[ii] += m4[0] * gv[0] + m4[1] * gv[1] + m4[2] * gv[2] + m4[3] * gv[3];
-        }
-      }
-    }
-    return change;
-  }
-
-#endif
 
   // ---- limit / contact rows: swept by the lane that owns the finger chain (plus a share of the static contacts) ----
   struct ChainState {
@@ -1607,8 +1503,11 @@ struct World2 {
   }
   // one sweep over this lane's limit rows and contact blocks (time slots 1..tmaxw, a warp barrier after each);
   // returns the lane's cost improvement.  The contact records live in the L2-resident scratch: the lane's schedule
-  // entries are fetched three blocks ahead (registers) and the 128-byte record of the next block is prefetched into
-  // L1 when the current block starts, so that no block waits for two dependent L2 round trips.
+  // entries are fetched three blocks ahead (registers) and the 128-byte record of a later block is prefetched into
+  // L1 when the current block starts, so that no block waits for two dependent L2 round trips.  (Measured neutral
+  // or worse and removed again: records staged in registers one block ahead -- 1.1 KB of spills, -12 %; helper lanes
+  // handing records over by shuffles, round 1; a reordered friction solve and a speculative M^-1 J' update -- the chain
+  // phase sits where issue slots (4 warps x ~120 000 instructions per step) and single-warp latency (~540 000 cycles) meet.)
   __device__ T chain_phase(ChainState& cs, int tmaxw, bool done) {
     T impr = 0;
     const int* order = auxi + L.i_order + cs.mystart;
@@ -1618,12 +1517,7 @@ struct World2 {
     if (cnt > 1) entB = order[1];
     if (cnt > 2) entC = order[2];
     const int ent0 = entA;
-#if SG_PIPE_REC
-    Rec cur;
-    if (sizeof(T) == 4) { if (cnt > 0) load_rec(cur, crec(entA & 0xff)); }
-    else
-#endif
-    if (cnt > 1 && !L.aux_in_smem) prefetch_l1(crec(entB & 0xff));
+    if (cnt > 1) prefetch_l1(crec(entB & 0xff));
     if (cs.chain_lane && !done) {
 #pragma unroll
       for (int jl = 0; jl < MAXCD; jl++) {
@@ -1646,29 +1540,6 @@ struct World2 {
       }
     }
     int k = 0;
-#if SG_PIPE_REC
-    if (sizeof(T) == 4) {
-      // fp32 fast path: the record of the lane's NEXT block is loaded into registers while the current block runs (32 words
-      // in flight per lane), so a block never waits for the L2 round trip of its own record; the first record of a sweep
-      // was requested before the limit rows above
-      for (int t = 1; t <= tmaxw; t++) {
-        if (k < cnt && ((entA >> 8) & 0xff) == t) {
-          T* r = crec(entA & 0xff);
-          const int e = (entA >> 16) - 1;
-          k++;
-          entA = entB; entB = entC;
-          const bool more = k < cnt;
-          Rec nxt;
-          if (more) load_rec(nxt, crec(entA & 0xff));
-          if (k + 2 < cnt) entC = order[k + 2];
-          impr -= contact_block(cur, r, e, cs.ag, cs.chain_lane, cs.mv);
-          if (more) cur = nxt;
-        }
-        __syncwarp();
-      }
-    } else
-#endif
-#if SG_LEAN_CHAIN
     {
       // one byte base for the records of this world; an entry's record is base + index * 128 (CR_STRIDE reals)
       unsigned char* const recb = reinterpret_cast<unsigned char*>(aux + L.crec);
@@ -1678,30 +1549,20 @@ struct World2 {
           T* r = reinterpret_cast<T*>(recb + (size_t)((unsigned)(entA & 0xff) * RB));
           const int e = (entA >> 16) - 1;
           k++;
+#if SG_PF_DIST == 1
+          if (k < cnt) prefetch_l1(recb + (size_t)((unsigned)(entB & 0xff) * RB));       // the next block's record
+#else
           if (k + 1 < cnt) prefetch_l1(recb + (size_t)((unsigned)(entC & 0xff) * RB));   // two blocks ahead, as the entries
+#endif
           const int entD = (k + 2 < cnt) ? order[k + 2] : 0;
-          impr -= contact_block(r, e, cs.ag, cs.chain_lane, cs.mv);
+          impr -= contact_block(r, e, cs.ag, cs.mv);
           entA = entB; entB = entC; entC = entD;
         }
         __syncwarp();
       }
     }
-#else
-    for (int t = 1; t <= tmaxw; t++) {
-      if (k < cnt && ((entA >> 8) & 0xff) == t) {
-        T* r = crec(entA & 0xff);
-        const int e = (entA >> 16) - 1;
-        k++;
-        entA = entB; entB = entC;
-        if (k + 1 < cnt && !L.aux_in_smem) prefetch_l1(crec(entB & 0xff));
-        if (k + 2 < cnt) entC = order[k + 2];
-        impr -= contact_block(r, e, cs.ag, cs.chain_lane, cs.mv);
-      }
-      __syncwarp();
-    }
-#endif
     // next sweep's first entries and record: towards L1 while the equality block is swept
-    if (cnt > 0 && !L.aux_in_smem) { prefetch_l1(order); prefetch_l1(crec(ent0 & 0xff)); }
+    if (cnt > 0) { prefetch_l1(order); prefetch_l1(crec(ent0 & 0xff)); }
     return impr;
   }
   __device__ void chain_epilogue(const ChainState& cs) {
@@ -1798,15 +1659,6 @@ struct World2 {
       const Slot<T> sc = sn;
       sn = ld_slot<T>(slots + (st + 1) * LPW);   // the table carries one empty step past the end
       const unsigned o2 = sc.x >> 16;
-#if SG_EQ_NOPRED && SG_SLOT8
-      // unpredicated: padding slots and the second slider of fix rows address dummies that stay 0 (sg_plan.hpp emit)
-      const bool valid = true, has2 = o2 != (unsigned)(D.ns * sizeof(T));
-      T* pa1 = reinterpret_cast<T*>(avb + (sc.x & 0xffffu));
-      T* pa2 = reinterpret_cast<T*>(avb + o2);
-      T* pr = reinterpret_cast<T*>(rwb + (sc.y & 0x3fffffffu));
-      T a1 = *pa1, a2 = *pa2, u, n;
-      ld2(pr, u, n);
-#else
       const bool valid = (sc.y & 0x40000000u) != 0u, has2 = o2 != 0xffffu;     // padding slot / fix row: predicated off
       T* pa1 = reinterpret_cast<T*>(avb + (sc.x & 0xffffu));
       T* pa2 = reinterpret_cast<T*>(avb + o2);
@@ -1814,7 +1666,6 @@ struct World2 {
       T a1 = 0, a2 = 0, u = 0, n = 0;
       if (valid) { a1 = *pa1; ld2(pr, u, n); }
       if (has2) a2 = *pa2;
-#endif
       const T res = (a1 - a2) + u;
       if (GATED) n = done ? T(0) : n;
       const T dl = res * n;
@@ -1826,12 +1677,8 @@ struct World2 {
 #endif
       T un = a2 - a1;
       if (GATED) un = done ? u : un;
-#if SG_EQ_NOPRED && SG_SLOT8
-      *pr = un; *pa1 = a1; *pa2 = a2;
-#else
       if (valid) { *pr = un; *pa1 = a1; }
       if (has2) *pa2 = a2;
-#endif
       // nearly every step of the 8-lane schedules ends a dependency level: an unconditional barrier is cheaper than
       // testing the flag; narrower worlds have runs of independent steps that are allowed to overlap
       if (LPW >= 8 || (int)sc.y < 0) __syncwarp();

@@ -13,10 +13,6 @@
 #ifndef SG_EQ2
 #define SG_EQ2 0
 #endif
-// unpredicated equality sweep (see sg_kernels2.cuh equality_rows); needs SG_SLOT8
-#ifndef SG_EQ_NOPRED
-#define SG_EQ_NOPRED 0
-#endif
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -245,19 +241,10 @@ inline int build_step_tables_for(const PlanDims& D, const std::vector<double>& t
   } else for (int p = 0; p < nrow; p++) perm[p] = p;
   auto emit = [&](int p, int fl) {
     unsigned x = 0xffffffffu, y = (unsigned)fl << 31; double iw1 = 0, iw2 = 0;
-#if SG_EQ_NOPRED
-    // unpredicated sweep: padding slots address the dummy slider (index ns, always 0) twice and the dummy row pair
-    // (position nrow: u = 0, n = -1); the missing second slider of a fix row is the dummy slider as well
-    const unsigned dummy = (unsigned)(D.ns * esize);
-    x = dummy | (dummy << 16); y = (unsigned)(nrow * 2 * esize);
-#endif
     if (p >= 0) {
       const int d1 = itab[D.io_row_d1 + p], d2 = itab[D.io_row_d2 + p];
       iw1 = 1.0 / tab[D.o_sl_m + d1];
       unsigned o2 = 0xffffu;
-#if SG_EQ_NOPRED
-      o2 = dummy;
-#endif
       if (d2 >= 0) { o2 = (unsigned)(d2 * esize); iw2 = 1.0 / tab[D.o_sl_m + d2]; }
       x = (unsigned)(d1 * esize) | (o2 << 16);
       y = ((unsigned)fl << 31) | (unsigned)(perm[p] * 2 * esize) | (1u << 30);

@@ -332,3 +332,58 @@ def test_bench_world_params_do_not_depend_on_the_sharding():
     assert ds is None and offs is None
     args.fixed_stiffness = 700.0
     assert np.all(bench.world_params(args, np.arange(8), 0)[0] == 700.0)
+
+
+def test_regenerate_multi_rank_noise_flags_and_statistics(tmp_path):
+    """the multi-rank path passes the noise seed to the */train files (a draw depends on the global world id only, so
+    the merged file equals the single-rank one), counts every status flag, drops every flagged world, and writes the per-file
+    statistics on rank 0 after the merge; a rollouts object with `prefetch` is asked for every shape once (stub rollouts)."""
+    rg, ds, batched = pkg("regenerate"), pkg("dataset"), pkg("batched")
+    tag = {"softball": 0.0, "softbox": 10000.0, "softcylinder": 20000.0}
+
+    class Rollouts:
+        def __init__(self):
+            self.calls, self.prefetched = [], []
+
+        def prefetch(self, files):
+            self.prefetched.append(sorted({shape for _, parts in files for shape, _, _ in parts}))
+
+        def __call__(self, shape, first, count, noise_seed=None):
+            self.calls.append((shape, first, count, noise_seed))
+            ids = np.arange(first, first + count)
+            k = batched.world_uniform(3, ids, 300.0, 1400.0)
+            x = np.broadcast_to(k[:, None, None], (count, 200, 12)) + tag[shape]
+            if noise_seed is not None:                       # stand-in for the device noise: a function of (seed, shape, world id)
+                x = x + (noise_seed + 1) * 1e-3 * (ids[:, None, None] % 17)
+            st = np.where(ids % 6 == 1, 1, 0) | np.where(ids % 10 == 3, 2, 0) | np.where(ids % 15 == 7, 8, 0)
+            yield x, k, st
+
+    one = Rollouts()
+    single = rg.regenerate(str(tmp_path / "one"), 11, 5, 4, one, log=lambda *_: None, noise_seed=5)
+    assert one.prefetched == [["softball", "softbox", "softcylinder"]]
+    many = Rollouts()
+    stems = None
+    for r in range(3):
+        stems = rg.regenerate_shard(str(tmp_path / "many"), 11, 5, 4, many, r, 3, noise_seed=5)
+    merged = rg.merge_shards(str(tmp_path / "many"), stems, 3, ds)
+    noisy = {c[:3] for c in many.calls if c[3] == 5}
+    assert noisy and all(c[3] is None or c[3] == 5 for c in many.calls)
+    for m, s1 in zip(merged, single):
+        xa, ya = ds.read_pickle(s1["file"])
+        xb, yb = ds.read_pickle(m["file"])
+        assert (xa == xb).all() and (ya == yb).all()
+        for key in ("diverged", "capacity", "unsupported", "dropped", "samples"):
+            assert m[key] == s1[key], (m["file"], key)
+        sa, sb = np.load(s1["file"].replace(".pickle", ".stats.npz")), np.load(m["file"].replace(".pickle", ".stats.npz"))
+        assert int(sb["n"]) == m["samples"] and int(sb["dropped"]) == m["dropped"]
+        np.testing.assert_allclose(sb["mean"], xb.mean(axis=(0, 1)), rtol=1e-12)
+        np.testing.assert_allclose(sb["std"], xb.std(axis=(0, 1)), rtol=1e-12)
+    # flagged worlds (any of the three bits) are not in the files
+    x, k = ds.read_pickle(single[0]["file"])                # sim_box/train: softbox worlds 0..10
+    ids = np.arange(11)
+    keep = (ids % 6 != 1) & (ids % 10 != 3) & (ids % 15 != 7)
+    assert len(k) == int(keep.sum()) and single[0]["dropped"] == int((~keep).sum())
+    # per-shape stiffness streams (DeviceRollouts.shape_seed): the three shapes do not share a label vector
+    dr = rg.DeviceRollouts.__new__(rg.DeviceRollouts)
+    dr.seed = 0
+    assert len({dr.shape_seed(s) for s in rg.SHAPES}) == 3

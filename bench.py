@@ -335,27 +335,33 @@ def workload_config(args, worlds_total, per_gpu, note=None):
 def measure_traj_kernels(torch, traj, flush, hbm_peak, reps=5):
     """Outside the timed region, N = 1 only: the HBM-bound kernels that post-process the trajectory buffer where the rollout
     left it (csrc/sg_traj.cuh: noise augmentation, channel statistics), each timed alone with CUDA events on the current
-    stream after an L2 flush; achieved = algorithmic bytes (noise: read + write, statistics: read) / average launch time.
+    stream after an L2 flush, four calls per timed region on a tensor several times the size of L2; achieved = algorithmic
+    bytes (noise: read + write, statistics: read) / average time per call.
     Extra information next to the headline numbers: a failure here is reported in the key, never raised."""
     try:
         fn = importlib.import_module("soft-grip_b200.functions")
         out = torch.empty_like(traj)
         nbytes = traj.numel() * traj.element_size()
+        ws, st_out = fn.stats_workspace(traj), torch.empty((2, traj.shape[-1]), dtype=torch.float64, device=traj.device)
+        # buffers are allocated once, outside the timed region: what is timed is the launch(es) of the C-ABI call
         cases = (("sg_traj_noise_kernel<float>", lambda: fn.noised_modality(traj, seed=1, out=out), 2 * nbytes),
-                 ("sg_traj_stats_partial_kernel<float> + final", lambda: fn.channel_mean_std(traj), nbytes))
+                 ("sg_traj_stats_partial_kernel<float> + final", lambda: fn.channel_mean_std(traj, workspace=ws, out=st_out), nbytes))
         res = {}
         for name, f, algo in cases:
             ms = []
+            calls = 4          # per timed region: the 629 MB tensor is several times the 126 MB L2, so back-to-back passes stream from
+                               # HBM every time, and the host-side cost of a call overlaps the previous launch
             for r in range(reps + 2):
                 flush.fill_(r & 255)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize()
                 e0.record()
-                f()
+                for _ in range(calls):
+                    f()
                 e1.record()
                 torch.cuda.synchronize()
                 if r >= 2:
-                    ms.append(e0.elapsed_time(e1))
+                    ms.append(e0.elapsed_time(e1) / calls)
             avg = sum(ms) / len(ms)
             gbs = algo / (avg * 1e-3) / 1e9
             res[name] = {"ms": avg, "algorithmic_bytes": algo, "achieved_GBps": gbs, "peak_GBps": hbm_peak, "frac": gbs / hbm_peak}

@@ -730,10 +730,14 @@ static int traj_noise_launch(const void* in, void* out, long long nrows, long lo
   const long long nquad = A.nelem / 4;
   long long grid = (nquad + block - 1) / block;
   auto kp = sg_traj_noise_kernel<T>;
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kp, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  static std::atomic<int> occ{0};                     // resident CTAs per SM of this instantiation (asked once)
+  int per_sm = occ.load(std::memory_order_relaxed);
+  if (!per_sm) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kp, block, 3 * 64 * sizeof(T)) != cudaSuccess || per_sm < 1) per_sm = 1;
+    occ.store(per_sm, std::memory_order_relaxed);
+  }
   if (grid > (long long)sms * per_sm) grid = (long long)sms * per_sm;   // exactly one resident wave, grid-stride beyond that
-  SG_LAUNCH(kp, (int)grid, block, 0, (cudaStream_t)stream, A);
+  SG_LAUNCH(kp, (int)grid, block, (size_t)3 * nchan * sizeof(T), (cudaStream_t)stream, A);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -769,11 +773,16 @@ static int traj_stats_grid(int nchan, long long nrows, int sms, int precision) {
   const int block = traj_stats_block(nchan);
   const long long nquad = nrows * (nchan / 4);
   long long grid = (nquad + block - 1) / block;
-  int per_sm = 0;
-  const size_t smem = (size_t)block * 8 * sizeof(double);
-  const cudaError_t e = precision == 32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_traj_stats_partial_kernel<float>, block, smem)
-                                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_traj_stats_partial_kernel<double>, block, smem);
-  if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+  static std::atomic<int> occ[2][17];                // [precision][block / 32]: asked once per instantiation and block size
+  std::atomic<int>& slot = occ[precision == 32 ? 0 : 1][(block / 32) & 15];
+  int per_sm = slot.load(std::memory_order_relaxed);
+  if (!per_sm) {
+    const size_t smem = (size_t)block * 8 * sizeof(double);
+    const cudaError_t e = precision == 32 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_traj_stats_partial_kernel<float>, block, smem)
+                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_traj_stats_partial_kernel<double>, block, smem);
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+    slot.store(per_sm, std::memory_order_relaxed);
+  }
   const long long cap = (long long)sms * per_sm;
   if (grid > cap) grid = cap;
   return (int)(grid < 1 ? 1 : grid);

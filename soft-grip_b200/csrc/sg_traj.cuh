@@ -105,27 +105,42 @@ struct TrajNoiseArgs {
   const double* stdev;
 };
 
+// per-channel constants in shared memory (kernel prologue): sigma, and for the fused standardisation mean and 1 / std in the
+// batch precision -- one 128-bit shared-memory load per table and quad instead of a compare + select per element, two
+// fp64 loads, two conversions and a division per element
 template <typename T>
-__device__ __forceinline__ void traj_noise_quad(const TrajNoiseArgs<T>& A, Vec4<T>& v, long long q, int g) {
+__device__ __forceinline__ void traj_noise_quad(const TrajNoiseArgs<T>& A, const T* tabs, Vec4<T>& v, long long q, int g) {
   const unsigned long long ctr = A.first_quad + (unsigned long long)q;
   const Philox4 r = philox4x32_10(Philox4{(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u}, A.k0, A.k1);
   float z[4];
   box_muller(r.x, r.y, z[0], z[1]);
   box_muller(r.z, r.w, z[2], z[3]);
   const int c0 = g * 4;
+  const Vec4<T> sig = load4(tabs + c0);
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const int c = c0 + j;
-    T x = v.v[j] + (T)(c < A.nacc ? A.sigma_acc : A.sigma_gyro) * (T)z[j];
-    if (A.mean) x = (x - (T)A.mean[c]) / (T)A.stdev[c];
-    v.v[j] = x;
+  for (int j = 0; j < 4; j++) v.v[j] += sig.v[j] * (T)z[j];
+  if (A.mean) {
+    const Vec4<T> m = load4(tabs + A.nchan + c0), is = load4(tabs + 2 * A.nchan + c0);
+#pragma unroll
+    for (int j = 0; j < 4; j++) v.v[j] = (v.v[j] - m.v[j]) * is.v[j];
   }
 }
 
-// Two quads per thread and iteration, both loads issued before any arithmetic: with 2 048 resident threads per SM that is
-// 64 KB of reads in flight per SM, enough to cover the HBM latency at the measured bandwidth.
+// Two quads per thread and iteration, both loads issued before any arithmetic.  (Measured and dropped again,
+// profiles/r02r_traj_bench.jsonl: issuing the NEXT iteration's loads before the arithmetic of the current one -- 0.69 of the
+// roof in fp32 instead of 0.68, but 0.79 instead of 0.90 in fp64 -- and 8 instead of 6 resident CTAs per SM at 32 registers:
+// 0.67.  The fp32 instance is bound by neither issue slots (62 %) nor HBM (55 %) alone: ~150 instructions per quad, a third
+// of them 32-bit multiplies of the ten Philox rounds, leave the two streams imperfectly overlapped.)
 template <typename T>
 __global__ void __launch_bounds__(256) sg_traj_noise_kernel(const __grid_constant__ TrajNoiseArgs<T> A) {
+  SG_SHARED_BYTES(smem_raw);
+  T* tabs = (T*)smem_raw;                                // [3][nchan]: sigma | mean | 1 / std
+  for (int c = threadIdx.x; c < A.nchan; c += blockDim.x) {
+    tabs[c] = (T)(c < A.nacc ? A.sigma_acc : A.sigma_gyro);
+    tabs[A.nchan + c] = A.mean ? (T)A.mean[c] : T(0);
+    tabs[2 * A.nchan + c] = A.mean ? T(1) / (T)A.stdev[c] : T(1);
+  }
+  __syncthreads();
   const long long nquad = A.nelem >> 2, stride = (long long)gridDim.x * blockDim.x;
   const int qpr = A.nchan >> 2;
   const long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,9 +154,9 @@ __global__ void __launch_bounds__(256) sg_traj_noise_kernel(const __grid_constan
     if (hb) vb = load4(A.in + 4 * qb);
     int gb = g + gstep;
     if (gb >= qpr) gb -= qpr;
-    traj_noise_quad(A, va, q, g);
+    traj_noise_quad(A, tabs, va, q, g);
     store4(A.out + 4 * q, va);
-    if (hb) { traj_noise_quad(A, vb, qb, gb); store4(A.out + 4 * qb, vb); }
+    if (hb) { traj_noise_quad(A, tabs, vb, qb, gb); store4(A.out + 4 * qb, vb); }
     g = gb + gstep;
     if (g >= qpr) g -= qpr;
   }

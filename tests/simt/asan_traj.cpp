@@ -16,16 +16,16 @@ template <typename T> void run(int W, int Tn, int nchan, int grid) {
   TrajNoiseArgs<T> A; A.in = in; A.out = out; A.nelem = nel; A.nchan = nchan; A.nacc = nchan / 2; A.sigma_acc = 0.7f; A.sigma_gyro = 0.06f;
   A.k0 = 1; A.k1 = 2; A.first_quad = 12345; A.mean = mean; A.stdev = sd;
   auto kn = sg_traj_noise_kernel<T>;
-  simt::launch(kn, grid, 256, 0, A);
+  simt::launch(kn, grid, 256, (size_t)3 * nchan * sizeof(T), A);        // exact-size dynamic shared memory: sigma | mean | 1 / std
   A.mean = nullptr; A.stdev = nullptr;
-  simt::launch(kn, grid, 256, 0, A);
+  simt::launch(kn, grid, 256, (size_t)3 * nchan * sizeof(T), A);
   // stats
   const int qpr = nchan / 4; int l = 32; while (l % qpr) l += 32; int block = l; while (block + l <= 384) block += l;
   TrajStatsArgs<T> S; S.in = in; S.nrows = rows; S.nchan = nchan; S.nblocks = grid;
   S.partial = (double*)malloc(sizeof(double) * grid * 2 * nchan); S.mean = mean; S.stdev = sd;
   auto k1 = sg_traj_stats_partial_kernel<T>; auto k2 = sg_traj_stats_final_kernel<T>;
   simt::launch(k1, grid, block, (size_t)block * 64, S);
-  simt::launch(k2, 1, 64, 0, S);
+  simt::launch(k2, 1, TRAJ_STATS_FINAL_THREADS, (size_t)(TRAJ_STATS_FINAL_THREADS / (2 * nchan)) * 2 * nchan * sizeof(double), S);
   // mask
   int* touch = (int*)malloc(sizeof(int) * rows); for (long long i = 0; i < rows; i++) touch[i] = (int)((i * 7) % 4) | ((i % 3) ? (1 << 30) : 0);
   int* fl = (int*)malloc(sizeof(int) * W); for (int w = 0; w < W; w++) fl[w] = 3;

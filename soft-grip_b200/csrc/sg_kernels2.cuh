@@ -52,8 +52,12 @@ namespace sg {
 #endif
 
 // contact record: 32 words of T, 16-byte aligned groups
-enum { CR_JG = 0 /*12*/, CR_NS = 12 /*3*/, CR_IWE = 15, CR_AREF = 16 /*3*/, CR_R0 = 19, CR_A = 20 /*6: 00 01 02 11 12 22*/,
-       CR_R1 = 26, CR_E = 27 /*slider index as a real, -1: none*/, CR_F = 28 /*3, then the friction multiplier*/, CR_STRIDE = 32 };
+// Words 15, 26, 27 carry the tangential 2x2 block the way the friction solve wants it -- scaled by the friction coefficient and
+// normalised by its trace (a22n = 1 - a11n), and the matching scale of the right-hand side -- so that none of it is redone
+// in each of the 30 sweeps; kb = 0 marks a singular block (mju_QCQP2: zero friction).  R1 = R0 / impratio and the slider's
+// 1 / m, which used to sit there, are a multiply resp. one shared-memory load away.
+enum { CR_JG = 0 /*12*/, CR_NS = 12 /*3*/, CR_A12N = 15, CR_AREF = 16 /*3*/, CR_R0 = 19, CR_A = 20 /*6: 00 01 02 11 12 22*/,
+       CR_A11N = 26, CR_KB = 27, CR_F = 28 /*3, then the friction multiplier*/, CR_STRIDE = 32 };
 
 // per-world memory plan.  Offsets are in elements (T for the real arrays, int for the int arrays).
 struct Layout2 {
@@ -154,7 +158,7 @@ inline Layout2 make_layout2(const PlanDims& D, int aux_in_smem, int wpw, int lpw
 // model constants in kernel precision
 template <typename T>
 struct Cst {
-  T h, g[3], tol, impratio, impr_scale;
+  T h, g[3], tol, impratio, inv_impratio, impr_scale;
   T eqj_K, eqj_B, eqj_si[7];
   T eqt_K, eqt_B, eqt_si[7], ten_iw, ten_k0, ten_d0, ten_lspring, ten_l0;
   T lim_K, lim_B, lim_si[7];
@@ -174,6 +178,7 @@ inline Cst<T> make_cst(const PlanDims& D) {
   Cst<T> C{};
   C.h = (T)D.h; for (int k = 0; k < 3; k++) { C.g[k] = (T)D.g[k]; C.sph_pos[k] = (T)D.sph_pos[k]; C.obj_pos[k] = (T)D.obj_pos[k]; }
   C.tol = (T)D.tol; C.impratio = (T)D.impratio; C.impr_scale = (T)D.impr_scale;
+  C.inv_impratio = (T)(1.0 / (D.impratio > SG_MINVAL ? D.impratio : SG_MINVAL));
   C.eqj_K = (T)D.eqj_K; C.eqj_B = (T)D.eqj_B; fill_si(C.eqj_si, D.eqj_solimp);
   C.eqt_K = (T)D.eqt_K; C.eqt_B = (T)D.eqt_B; fill_si(C.eqt_si, D.eqt_solimp);
   C.ten_iw = (T)D.ten_iw; C.ten_k0 = (T)D.ten_k0; C.ten_d0 = (T)D.ten_d0; C.ten_lspring = (T)D.ten_lspring; C.ten_l0 = (T)D.ten_l0;
@@ -224,6 +229,38 @@ template <> __device__ __forceinline__ float trcp<float>(float x) {
 #else
   return 1.0f / x;
 #endif
+}
+
+// Pins a loop-invariant pointer / value in registers: without it ptxas rebuilds such values from the kernel-parameter
+// bank inside the contact loop (three constant loads plus 64-bit address arithmetic per record pointer, per block).
+#ifndef SG_HOIST
+#define SG_HOIST 1
+#endif
+// (the OFFSET is pinned, not the pointer: a pointer that went through an asm statement loses its address space and every
+// access through it becomes a generic load)
+__device__ __forceinline__ long long keep_off(long long o) {
+#if defined(__CUDA_ARCH__) && SG_HOIST
+  asm volatile("" : "+l"(o));
+#endif
+  return o;
+}
+__device__ __forceinline__ int keep_off(int o) {
+#if defined(__CUDA_ARCH__) && SG_HOIST
+  asm volatile("" : "+r"(o));
+#endif
+  return o;
+}
+__device__ __forceinline__ float keep_val(float x) {
+#if defined(__CUDA_ARCH__) && SG_HOIST
+  asm volatile("" : "+f"(x));
+#endif
+  return x;
+}
+__device__ __forceinline__ double keep_val(double x) {
+#if defined(__CUDA_ARCH__) && SG_HOIST
+  asm volatile("" : "+d"(x));
+#endif
+  return x;
 }
 
 // one 128-byte contact record ahead into L1 (global scratch only)
@@ -320,16 +357,16 @@ __device__ __forceinline__ float trsqrt(float x) {
 #if defined(SG_FRIC_STATS) && !defined(__CUDA_ARCH__)
 static long sg_fric_evals = 0, sg_fric_calls = 0;     // development statistics under the emulator (Newton evaluations per call)
 #endif
-__device__ __forceinline__ void friction_fast(float& f1, float& f2, float& la_io, float A11i, float A12i, float A22i, float bc0, float bc1, float frc, float f0) {
+__device__ __forceinline__ void friction_fast(float& f1, float& f2, float& la_io, float a11, float a12, float kb, float bc0, float bc1, float frc, float f0) {
 #if defined(SG_FRIC_STATS) && !defined(__CUDA_ARCH__)
   sg_fric_calls++;
   if ((sg_fric_calls & 0x3ffff) == 0) fprintf(stderr, "friction_fast: %ld calls, %.3f evaluations per call\n", sg_fric_calls, (double)sg_fric_evals / (double)sg_fric_calls);
 #endif
-  const float d2 = frc * frc;
-  float a11 = A11i * d2, a12 = A12i * d2, a22 = A22i * d2, b1 = bc0 * frc, b2 = bc1 * frc;
-  if (a11 * a22 - a12 * a12 < 1e-10f) { f1 = 0; f2 = 0; la_io = 0; return; }       // mju_QCQP2: singular -> zero, inactive
-  const float sc = trcp<float>(a11 + a22), rr = trcp<float>(f0);
-  a11 *= sc; a12 *= sc; a22 *= sc; b1 *= sc; b2 *= sc;
+  // (a11, a12, 1 - a11) = frc^2 A_tt / trace and kb = frc / trace come ready-made from the contact record (contact_rows);
+  // kb = 0 marks a singular block
+  if (kb == 0.0f) { f1 = 0; f2 = 0; la_io = 0; return; }                  // mju_QCQP2: singular -> zero, inactive
+  const float a22 = 1.0f - a11, b1 = bc0 * kb, b2 = bc1 * kb;
+  const float rr = trcp<float>(f0);
 #ifndef SG_X_FRIC_MAXIT
 #define SG_X_FRIC_MAXIT 8          // (timing experiments only: a lower cap changes the results)
 #endif
@@ -830,11 +867,11 @@ struct World2 {
     }
 #pragma unroll
     for (int r = 0; r < 3; r++) cr[CR_NS + r] = ns[r];
-    cr[CR_IWE] = iw_e; cr[CR_E] = T(e); cr[CR_F + 3] = 0;     // word 31: friction multiplier of the previous sweep
+    cr[CR_F + 3] = 0;                                         // word 31: friction multiplier of the previous sweep
     const T imp = impedance2<T>(C.con_si, rc.dist);
     const T R0 = tmax(T(SG_MINVAL), (T(1) - imp) * biw / imp);
-    const T R1 = R0 / tmax(T(SG_MINVAL), C.impratio);
-    cr[CR_R0] = R0; cr[CR_R1] = R1;
+    const T R1 = R0 * C.inv_impratio;
+    cr[CR_R0] = R0;
     // velocity, aref
     T vel[3];
 #pragma unroll
@@ -861,6 +898,7 @@ struct World2 {
         MJ[r][i] = s;
       }
     int idx = 0;
+    T Ab[6];
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
@@ -869,8 +907,16 @@ struct World2 {
 #pragma unroll
         for (int jj = 0; jj < MAXCD; jj++) s += Jg[r][jj] * MJ[s2][jj];
         if (r == s2) s += (r == 0 ? R0 : R1);
+        Ab[idx] = s;
         cr[CR_A + idx++] = s;    // order: 00 01 02 11 12 22
       }
+    {
+      // the friction block of the fast path's solve: (frc^2 A_tt) / trace and frc / trace (see friction_fast)
+      const T d2 = C.con_fr * C.con_fr, a11 = Ab[3] * d2, a12 = Ab[4] * d2, a22 = Ab[5] * d2;
+      T a11n = T(0.5), a12n = 0, kb = 0;
+      if (!(a11 * a22 - a12 * a12 < T(1e-10))) { const T sc = T(1) / (a11 + a22); a11n = a11 * sc; a12n = a12 * sc; kb = C.con_fr * sc; }
+      cr[CR_A11N] = a11n; cr[CR_A12N] = a12n; cr[CR_KB] = kb;
+    }
     auxi[L.i_con + slot] = (c + 1) | ((e + 1) << 4);
     if (dbg && K.debug_out) {
       double* o = K.debug_out + 64 + 16 * (size_t)dbg_index;   // dist, pos3, frame9
@@ -1288,7 +1334,7 @@ struct World2 {
       const int ce = auxi[L.i_con + i];
       const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
       T* r = crec(i);
-      const T R0 = r[CR_R0], R1 = r[CR_R1];
+      const T R0 = r[CR_R0], R1 = R0 * C.inv_impratio;
       T jar[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) {
@@ -1382,10 +1428,10 @@ struct World2 {
 
   // friction forces with the normal force fixed: mju_QCQP2 + rescaling onto the cone (mj_solPGS); the fp32 fast path
   // solves the same problem with friction_fast
-  __device__ __forceinline__ void friction(T& f1, T& f2, T& la, T A11, T A12, T A22, const T* bc, T frc, T f0) {
+  __device__ __forceinline__ void friction(T& f1, T& f2, T& la, T A11, T A12, T A22, T a11n, T a12n, T kb, const T* bc, T frc, T f0) {
     if (sizeof(T) == 4) {
       float g1, g2, gl = (float)la;
-      friction_fast(g1, g2, gl, (float)A11, (float)A12, (float)A22, (float)bc[0], (float)bc[1], (float)frc, (float)f0);
+      friction_fast(g1, g2, gl, (float)a11n, (float)a12n, (float)kb, (float)bc[0], (float)bc[1], (float)frc, (float)f0);
       f1 = T(g1); f2 = T(g2); la = T(gl); return;
     }
     T vv[2];
@@ -1406,19 +1452,20 @@ struct World2 {
   struct Rec { T jg[12], w1[4], w2[4], Aw[8], w3[4]; };      // the 32 words of one contact record in registers
   __device__ __forceinline__ void load_rec(Rec& x, const T* r) const {
     ld4(r + CR_JG, x.jg); ld4(r + CR_JG + 4, x.jg + 4); ld4(r + CR_JG + 8, x.jg + 8);
-    ld4(r + CR_NS, x.w1);          // ns0 ns1 ns2 iwe
+    ld4(r + CR_NS, x.w1);          // ns0 ns1 ns2 a12n
     ld4(r + CR_AREF, x.w2);        // aref0 aref1 aref2 R0
-    ld4(r + CR_A, x.Aw); ld4(r + CR_A + 4, x.Aw + 4);   // A00 A01 A02 A11 | A12 A22 R1 e
+    ld4(r + CR_A, x.Aw); ld4(r + CR_A + 4, x.Aw + 4);   // A00 A01 A02 A11 | A12 A22 a11n kb
     ld4(r + CR_F, x.w3);           // f0 f1 f2, friction multiplier of the previous sweep
   }
-  __device__ __forceinline__ T contact_block(T* r, int e, T* ag, const T* mv) {
+  __device__ __forceinline__ T contact_block(T* r, int e, T* ag, const T* mv, T* asl, T frc) {
     Rec x; load_rec(x, r);
     // a contact without a slider (centre sphere) reads and writes the dummy slider: its ns and 1/m words are zero
-    T* const pae = a() + D.nfd + (e >= 0 ? e : D.ns);
+    T* const pae = asl + (e >= 0 ? e : D.ns);
     const T ae = *pae;
     const T* jg = x.jg; const T* w1 = x.w1; const T* w2 = x.w2; const T* Aw = x.Aw; const T* w3 = x.w3;
     const T A00 = Aw[0], A01 = Aw[1], A02 = Aw[2], A11 = Aw[3], A12 = Aw[4], A22 = Aw[5];
-    const T R0 = w2[3], R1 = Aw[6];
+    const T R0 = w2[3], R1 = R0 * C.inv_impratio;
+    const T iwe = e >= 0 ? stiw(e) : T(0);               // 1 / m of the contact's slider (CTA-shared table)
     const T old0 = w3[0], old1 = w3[1], old2 = w3[2];
     T la = w3[3];
     T res[3];
@@ -1450,7 +1497,7 @@ struct World2 {
       bc[0] = res[1] - (A11 * old1 + A12 * old2) + A01 * (f0 - old0);
       bc[1] = res[2] - (A12 * old1 + A22 * old2) + A02 * (f0 - old0);
       if (f0 < T(SG_MINVAL)) { f1 = 0; f2 = 0; la = 0; }
-      else friction(f1, f2, la, A11, A12, A22, bc, C.con_fr, f0);
+      else friction(f1, f2, la, A11, A12, A22, Aw[6], w1[3], Aw[7], bc, frc, f0);
     }
     // cost change, revert if positive
     T d0f = f0 - old0, d1f = f1 - old1, d2f = f2 - old2;
@@ -1462,7 +1509,7 @@ struct World2 {
     change = revert ? T(0) : change;
     st4(r + CR_F, f0, f1, f2, la);
     // qacc += M^-1 J^T delta: unconditionally (a zero change adds exact zeros)
-    *pae = ae + (w1[0] * d0f + w1[1] * d1f + w1[2] * d2f) * w1[3];
+    *pae = ae + (w1[0] * d0f + w1[1] * d1f + w1[2] * d2f) * iwe;
     T gv[MAXCD];
 #pragma unroll
     for (int jj = 0; jj < MAXCD; jj++) gv[jj] = jg[jj] * d0f + jg[4 + jj] * d1f + jg[8 + jj] * d2f;
@@ -1478,13 +1525,17 @@ struct World2 {
   struct ChainState {
     T ag[MAXCD];            // running qacc of the chain dofs, in registers for the whole solve
     const T* mv;            // the chain's M^-1 block (shared memory)
+    T* asl;                 // the world's slider accelerations (shared memory): a() + nfd
+    T frc;                  // contact friction coefficient
     int lmask, mystart, mycnt;
     bool chain_lane;
   };
   // this lane's slice of the contact schedule (contacts in their sequential order) and the chain's qacc
   __device__ void chain_prologue(ChainState& cs) {
     cs.chain_lane = sl < D.nchain;
-    cs.mv = hot + L.minv + 16 * (cs.chain_lane ? sl : 0);
+    cs.mv = reinterpret_cast<const T*>(smem_base + keep_off((int)(reinterpret_cast<unsigned char*>(hot + L.minv + 16 * (cs.chain_lane ? sl : 0)) - smem_base)));
+    cs.asl = reinterpret_cast<T*>(smem_base + keep_off((int)(reinterpret_cast<unsigned char*>(a() + D.nfd) - smem_base)));
+    cs.frc = keep_val(C.con_fr);
     cs.lmask = cs.chain_lane ? misc(M2_LMASK + sl) : 0;
     cs.mystart = 0; cs.mycnt = 0;
     const int ncon = misc(M2_NCON);
@@ -1510,7 +1561,7 @@ struct World2 {
   // phase sits where issue slots (4 warps x ~120 000 instructions per step) and single-warp latency (~540 000 cycles) meet.)
   __device__ T chain_phase(ChainState& cs, int tmaxw, bool done) {
     T impr = 0;
-    const int* order = auxi + L.i_order + cs.mystart;
+    const int* order = reinterpret_cast<const int*>(K.scratch + keep_off((long long)(reinterpret_cast<unsigned char*>(auxi + L.i_order + cs.mystart) - K.scratch)));
     const int cnt = done ? 0 : cs.mycnt;
     int entA = 0, entB = 0, entC = 0;
     if (cnt > 0) entA = order[0];
@@ -1542,7 +1593,7 @@ struct World2 {
     int k = 0;
     {
       // one byte base for the records of this world; an entry's record is base + index * 128 (CR_STRIDE reals)
-      unsigned char* const recb = reinterpret_cast<unsigned char*>(aux + L.crec);
+      unsigned char* const recb = K.scratch + keep_off((long long)(reinterpret_cast<unsigned char*>(aux + L.crec) - K.scratch));
       constexpr unsigned RB = CR_STRIDE * sizeof(T);
       for (int t = 1; t <= tmaxw; t++) {
         if (k < cnt && ((entA >> 8) & 0xff) == t) {
@@ -1555,7 +1606,7 @@ struct World2 {
           if (k + 1 < cnt) prefetch_l1(recb + (size_t)((unsigned)(entC & 0xff) * RB));   // two blocks ahead, as the entries
 #endif
           const int entD = (k + 2 < cnt) ? order[k + 2] : 0;
-          impr -= contact_block(r, e, cs.ag, cs.mv);
+          impr -= contact_block(r, e, cs.ag, cs.mv, cs.asl, cs.frc);
           entA = entB; entB = entC; entC = entD;
         }
         __syncwarp();
@@ -1884,7 +1935,7 @@ struct World2 {
         for (int k = 0; k < 3; k++, r++) {
           const T* cr = crec(i);
           o[eb + r] = (double)cr[CR_F + k]; o[eb + nefc + r] = (double)cr[CR_AREF + k];
-          o[eb + 2 * nefc + r] = (double)(k ? cr[CR_R1] : cr[CR_R0]);
+          o[eb + 2 * nefc + r] = (double)(k ? cr[CR_R0] * C.inv_impratio : cr[CR_R0]);
         }
     }
   }

@@ -510,6 +510,14 @@ struct World2 {
     auxi = reinterpret_cast<int*>(aux + L.auxT);
   }
 
+  // loop-invariant base pointers pinned in registers (see keep_off): scratch-relative, table-relative, shared-memory-relative
+  template <typename P> __device__ __forceinline__ P* pin_g(P* p) const {
+    return reinterpret_cast<P*>(K.scratch + keep_off((long long)(reinterpret_cast<unsigned char*>(p) - K.scratch)));
+  }
+  __device__ __forceinline__ const T* pin_t(const T* p) const { return K.tab + keep_off((long long)(p - K.tab)); }
+  template <typename P> __device__ __forceinline__ P* pin_s(P* p) const {
+    return reinterpret_cast<P*>(smem_base + keep_off((int)(reinterpret_cast<unsigned char*>(p) - smem_base)));
+  }
   __device__ __forceinline__ const T* tab(int o) const { return K.tab + o; }
   __device__ __forceinline__ const int* itab(int o) const { return K.itab + o; }
   __device__ __forceinline__ T* q() { return aux + L.q; }
@@ -933,8 +941,8 @@ struct World2 {
     // ---- capsule centres into the scratch (the sliders only move along their axes) ----
     T blo[3] = {T(SG_MAXVAL), T(SG_MAXVAL), T(SG_MAXVAL)}, bhi[3] = {-T(SG_MAXVAL), -T(SG_MAXVAL), -T(SG_MAXVAL)};
     {
-      const T* __restrict__ qsl = q() + D.nfd;
-      const T* __restrict__ c0 = tab(D.o_sl_cap0);
+      const T* __restrict__ qsl = pin_g(q() + D.nfd);
+      const T* __restrict__ c0 = pin_t(tab(D.o_sl_cap0));
       T* cen = scr(L.sc_cen);
 #pragma unroll 2
       for (int e = sl; e < D.ns; e += LPW) {
@@ -1141,10 +1149,12 @@ struct World2 {
     __syncwarp();
     if (sl == 0) {
       int tmax_ = 0, nstat = 0;
-      int ce_next = ncon > 0 ? auxi[L.i_con] : 0;
+      const int* const icon = pin_g(auxi + L.i_con);
+      int* const itl = pin_g(auxi + L.i_tl);
+      int ce_next = ncon > 0 ? icon[0] : 0;
       for (int i = 0; i < ncon; i++) {
         const int ce = ce_next;
-        if (i + 1 < ncon) ce_next = auxi[L.i_con + i + 1];       // the record index list lives in the global scratch
+        if (i + 1 < ncon) ce_next = icon[i + 1];                 // the record index list lives in the global scratch
         const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
         int ln;
         if (c >= 0) ln = c % clpw;
@@ -1154,7 +1164,7 @@ struct World2 {
         t += 1;
         lanet[ln] = t;
         if (e >= 0) lastt[e] = t;
-        auxi[L.i_tl + i] = t | (ln << 16);
+        itl[i] = t | (ln << 16);
         if (t > tmax_) tmax_ = t;
       }
       misc(M2_TMAX) = tmax_;
@@ -1180,8 +1190,8 @@ struct World2 {
     const int nfd = D.nfd, ns = D.ns;
     const bool dbg = valid && (w == K.debug_world) && K.debug_out;
     // volume tendon: L = sum c_e q_e, Ldot = sum c_e v_e
-    const T* __restrict__ qp = q() + nfd;     // qpos / qvel of the sliders are read-only in this stage
-    const T* __restrict__ vp = v() + nfd;
+    const T* __restrict__ qp = pin_g(q() + nfd);     // qpos / qvel of the sliders are read-only in this stage
+    const T* __restrict__ vp = pin_g(v() + nfd);
     T Ls = 0, Lv = 0, As = 0;
 #pragma unroll 4
     for (int e = sl; e < ns; e += LPW) {
@@ -1192,7 +1202,7 @@ struct World2 {
     const T Ft = -ten_stiffness() * (Ls - C.ten_lspring) - ten_damping() * Lv;
     Ft_out = Ft;
     // sliders: qacc_smooth = (passive - bias) / m  (bias = -m axis.g for a slider on a static parent)
-    T* __restrict__ qsp = qs() + nfd;
+    T* __restrict__ qsp = pin_g(qs() + nfd);
 #pragma unroll 2
     for (int e = sl; e < ns; e += LPW) {
       const T qe = qp[e], ve = vp[e], m = tab(D.o_sl_m)[e];
@@ -1204,7 +1214,7 @@ struct World2 {
     }
     // joint-equality rows in schedule order: row2 = (aref, R) until the warm start turns aref into u
     const int* __restrict__ rd = srd;
-    const T* __restrict__ siwt = tab(D.o_sl_iw);
+    const T* __restrict__ siwt = pin_t(tab(D.o_sl_iw));
     T* __restrict__ row2 = hot + L.row2;
 #pragma unroll 4
     for (int p = sl; p < D.nrow; p += LPW) {
@@ -1282,14 +1292,17 @@ struct World2 {
     const int ncon = misc(M2_NCON);
     const int* rd = srd;
     T* row2 = hot + L.row2;
-    T* jtf = aux + L.jtf;
+    T* jtf = pin_g(aux + L.jtf);
+    const int* const dof_rows = K.itab + keep_off((long long)D.io_dof_rows);
+    const int* const icon = pin_g(auxi + L.i_con);
+    T* const rec0 = pin_g(aux + L.crec);
     // dual cost = sum_rows (0.5 R f^2 - f aref) + (J^T f).qacc_smooth + 0.5 (J^T f)' M^-1 (J^T f): the middle term is
     // sum_rows f (J qacc_smooth) regrouped per dof, so no row ever has to gather qacc_smooth
     T cost = 0;
     // equality rows: per-dof gather of J^T f over the rows of each slider (no scatter, no atomics)
     T tja = 0;
     for (int e = sl; e < ns; e += LPW) {
-      const int* dr = itab(D.io_dof_rows) + e * MAXDOFROWS;
+      const int* dr = dof_rows + e * MAXDOFROWS;
       T s = 0;
 #pragma unroll
       const T ae = a()[nfd + e];
@@ -1331,9 +1344,9 @@ struct World2 {
     }
     // contacts
     for (int i = sl; i < ncon; i += LPW) {
-      const int ce = auxi[L.i_con + i];
+      const int ce = icon[i];
       const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
-      T* r = crec(i);
+      T* r = rec0 + CR_STRIDE * i;
       const T R0 = r[CR_R0], R1 = R0 * C.inv_impratio;
       T jar[3];
 #pragma unroll
@@ -1360,10 +1373,10 @@ struct World2 {
 #pragma unroll
         for (int jj = 0; jj < MAXCD; jj++) gd[c][jj] = 0;
       for (int i = 0; i < ncon; i++) {
-        const int ce = auxi[L.i_con + i];
+        const int ce = icon[i];
         const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
         if ((e >= 0 ? e : i) % LPW != sl) continue;
-        const T* r = crec(i);
+        const T* r = rec0 + CR_STRIDE * i;
         T jg[12], w1[4], f[4];
         ld4(r + CR_NS, w1); ld4(r + CR_F, f);
         if (e >= 0) jtf[nfd + e] += w1[0] * f[0] + w1[1] * f[1] + w1[2] * f[2];
@@ -1412,7 +1425,7 @@ struct World2 {
 #pragma unroll
         for (int jl = 0; jl < MAXCD; jl++) if (jl < D.ncd[sl]) lf(D.chain_dof0[sl] + jl) = 0;
       }
-      for (int i = sl; i < ncon; i += LPW) { T* r = crec(i); r[CR_F] = 0; r[CR_F + 1] = 0; r[CR_F + 2] = 0; }
+      for (int i = sl; i < ncon; i += LPW) { T* r = rec0 + CR_STRIDE * i; r[CR_F] = 0; r[CR_F + 1] = 0; r[CR_F + 2] = 0; }
     }
     __syncwarp();
     // a = qacc_smooth + M^-1 jtf (or qacc_smooth alone)
@@ -1539,15 +1552,18 @@ struct World2 {
     cs.lmask = cs.chain_lane ? misc(M2_LMASK + sl) : 0;
     cs.mystart = 0; cs.mycnt = 0;
     const int ncon = misc(M2_NCON);
+    const int* const itl = pin_g(auxi + L.i_tl);
+    const int* const icon = pin_g(auxi + L.i_con);
     for (int i = 0; i < ncon; i++) {
-      const int ln = auxi[L.i_tl + i] >> 16;
+      const int ln = itl[i] >> 16;
       if (ln < sl) cs.mystart++;
       else if (ln == sl) cs.mycnt++;
     }
     int k = 0;
+    int* const iord = pin_g(auxi + L.i_order + cs.mystart);
     for (int i = 0; i < ncon; i++) {
-      const int tl = auxi[L.i_tl + i];
-      if ((tl >> 16) == sl) { auxi[L.i_order + cs.mystart + k] = i | ((tl & 0xff) << 8) | ((auxi[L.i_con + i] >> 4) << 16); k++; }
+      const int tl = itl[i];
+      if ((tl >> 16) == sl) { iord[k] = i | ((tl & 0xff) << 8) | ((icon[i] >> 4) << 16); k++; }
     }
 #pragma unroll
     for (int jj = 0; jj < MAXCD; jj++) cs.ag[jj] = (cs.chain_lane && jj < D.ncd[sl]) ? a()[D.chain_dof0[sl] + jj] : T(0);
@@ -1848,8 +1864,8 @@ struct World2 {
   __device__ void euler() {
     const int nfd = D.nfd; const T h = C.h;
     {
-      T* __restrict__ qp = q() + nfd; T* __restrict__ vp = v() + nfd;
-      const T* __restrict__ ap = a() + nfd;
+      T* __restrict__ qp = pin_g(q() + nfd); T* __restrict__ vp = pin_g(v() + nfd);
+      const T* __restrict__ ap = pin_s(a() + nfd);
 #pragma unroll 4
       for (int e = sl; e < D.ns; e += LPW) {
         const T m = tab(D.o_sl_m)[e];

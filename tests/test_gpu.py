@@ -12,8 +12,11 @@ from conftest import GOLDEN, ROOT, blob_path, pkg
 pytestmark = pytest.mark.gpu
 
 # stated fp32 single-step tolerances, relative to the max magnitude of the quantity over the world
-FP32_TOL = {"q": 5e-5, "v": 3e-3, "qacc": 3e-3, "sens": 1e-2}
-FP64_TOL = 1e-9
+# about ten times what is measured on a B200 for softbox (profiles/r02x_test_gpu_measured.txt: q 1.1e-6, v 3.6e-5, qacc 1.6e-5,
+# sens 1.0e-4 over the twelve golden snapshots); the larger models, in contact from the first step, get their own bound below
+FP32_TOL = {"q": 1e-5, "v": 3e-4, "qacc": 2e-4, "sens": 1e-3}
+FP32_TOL_OTHER = {"q": 5e-5, "v": 3e-3, "qacc": 3e-3, "sens": 1e-2}
+FP64_TOL = 1e-10         # measured 8e-14 (softbox) .. 4e-13 (refined softbox); north_star asks 1e-5
 
 
 def _note(text):
@@ -52,6 +55,7 @@ def test_single_step_parity_against_golden_states(torch_cuda, batched, states, p
     env = make_env(batched, torch, W=W, dtype=torch.float64 if prec == "f64" else torch.float32)
     env.set_new_stiffness(stiffness=[700.0] * W)
     env.set_debug_world(1)
+    worst = {}
     for i in range(len(states["step"])):
         (q1, v1, a1, qacc), sens, touch = one_step_from(env, states["q"][i], states["v"][i], states["act"][i], states["warm"][i],
                                                         [states["ctrl"][i]] * 2, W)
@@ -61,11 +65,13 @@ def test_single_step_parity_against_golden_states(torch_cuda, batched, states, p
         err = {"q": rel(q1[1], states["q1"][i]), "v": rel(v1[1], states["v1"][i]), "qacc": rel(qacc[1], states["qacc1"][i]),
                "sens": rel(sens[1], states["sens1"][i])}
         for k, e in err.items():
+            worst[k] = max(worst.get(k, 0.0), e)
             assert e <= (FP64_TOL if prec == "f64" else FP32_TOL[k]), (int(states["step"][i]), k, e)
         if prec == "f64":
             assert int(env.debug(1, "solver_iter")[0]) == states["iter1"][i]
             np.testing.assert_array_equal(q1[0], q1[2])          # worlds with identical inputs are bit-identical
         assert env.status()[1] == 0
+    _note("single step %s vs golden states, worst over %d snapshots: %s" % (prec, len(states["step"]), ", ".join("%s %.2e" % kv for kv in sorted(worst.items()))))
 
 
 def test_stage_diagnostics_match_oracle(torch_cuda, batched, states, make_world):

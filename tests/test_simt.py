@@ -14,7 +14,10 @@ from conftest import GOLDEN, ROOT, blob_path
 
 sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
 
-FP32_TOL = {"q": 5e-5, "v": 3e-3, "qacc": 3e-3, "sens": 1e-2}
+# about ten times what is measured on a B200 for softbox (profiles/r02x_test_gpu_measured.txt: q 1.1e-6, v 3.6e-5, qacc 1.6e-5,
+# sens 1.0e-4 over the twelve golden snapshots); the larger models, in contact from the first step, get their own bound below
+FP32_TOL = {"q": 1e-5, "v": 3e-4, "qacc": 2e-4, "sens": 1e-3}
+FP32_TOL_OTHER = {"q": 5e-5, "v": 3e-3, "qacc": 3e-3, "sens": 1e-2}
 
 
 def rel(a, b):
@@ -51,7 +54,7 @@ def test_emulated_single_step_parity_against_golden_states(emu, states, prec, lp
         err = {"q": rel(q1[-1], states["q1"][i]), "v": rel(v1[-1], states["v1"][i]), "qacc": rel(qacc[-1], states["qacc1"][i]),
                "sens": rel(sens[-1], states["sens1"][i])}
         for k, e in err.items():
-            assert e <= (1e-9 if prec == 64 else FP32_TOL[k]), (int(states["step"][i]), k, e)
+            assert e <= (1e-10 if prec == 64 else FP32_TOL[k]), (int(states["step"][i]), k, e)
         if prec == 64:
             assert int(env.debug("solver_iter")[0]) == states["iter1"][i]
         for w in range(W - 1):             # every group of the warp computes the same bits
@@ -403,7 +406,7 @@ def test_emulated_other_models_along_a_stabilised_episode(emu, make_world, name,
         assert int(env.debug("ncon")[0]) == ncon
         err = {"q": rel(q1[1], oq), "v": rel(v1[1], ov), "qacc": rel(qacc[1], oacc)}
         for key, e in err.items():
-            assert e < (1e-8 if prec == 64 else FP32_TOL[key]), (step, key, e)
+            assert e < (1e-8 if prec == 64 else FP32_TOL_OTHER[key]), (step, key, e)
         assert rel(a1[1], oa) < (1e-12 if prec == 64 else 1e-6), step
         ncons.append(ncon)
     assert (env.status() == 0).all() and max(ncons) > min(ncons)

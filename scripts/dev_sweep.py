@@ -24,6 +24,9 @@ for cfg in cfgs:
     os.environ["SOFTGRIP_STEP_BARRIER"] = str(parts.get("s", 1))
     if "m" in parts: os.environ["SOFTGRIP_MAXCON"] = str(parts["m"])
     else: os.environ.pop("SOFTGRIP_MAXCON", None)
+    # t0 / t1: equality rows in shared memory / forced into tensor memory (default: the library decides)
+    if "t" in parts: os.environ["SOFTGRIP_TMEM"] = str(parts["t"])
+    else: os.environ.pop("SOFTGRIP_TMEM", None)
     if "n" in parts: os.environ["SOFTGRIP_NW"] = str(parts["n"])
     else: os.environ.pop("SOFTGRIP_NW", None)
     dm = batched.DeviceModel(blob)

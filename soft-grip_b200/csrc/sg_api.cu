@@ -36,6 +36,7 @@ struct sg_batch {
   int kernel = 2;             // kernel generation (sg_kernels2.cuh: sub-warp worlds); the first-generation kernel is gone
   int lpw = 8;                // lanes per world of kernel 2
   int nwarp = 16;             // warps per CTA of kernel 2
+  int tm_cols = 0, tm_stride = 0;   // tensor-memory window of the equality rows (KArgs2::tm_cols, tm_stride); 0: shared memory
   size_t smem2 = 0;           // dynamic shared memory per CTA of kernel 2
   Layout2 L2;
   unsigned char* scratch = nullptr;   // global aux slots of kernel 2 (when aux is not in shared memory)
@@ -305,6 +306,20 @@ static int batch_create_body(const sg_model* m, int nworlds, int device, int pre
     if (e) { return fail(std::string("kernel configuration failed: ") + cudaGetErrorString((cudaError_t)e)); }
     if (per_sm < 1) per_sm = 1;
     b->max_ctas = per_sm * prop.multiProcessorCount; b->per_sm = per_sm;
+#if !(SG_EQ2 && SG_SLOT8)
+    {
+      // The (u, n) pairs of the equality sweep go to tensor memory when every resident CTA of an SM gets its window:
+      // 2 (fp32) or 4 (fp64) columns per step and one empty step past the end for each warp, four warps (one per lane
+      // quarter) share a column block, 512 columns per SM.  SOFTGRIP_TMEM=0 keeps them in shared memory, =1 takes
+      // tensor memory whenever one CTA fits (further CTAs of the SM then wait for the allocation).
+      const int stride = (b->D.nstep + 1) * (precision == 32 ? 2 : 4);
+      int need = 32;
+      while (need < ((b->nwarp + 3) / 4) * stride) need *= 2;
+      int mode = -1;
+      if (const char* te = std::getenv("SOFTGRIP_TMEM")) mode = std::atoi(te);
+      if (need <= 512 && mode != 0 && (mode == 1 || need * per_sm <= 512)) { b->tm_cols = need; b->tm_stride = stride; }
+    }
+#endif
     const int cta_worlds = wpw * b->nwarp;
     int need = (nworlds + cta_worlds - 1) / cta_worlds;
     int slots = need < b->max_ctas ? need : b->max_ctas;
@@ -454,6 +469,7 @@ static int launch_v2(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
   K.step_barrier = 1;
   if (const char* sb = std::getenv("SOFTGRIP_STEP_BARRIER")) K.step_barrier = std::atoi(sb) != 0;
   K.scratch = b->scratch;
+  K.tm_cols = b->tm_cols; K.tm_stride = b->tm_stride;
   K.qpos = (T*)b->qpos; K.qvel = (T*)b->qvel; K.warm = (T*)b->warm; K.act = (T*)b->act; K.ctrl = (T*)b->ctrl;
   K.p_stiff = b->has_stiff ? b->p_stiff : nullptr; K.p_damp = b->has_damp ? b->p_damp : nullptr;
   K.p_tdamp = b->has_tdamp ? b->p_tdamp : nullptr; K.p_objoff = b->has_objoff ? b->p_objoff : nullptr;
@@ -664,6 +680,11 @@ extern "C" int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int
     return put(t.data(), (int)t.size());
   }
   auto scalar = [&](double v) { if (out && cap > 0) out[0] = v; return 1; };
+  if (k == "tensor_memory") {
+    // [columns the CTA allocates (0: the equality rows stay in shared memory), columns per warp]
+    const double t[2] = {(double)b->tm_cols, (double)b->tm_stride};
+    return put(t, 2);
+  }
   if (k == "ncon") return scalar(ncontot);
   if (k == "nefc") return scalar(nefc);
   if (k == "solver_iter") return scalar(h[2]);

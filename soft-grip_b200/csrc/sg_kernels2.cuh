@@ -198,6 +198,8 @@ struct KArgs2 {
   const int* itab;
   int nworlds;
   int step_barrier;            // 1: the warps of a CTA start every physics step together (CTA barrier per step)
+  int tm_cols;                 // tensor-memory columns the CTA allocates (power of two >= 32), 0: the (u, n) rows stay in shared memory
+  int tm_stride;               // columns per warp: warp w owns [tm_stride (w / 4), +tm_stride) of its lane quarter
   unsigned char* scratch;      // global aux slots [gridDim.x * WPW][L.gs_stride] (null when aux_in_smem)
   // state, world-major
   T *qpos, *qvel, *warm, *act, *ctrl;
@@ -271,6 +273,62 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
   (void)p;
 #endif
 }
+// ---- tensor memory as per-thread scratch --------------------------------------------------------------------------
+// The kernel has no matrix work for the tensor cores, but their 256 KB of tensor memory per SM is the one on-chip store
+// that shared memory (full) and the register file (full) leave unused.  In the 32x32b access shape every thread of a warp
+// reads and writes its own TMEM lane (warp w of the CTA: lanes 32 (w % 4) ..), at a column address that is uniform over
+// the warp -- which is exactly the access pattern of the equality sweep: every lane handles the row of ITS slot of step
+// `st`, so the (u, n) pair of slot (st, lane) lives in the lane's TMEM lane at column 2 st (4 st in double precision).
+// Measured with the sweep's load -> flops -> store -> warp-barrier pattern (scripts/tmem_probe.cu, 16 warps per SM):
+// 50.6 cycles per step from tensor memory against 64.3 from shared memory, bit-identical results.
+// The loads are asynchronous: the registers are only valid after tm_wait_ld, which takes them as operands so that the
+// compiler cannot move a use above the wait.
+template <typename T> struct TmPair;   // columns per (u, n) pair
+template <> struct TmPair<float> { static constexpr int cols = 2; };
+template <> struct TmPair<double> { static constexpr int cols = 4; };
+#if defined(SG_SIMT_EMU)
+// emulator: simt.h keeps a [128][512] word array per CTA and checks that the column address is uniform over the warp
+__device__ __forceinline__ void tm_ld2(unsigned ta, float& x, float& y) { unsigned w[2]; simt_tm_ld(ta, 2, w); memcpy(&x, w, 4); memcpy(&y, w + 1, 4); }
+__device__ __forceinline__ void tm_ld2(unsigned ta, double& x, double& y) { unsigned w[4]; simt_tm_ld(ta, 4, w); memcpy(&x, w, 8); memcpy(&y, w + 2, 8); }
+__device__ __forceinline__ void tm_st1(unsigned ta, float x) { unsigned w[1]; memcpy(w, &x, 4); simt_tm_st(ta, 1, w); }
+__device__ __forceinline__ void tm_st1(unsigned ta, double x) { unsigned w[2]; memcpy(w, &x, 8); simt_tm_st(ta, 2, w); }
+__device__ __forceinline__ void tm_st2(unsigned ta, float x, float y) { unsigned w[2]; memcpy(w, &x, 4); memcpy(w + 1, &y, 4); simt_tm_st(ta, 2, w); }
+__device__ __forceinline__ void tm_st2(unsigned ta, double x, double y) { unsigned w[4]; memcpy(w, &x, 8); memcpy(w + 2, &y, 8); simt_tm_st(ta, 4, w); }
+template <typename T> __device__ __forceinline__ void tm_wait_ld(T&, T&) {}
+__device__ __forceinline__ void tm_wait_st() {}
+#elif defined(__CUDA_ARCH__)
+__device__ __forceinline__ void tm_ld2(unsigned ta, float& x, float& y) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(ta));
+}
+__device__ __forceinline__ void tm_ld2(unsigned ta, double& x, double& y) {
+  unsigned a, b, c, d;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(ta));
+  // (the words are only valid after tm_wait_ld: the wait below is part of the load for the two-register type)
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a), "+r"(b), "+r"(c), "+r"(d)::"memory");
+  x = __hiloint2double((int)b, (int)a); y = __hiloint2double((int)d, (int)c);
+}
+__device__ __forceinline__ void tm_st1(unsigned ta, float x) { asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(ta), "f"(x)); }
+__device__ __forceinline__ void tm_st1(unsigned ta, double x) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(ta), "r"(__double2loint(x)), "r"(__double2hiint(x)));
+}
+__device__ __forceinline__ void tm_st2(unsigned ta, float x, float y) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(ta), "f"(x), "f"(y));
+}
+__device__ __forceinline__ void tm_st2(unsigned ta, double x, double y) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "r"(__double2loint(x)), "r"(__double2hiint(x)),
+               "r"(__double2loint(y)), "r"(__double2hiint(y)));
+}
+__device__ __forceinline__ void tm_wait_ld(float& x, float& y) { asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(x), "+f"(y)::"memory"); }
+__device__ __forceinline__ void tm_wait_ld(double&, double&) {}     // waited inside tm_ld2<double>
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#else   // host pass of nvcc: never executed
+template <typename T> __device__ __forceinline__ void tm_ld2(unsigned, T&, T&) {}
+template <typename T> __device__ __forceinline__ void tm_st1(unsigned, T) {}
+template <typename T> __device__ __forceinline__ void tm_st2(unsigned, T, T) {}
+template <typename T> __device__ __forceinline__ void tm_wait_ld(T&, T&) {}
+__device__ __forceinline__ void tm_wait_st() {}
+#endif
+
 // division inside the contact blocks: MUFU.RCP + FMUL on the fp32 fast path (2 ulp), IEEE in the verification build
 template <typename T> __device__ __forceinline__ T tdiv(T a, T b);
 template <> __device__ __forceinline__ double tdiv<double>(double a, double b) { return a / b; }
@@ -473,6 +531,7 @@ struct World2 {
   T kw, dw, tdw, off[3];
 
   unsigned char* smem_base;
+  unsigned tm;            // this warp's tensor-memory window: lane quarter << 16 | first column (see tm_ld2)
   const Slot<T>* slots;  // CTA-shared step tables of the level sweep (shared memory), already offset to this lane
   const T *stc, *stciw;   // CTA-shared copies of the tendon coefficients and coefficient / mass
   const T* stim;          // CTA-shared 1 / slider mass
@@ -489,6 +548,7 @@ struct World2 {
     lane = threadIdx.x & 31; grp = lane / LPW; sl = lane % LPW; gshift = grp * LPW;
     const int warp = vwarp >= 0 ? vwarp : (int)(threadIdx.x >> 5), nwarp = vnwarp >= 0 ? vnwarp : (int)(blockDim.x >> 5);
     smem_base = smem;
+    tm = 0;
     slots = reinterpret_cast<const Slot<T>*>(smem) + sl;
     stc = reinterpret_cast<const T*>(smem + (size_t)(D.nstep + 1) * LPW * sizeof(Slot<T>));
     stciw = stc + D.ns;
@@ -1411,6 +1471,10 @@ struct World2 {
     const bool keep = !(cost > T(0));
     // (aref, R) -> (u, n):  u = R f - aref is -(J.qacc_warm) when the warm start is kept and -aref when it is dropped;
     // n = -1 / (1/m1 + 1/m2 + R) is what the sweep multiplies the residual with
+#if !(SG_EQ2 && SG_SLOT8)
+    if (K.tm_cols) rows_to_tm(keep);
+    else
+#endif
     for (int p = sl; p < D.nrow; p += LPW) {
       const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
       T ar, R; ld2(row2 + 2 * p, ar, R);
@@ -1704,12 +1768,19 @@ struct World2 {
     return T(-0.5) * acc;
   }
 #else
-  template <bool GATED>
+  // TM: the (u, n) pair of this lane's slot of step `st` is in the lane's tensor memory at column st * TmPair<T>::cols
+  // (written by rows_to_tm at the end of the warm start); the pair of the next step is requested before this step's
+  // arithmetic, so the sweep never waits for it.  Padding slots hold (0, 0) and go through the arithmetic as zeros.
+  template <bool GATED, bool TM = false>
   __device__ __forceinline__ T equality_rows(bool done) {
     const int nstep = D.nstep;
     char* avb = reinterpret_cast<char*>(a() + D.nfd);
     char* rwb = reinterpret_cast<char*>(hot);     // Layout2::row2 == 0 (make_layout2)
     T acc = 0;                                   // sum of res * dl = -2 * cost improvement
+    constexpr unsigned CW = TmPair<T>::cols;
+    unsigned tcol = tm;
+    T un_ = 0, nn_ = 0;
+    if (TM) tm_ld2(tcol, un_, nn_);
 #if SG_SLOT8
     const T iwu = stim[0];                       // 1 / element mass, the same for every slider
 #endif
@@ -1731,7 +1802,12 @@ struct World2 {
       T* pa2 = reinterpret_cast<T*>(avb + o2);
       T* pr = reinterpret_cast<T*>(rwb + (sc.y & 0x3fffffffu));
       T a1 = 0, a2 = 0, u = 0, n = 0;
-      if (valid) { a1 = *pa1; ld2(pr, u, n); }
+      if (TM) {
+        tm_wait_ld(un_, nn_);
+        u = un_; n = nn_;
+        tm_ld2(tcol + CW, un_, nn_);              // next step's pair (the window carries one empty step past the end)
+        if (valid) a1 = *pa1;
+      } else if (valid) { a1 = *pa1; ld2(pr, u, n); }
       if (has2) a2 = *pa2;
       const T res = (a1 - a2) + u;
       if (GATED) n = done ? T(0) : n;
@@ -1744,13 +1820,59 @@ struct World2 {
 #endif
       T un = a2 - a1;
       if (GATED) un = done ? u : un;
-      if (valid) { *pr = un; *pa1 = a1; }
+      if (TM) { tm_st1(tcol, un); tcol += CW; if (valid) *pa1 = a1; }
+      else if (valid) { *pr = un; *pa1 = a1; }
       if (has2) *pa2 = a2;
       // nearly every step of the 8-lane schedules ends a dependency level: an unconditional barrier is cheaper than
       // testing the flag; narrower worlds have runs of independent steps that are allowed to overlap
       if (LPW >= 8 || (int)sc.y < 0) __syncwarp();
     }
+    if (TM) { tm_wait_ld(un_, nn_); tm_wait_st(); }     // the look-ahead load has landed; the stores are visible to the next sweep
     return T(-0.5) * acc;
+  }
+  // (aref, R) of the warm start -> (u, n) of the sweep, from the compact shared-memory pairs into the slot order of the
+  // lane's tensor memory (see warmstart for the formulas); padding slots and the step past the end become (0, 0)
+  __device__ void rows_to_tm(bool keep) {
+    const int nstep = D.nstep;
+    const char* avb = reinterpret_cast<const char*>(a() + D.nfd);
+    const char* rwb = reinterpret_cast<const char*>(hot);
+    constexpr unsigned CW = TmPair<T>::cols;
+    unsigned tcol = tm;
+#if SG_SLOT8
+    const T iwu = stim[0];
+#endif
+    for (int st = 0; st <= nstep; st++, tcol += CW) {
+      const Slot<T> sc = ld_slot<T>(slots + st * LPW);
+      const unsigned o2 = sc.x >> 16;
+      const bool valid = st < nstep && (sc.y & 0x40000000u) != 0u, has2 = st < nstep && o2 != 0xffffu;
+      T u = 0, n = 0;
+      if (valid) {
+        T ar, R; ld2(reinterpret_cast<const T*>(rwb + (sc.y & 0x3fffffffu)), ar, R);
+        T ja = *reinterpret_cast<const T*>(avb + (sc.x & 0xffffu));
+#if SG_SLOT8
+        T diag = iwu;
+        if (has2) { ja -= *reinterpret_cast<const T*>(avb + o2); diag += iwu; }
+#else
+        T diag = sc.iw1;
+        if (has2) { ja -= *reinterpret_cast<const T*>(avb + o2); diag += sc.iw2; }
+#endif
+        u = keep ? -ja : -ar;
+        n = T(-1) / (diag + R);
+      }
+      tm_st2(tcol, u, n);
+    }
+    tm_wait_st();
+  }
+  // the u's back into the compact shared-memory pairs (debug dump only; every lane of the warp takes part)
+  __device__ void rows_from_tm() {
+    char* rwb = reinterpret_cast<char*>(hot);
+    constexpr unsigned CW = TmPair<T>::cols;
+    for (int st = 0; st < D.nstep; st++) {
+      const Slot<T> sc = ld_slot<T>(slots + st * LPW);
+      T u, n; tm_ld2(tm + (unsigned)st * CW, u, n); tm_wait_ld(u, n);
+      if (sc.y & 0x40000000u) *reinterpret_cast<T*>(rwb + (sc.y & 0x3fffffffu)) = u;
+    }
+    __syncwarp();
   }
 #endif
   __device__ __forceinline__ T equality_sweep(Tendon& tn, bool done) {
@@ -1758,7 +1880,13 @@ struct World2 {
     T* av = a() + D.nfd;
     // worlds stop sweeping one by one (rarely before the last sweep): the gated loop is only taken by a warp that
     // holds a finished world
+#if SG_EQ2 && SG_SLOT8
     T impr = __any_sync(FULLMASK, done) ? equality_rows<true>(done) : equality_rows<false>(false);
+#else
+    T impr;
+    if (K.tm_cols) impr = __any_sync(FULLMASK, done) ? equality_rows<true, true>(done) : equality_rows<false, true>(false);
+    else impr = __any_sync(FULLMASK, done) ? equality_rows<true>(done) : equality_rows<false>(false);
+#endif
     // volume-tendon row: dense over the shell, sub-warp shuffle reduction
     {
       T s = 0;
@@ -1853,6 +1981,9 @@ struct World2 {
     }
     __syncwarp();
     tick(PH_SENSORS);
+#if !(SG_EQ2 && SG_SLOT8)
+    if (K.tm_cols && K.debug_out && __any_sync(FULLMASK, valid && w == K.debug_world)) rows_from_tm();
+#endif
     if (valid && w == K.debug_world) debug_dump(tn);
     bool badacc = false;
     for (int i = sl; i < D.nv; i += LPW) if (!(tabs(a()[i]) <= T(SG_MAXVAL))) badacc = true;
@@ -1982,6 +2113,16 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
   const Layout2& L = K.L;
   const int lane = threadIdx.x & 31, grp = lane / LPW, sl = lane % LPW;
   const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  // tensor memory for the (u, n) rows of the equality sweep (see tm_ld2): warp 0 allocates K.tm_cols columns for the CTA
+  unsigned tm_window = 0;
+#if defined(__CUDA_ARCH__)
+  __shared__ unsigned tm_base_s;
+  if (K.tm_cols && warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&tm_base_s)), "r"(K.tm_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+#endif
   {
     // stage the step tables: one {descriptor, (1/m, 1/m)} slot per (step, lane)
     Slot<T>* ss = reinterpret_cast<Slot<T>*>(smem_raw);
@@ -2009,6 +2150,13 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
     for (int i = threadIdx.x; i < D.nrow; i += blockDim.x) rn[4 * D.nrun + i] = K.itab[D.io_row_d12 + i];
     __syncthreads();
   }
+  if (K.tm_cols) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tm_window = tm_base_s;
+#endif
+    tm_window += ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((warp >> 2) * K.tm_stride);
+  }
 #if defined(__CUDA_ARCH__)
   if (K.prof && lane == 0) K.prof[PH_COUNT + (size_t)blockIdx.x * nwarp + warp] = clock64();
 #endif
@@ -2017,6 +2165,7 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
     const int wi = b0 + warp * WPW + grp;
     const bool valid = wi < K.nworlds;
     World2<T, LPW> W(K, smem_raw, valid ? wi : K.nworlds - 1, valid);
+    W.tm = tm_window;
     W.load_params();
     if (sl == 0) { W.misc(M2_STATUS) = 0; W.a()[D.nv] = 0; W.hot[L.row2 + 2 * D.nrow] = 0; W.hot[L.row2 + 2 * D.nrow + 1] = -1; }
     const int w = W.w;
@@ -2072,6 +2221,13 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
     }
     __syncwarp();
   }
+#if defined(__CUDA_ARCH__)
+  if (K.tm_cols) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base_s), "r"(K.tm_cols) : "memory");
+  }
+#endif
 }
 
 }  // namespace sg

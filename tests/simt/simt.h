@@ -135,6 +135,10 @@ inline void run_cta() {
   }
 }
 
+// tensor memory of the running CTA (see simt_tm_ld / simt_tm_st below); poisoned with NaN patterns at CTA start
+inline unsigned tmem[128][512];
+inline void tm_poison() { memset(tmem, 0xff, sizeof(tmem)); }
+
 template <typename F, typename A>
 struct Thunk { F f; A a; static void call(void* p) { Thunk* t = (Thunk*)p; t->f(t->a); } };
 
@@ -150,6 +154,7 @@ inline void launch(F kernel, unsigned grid, unsigned block, size_t smem, const A
   for (unsigned b = 0; b < grid; b++) {
     blockIdx.x = b;
     if (smem) memset(CTA.smem, 0xff, smem);   // NaN pattern: reads of never-written shared memory show up as NaNs
+    tm_poison();
     run_cta();
   }
 }
@@ -214,6 +219,26 @@ inline int __reduce_max_sync(unsigned, int v) {
   int r = simt::from_bits<int>(simt::cur_warp().slot[g & 1][0]);
   for (int l = 1; l < 32; l++) { int x = simt::from_bits<int>(simt::cur_warp().slot[g & 1][l]); if (x > r) r = x; }
   return r;
+}
+// tensor memory in the 32x32b access shape (tcgen05.ld / tcgen05.st): [128 lanes][512 columns] of 32-bit words per CTA; a thread
+// of warp w owns lane 32 (w % 4) + its lane id.  The instructions are warp-collective with a warp-uniform address: the
+// emulator makes them a rendezvous and aborts on a non-uniform address, a lane quarter that is not the warp's, or a column
+// past the end.
+inline void simt_tm_check(unsigned ta, int n, int site) {
+  const int g = simt::rendezvous(ta, site);
+  for (int l = 0; l < 32; l++)
+    if ((unsigned)simt::cur_warp().slot[g & 1][l] != ta) { fprintf(stderr, "simt: tensor-memory access with a non-uniform address\n"); abort(); }
+  const unsigned lane0 = ta >> 16, col = ta & 0xffffu;
+  if (lane0 != 32u * (unsigned)(simt::CTA.cur_warp & 3)) { fprintf(stderr, "simt: warp %d accesses tensor-memory lanes %u..\n", simt::CTA.cur_warp, lane0); abort(); }
+  if (col + (unsigned)n > 512u) { fprintf(stderr, "simt: tensor-memory column %u + %d out of range\n", col, n); abort(); }
+}
+inline void simt_tm_ld(unsigned ta, int n, unsigned* out) {
+  simt_tm_check(ta, n, 8);
+  memcpy(out, &simt::tmem[(ta >> 16) + (unsigned)simt::cur_lane()][ta & 0xffffu], 4 * (size_t)n);
+}
+inline void simt_tm_st(unsigned ta, int n, const unsigned* in) {
+  simt_tm_check(ta, n, 9);
+  memcpy(&simt::tmem[(ta >> 16) + (unsigned)simt::cur_lane()][ta & 0xffffu], in, 4 * (size_t)n);
 }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }

@@ -27,6 +27,9 @@ for cfg in cfgs:
     # t0 / t1: equality rows in shared memory / forced into tensor memory (default: the library decides)
     if "t" in parts: os.environ["SOFTGRIP_TMEM"] = str(parts["t"])
     else: os.environ.pop("SOFTGRIP_TMEM", None)
+    # r0: contact records read from the scratch instead of the shared-memory ring
+    if "r" in parts: os.environ["SOFTGRIP_RING"] = str(parts["r"])
+    else: os.environ.pop("SOFTGRIP_RING", None)
     if "n" in parts: os.environ["SOFTGRIP_NW"] = str(parts["n"])
     else: os.environ.pop("SOFTGRIP_NW", None)
     dm = batched.DeviceModel(blob)

@@ -37,6 +37,7 @@ struct sg_batch {
   int lpw = 8;                // lanes per world of kernel 2
   int nwarp = 16;             // warps per CTA of kernel 2
   int tm_cols = 0, tm_stride = 0;   // tensor-memory window of the equality rows (KArgs2::tm_cols, tm_stride); 0: shared memory
+  int rec_ring = 0;                 // contact records through a shared-memory ring in the freed row region (KArgs2::rec_ring)
   size_t smem2 = 0;           // dynamic shared memory per CTA of kernel 2
   Layout2 L2;
   unsigned char* scratch = nullptr;   // global aux slots of kernel 2 (when aux is not in shared memory)
@@ -318,6 +319,13 @@ static int batch_create_body(const sg_model* m, int nworlds, int device, int pre
       int mode = -1;
       if (const char* te = std::getenv("SOFTGRIP_TMEM")) mode = std::atoi(te);
       if (need <= 512 && mode != 0 && (mode == 1 || need * per_sm <= 512)) { b->tm_cols = need; b->tm_stride = stride; }
+      // With the rows in tensor memory their shared-memory region is free during the solve: a two-entry ring of contact
+      // records per lane goes there if it fits (SOFTGRIP_RING=0: records are read from the scratch as before).
+      const size_t esz = precision == 32 ? 4 : 8;
+      const size_t ring_bytes = (size_t)b->lpw * (2 * CR_STRIDE * esz + 16);
+      int ring_mode = 1;
+      if (const char* re = std::getenv("SOFTGRIP_RING")) ring_mode = std::atoi(re);
+      if (b->tm_cols && ring_mode != 0 && ring_bytes <= 2 * (size_t)b->D.nrow * esz) b->rec_ring = 1;
     }
 #endif
     const int cta_worlds = wpw * b->nwarp;
@@ -469,7 +477,7 @@ static int launch_v2(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
   K.step_barrier = 1;
   if (const char* sb = std::getenv("SOFTGRIP_STEP_BARRIER")) K.step_barrier = std::atoi(sb) != 0;
   K.scratch = b->scratch;
-  K.tm_cols = b->tm_cols; K.tm_stride = b->tm_stride;
+  K.tm_cols = b->tm_cols; K.tm_stride = b->tm_stride; K.rec_ring = b->rec_ring;
   K.qpos = (T*)b->qpos; K.qvel = (T*)b->qvel; K.warm = (T*)b->warm; K.act = (T*)b->act; K.ctrl = (T*)b->ctrl;
   K.p_stiff = b->has_stiff ? b->p_stiff : nullptr; K.p_damp = b->has_damp ? b->p_damp : nullptr;
   K.p_tdamp = b->has_tdamp ? b->p_tdamp : nullptr; K.p_objoff = b->has_objoff ? b->p_objoff : nullptr;
@@ -681,9 +689,9 @@ extern "C" int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int
   }
   auto scalar = [&](double v) { if (out && cap > 0) out[0] = v; return 1; };
   if (k == "tensor_memory") {
-    // [columns the CTA allocates (0: the equality rows stay in shared memory), columns per warp]
-    const double t[2] = {(double)b->tm_cols, (double)b->tm_stride};
-    return put(t, 2);
+    // [columns the CTA allocates (0: the equality rows stay in shared memory), columns per warp, record ring in use]
+    const double t[3] = {(double)b->tm_cols, (double)b->tm_stride, (double)b->rec_ring};
+    return put(t, 3);
   }
   if (k == "ncon") return scalar(ncontot);
   if (k == "nefc") return scalar(nefc);

@@ -200,6 +200,7 @@ struct KArgs2 {
   int step_barrier;            // 1: the warps of a CTA start every physics step together (CTA barrier per step)
   int tm_cols;                 // tensor-memory columns the CTA allocates (power of two >= 32), 0: the (u, n) rows stay in shared memory
   int tm_stride;               // columns per warp: warp w owns [tm_stride (w / 4), +tm_stride) of its lane quarter
+  int rec_ring;                // 1: contact records reach the chain phase through a two-entry shared-memory ring per lane (needs tm_cols)
   unsigned char* scratch;      // global aux slots [gridDim.x * WPW][L.gs_stride] (null when aux_in_smem)
   // state, world-major
   T *qpos, *qvel, *warm, *act, *ctrl;
@@ -329,6 +330,25 @@ template <typename T> __device__ __forceinline__ void tm_wait_ld(T&, T&) {}
 __device__ __forceinline__ void tm_wait_st() {}
 #endif
 
+// asynchronous copy of one contact record (NB bytes, 16-byte pieces) from the global scratch into shared memory: no
+// registers are held while the record is on its way from L2 (cp.async.cg: straight from L2, which is where the record's
+// force words were last written)
+template <int NB>
+__device__ __forceinline__ void cp_rec(unsigned char* dst_smem, const unsigned char* src) {
+#if defined(__CUDA_ARCH__)
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+#pragma unroll
+  for (int i = 0; i < NB; i += 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i), "l"(src + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+  memcpy(dst_smem, src, NB);
+#endif
+}
+__device__ __forceinline__ void cp_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
 // division inside the contact blocks: MUFU.RCP + FMUL on the fp32 fast path (2 ulp), IEEE in the verification build
 template <typename T> __device__ __forceinline__ T tdiv(T a, T b);
 template <> __device__ __forceinline__ double tdiv<double>(double a, double b) { return a / b; }
@@ -1534,8 +1554,10 @@ struct World2 {
     ld4(r + CR_A, x.Aw); ld4(r + CR_A + 4, x.Aw + 4);   // A00 A01 A02 A11 | A12 A22 a11n kb
     ld4(r + CR_F, x.w3);           // f0 f1 f2, friction multiplier of the previous sweep
   }
-  __device__ __forceinline__ T contact_block(T* r, int e, T* ag, const T* mv, T* asl, T frc) {
-    Rec x; load_rec(x, r);
+  // rl: where the record is read from (the record itself, or its copy in the lane's shared-memory ring); r: the record in
+  // the scratch, which takes the new force
+  __device__ __forceinline__ T contact_block(T* r, const T* rl, int e, T* ag, const T* mv, T* asl, T frc) {
+    Rec x; load_rec(x, rl);
     // a contact without a slider (centre sphere) reads and writes the dummy slider: its ns and 1/m words are zero
     T* const pae = asl + (e >= 0 ? e : D.ns);
     const T ae = *pae;
@@ -1606,6 +1628,7 @@ struct World2 {
     T frc;                  // contact friction coefficient
     int lmask, mystart, mycnt;
     bool chain_lane;
+    bool primed;            // ring mode: the first record of the next sweep is already on its way
   };
   // this lane's slice of the contact schedule (contacts in their sequential order) and the chain's qacc
   __device__ void chain_prologue(ChainState& cs) {
@@ -1614,7 +1637,7 @@ struct World2 {
     cs.asl = reinterpret_cast<T*>(smem_base + keep_off((int)(reinterpret_cast<unsigned char*>(a() + D.nfd) - smem_base)));
     cs.frc = keep_val(C.con_fr);
     cs.lmask = cs.chain_lane ? misc(M2_LMASK + sl) : 0;
-    cs.mystart = 0; cs.mycnt = 0;
+    cs.mystart = 0; cs.mycnt = 0; cs.primed = false;
     const int ncon = misc(M2_NCON);
     const int* const itl = pin_g(auxi + L.i_tl);
     const int* const icon = pin_g(auxi + L.i_con);
@@ -1639,8 +1662,18 @@ struct World2 {
   // or worse and removed again: records staged in registers one block ahead -- 1.1 KB of spills, -12 %; helper lanes
   // handing records over by shuffles, round 1; a reordered friction solve and a speculative M^-1 J' update -- the chain
   // phase sits where issue slots (4 warps x ~120 000 instructions per step) and single-warp latency (~540 000 cycles) meet.)
+  // RING: the record of the lane's next block is copied asynchronously (cp.async, L2 -> shared memory) into the other
+  // entry of a two-entry ring while the current block is computed, and the block reads its record from shared memory.
+  // The ring of lane sl sits in the world's (aref, R) region, which is dead once rows_to_tm has moved the equality rows
+  // to tensor memory: entry stride RB, lane stride 2 RB + 16 (the two chain lanes of a world land in different banks).
+  // The contact-only profile (profiles/r02y_k2_ncu_contact_summary.txt) had 26 % of all stall samples on the first uses
+  // of the record words: the L1 prefetch does not hold -- 64 worlds x ~2 blocks per slot x 128 B x (current + two ahead)
+  // is twice the 27 KB of L1 that 228 KB of shared memory leave.
+  template <bool RING>
   __device__ T chain_phase(ChainState& cs, int tmaxw, bool done) {
     T impr = 0;
+    constexpr unsigned RB = CR_STRIDE * sizeof(T);
+    unsigned char* const ring = smem_base + keep_off((int)(reinterpret_cast<unsigned char*>(hot) - smem_base) + sl * (int)(2 * RB + 16));
     const int* order = reinterpret_cast<const int*>(K.scratch + keep_off((long long)(reinterpret_cast<unsigned char*>(auxi + L.i_order + cs.mystart) - K.scratch)));
     const int cnt = done ? 0 : cs.mycnt;
     int entA = 0, entB = 0, entC = 0;
@@ -1648,7 +1681,9 @@ struct World2 {
     if (cnt > 1) entB = order[1];
     if (cnt > 2) entC = order[2];
     const int ent0 = entA;
-    if (cnt > 1) prefetch_l1(crec(entB & 0xff));
+    if (RING) {
+      if (cnt > 0 && !cs.primed) { cp_rec<RB>(ring, reinterpret_cast<const unsigned char*>(crec(ent0 & 0xff))); cs.primed = true; }
+    } else if (cnt > 1) prefetch_l1(crec(entB & 0xff));
     if (cs.chain_lane && !done) {
 #pragma unroll
       for (int jl = 0; jl < MAXCD; jl++) {
@@ -1674,26 +1709,37 @@ struct World2 {
     {
       // one byte base for the records of this world; an entry's record is base + index * 128 (CR_STRIDE reals)
       unsigned char* const recb = K.scratch + keep_off((long long)(reinterpret_cast<unsigned char*>(aux + L.crec) - K.scratch));
-      constexpr unsigned RB = CR_STRIDE * sizeof(T);
       for (int t = 1; t <= tmaxw; t++) {
         if (k < cnt && ((entA >> 8) & 0xff) == t) {
           T* r = reinterpret_cast<T*>(recb + (size_t)((unsigned)(entA & 0xff) * RB));
           const int e = (entA >> 16) - 1;
+          const T* rl = r;
+          if (RING) {
+            cp_wait();                                                // this block's record has landed in its ring entry
+            rl = reinterpret_cast<const T*>(ring + (k & 1) * RB);
+            if (k + 1 < cnt) cp_rec<RB>(ring + ((k + 1) & 1) * RB, recb + (size_t)((unsigned)(entB & 0xff) * RB));
+          }
           k++;
+          if (!RING) {
 #if SG_PF_DIST == 1
-          if (k < cnt) prefetch_l1(recb + (size_t)((unsigned)(entB & 0xff) * RB));       // the next block's record
+            if (k < cnt) prefetch_l1(recb + (size_t)((unsigned)(entB & 0xff) * RB));       // the next block's record
 #else
-          if (k + 1 < cnt) prefetch_l1(recb + (size_t)((unsigned)(entC & 0xff) * RB));   // two blocks ahead, as the entries
+            if (k + 1 < cnt) prefetch_l1(recb + (size_t)((unsigned)(entC & 0xff) * RB));   // two blocks ahead, as the entries
 #endif
+          }
           const int entD = (k + 2 < cnt) ? order[k + 2] : 0;
-          impr -= contact_block(r, e, cs.ag, cs.mv, cs.asl, cs.frc);
+          impr -= contact_block(r, rl, e, cs.ag, cs.mv, cs.asl, cs.frc);
           entA = entB; entB = entC; entC = entD;
         }
         __syncwarp();
       }
     }
-    // next sweep's first entries and record: towards L1 while the equality block is swept
-    if (cnt > 0) { prefetch_l1(order); prefetch_l1(crec(ent0 & 0xff)); }
+    // next sweep's first entries and record: on their way while the equality block is swept
+    if (cnt > 0) {
+      prefetch_l1(order);
+      if (RING) cp_rec<RB>(ring, reinterpret_cast<const unsigned char*>(crec(ent0 & 0xff)));
+      else prefetch_l1(crec(ent0 & 0xff));
+    }
     return impr;
   }
   __device__ void chain_epilogue(const ChainState& cs) {
@@ -1929,13 +1975,14 @@ struct World2 {
         if (!__any_sync(FULLMASK, !done)) break;
         T impr = equality_sweep(tn, done);
         tick(PH_PGS_EQUALITY);
-        impr += chain_phase(cs, tmaxw, done);
+        impr += K.rec_ring ? chain_phase<true>(cs, tmaxw, done) : chain_phase<false>(cs, tmaxw, done);
         tick(PH_PGS_CHAIN);
         impr = gsum(impr) * C.impr_scale;
         if (!done) { iter++; if (impr < C.tol) done = true; }
       }
       chain_epilogue(cs);
     }
+    if (K.rec_ring) cp_wait();     // (a record requested for a sweep that did not happen)
     if (sl == 0) misc(M2_ITERS) = iter;
     __syncwarp();
   }

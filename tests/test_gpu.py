@@ -476,4 +476,34 @@ def test_plain_c_caller_matches_the_python_path(torch_cuda, batched, tmp_path):
     assert status.shape == (W,) and (status == 0).all()
     env = make_env(batched, torch, W=W, dtype=torch.float32)
     traj, k, st = env.rollout(stiffness=[300.0 + 1100.0 * w / (W - 1) for w in range(W)])
-    np.testing.assert_array_equal(traj.cpu().numpy(), raw)
+    np.testing.assert_array_equal(traj.cpu().numpy(), raw)@pytest.mark.gpu
+def test_tensor_memory_rows_and_record_ring_change_no_bit(torch_cuda, batched, monkeypatch):
+    """The default geometry (16 warps, one CTA per SM) keeps the equality rows in tensor memory and feeds the contact
+    blocks from the shared-memory record ring (cp.async one block ahead).  Both are storage changes: the trajectories of
+    a squeeze episode with per-world stiffness, damping and pose equal those of SOFTGRIP_TMEM=0 (rows in shared memory,
+    records read from the scratch) and of SOFTGRIP_RING=0 bit for bit, in both precisions; a small batch (a few warps
+    per CTA, tensor memory forced) as well."""
+    torch = torch_cuda
+    sched = batched.default_schedule(2, n_settle=10, n_iter=40, open_close_div=20)
+    for dtype, W in ((torch.float32, 9472 + 37), (torch.float64, 700), (torch.float32, 19)):
+        rng = np.random.default_rng(5)
+        k, d, off = rng.uniform(300, 1400, W), rng.uniform(100.0, 200.0, W), rng.uniform(-0.05, 0.05, (W, 3))
+        out = []
+        for tmem, ring in ((None if W > 100 else "1", None), ("0", None), (None if W > 100 else "1", "0")):
+            for key, val in (("SOFTGRIP_TMEM", tmem), ("SOFTGRIP_RING", ring)):
+                if val is None: monkeypatch.delenv(key, raising=False)
+                else: monkeypatch.setenv(key, val)
+            env = make_env(batched, torch, W=W, dtype=dtype)
+            tm = env.debug(0, "tensor_memory")
+            assert (tm[0] > 0) == (tmem != "0") and (tm[2] > 0) == (tmem != "0" and ring != "0"), (tmem, ring, tm)
+            env.set_params(damping=d, object_offset=off)
+            traj, _, st = env.rollout(schedule=sched, stiffness=k)
+            assert int((st.cpu().numpy() & 1).sum()) == 0
+            out.append(traj.cpu().numpy())
+            del env
+        np.testing.assert_array_equal(out[0], out[1])
+        np.testing.assert_array_equal(out[0], out[2])
+        assert np.abs(out[0][:, -1, :]).max() > 0
+
+
+

@@ -152,6 +152,46 @@ def test_emulated_multi_warp_cta_and_persistent_batches(emu, batched):
     assert np.abs(out[0] - out[2]).max() / np.abs(out[0]).max() < 1e-4      # other lane count: other summation order
 
 
+@pytest.mark.parametrize("prec,lpw,nw", [(32, 8, 2), (64, 8, 5), (32, 32, 1), (32, 4, 2)])
+def test_emulated_tensor_memory_rows_and_record_ring_are_bit_identical(emu, states, monkeypatch, prec, lpw, nw):
+    """The equality rows in tensor memory (tcgen05.ld / st, one TMEM lane per thread) and the contact records read through
+    the per-lane shared-memory ring compute the same bits as the rows in shared memory and the records read from the
+    scratch: same arithmetic, other storage.  The emulator aborts on a tensor-memory address that is not uniform over
+    the warp, outside the warp's lane quarter or outside the 512 columns; several warps per CTA exercise the column
+    blocks of warps 4.. (nw = 5) and the quarters of warps 1..3."""
+    W = (32 // lpw) * nw + 1
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SOFTGRIP_TMEM", mode)
+        env = emu.EmuBatch(blob_path("softbox"), W, prec=prec, lpw=lpw, nw=nw)
+        tm = env.debug("tensor_memory")
+        esz, nrow = prec // 8, int(env.debug("sweep_schedule")[3])
+        ring_fits = lpw * (2 * 32 * esz + 16) <= 2 * nrow * esz      # two 32-word records + skew per lane in the (aref, R) region
+        assert (tm[0] > 0) == (mode == "1") and (tm[2] > 0) == (mode == "1" and ring_fits)
+        assert ring_fits == (lpw <= 8)
+        if mode == "1":
+            words = 2 if prec == 32 else 4
+            assert tm[1] == (env.debug("sweep_schedule")[0] + 1) * words and tm[0] >= tm[1] * ((nw + 3) // 4) and tm[0] <= 512
+        env.set_params(stiffness=np.linspace(400.0, 1000.0, W))
+        env.set_debug_world(W - 1)
+        res = []
+        for i in (len(states["step"]) - 1, int(np.argmax(states["ncon1"]))):     # late squeeze and the contact-richest snapshot
+            env.set_state(states["q"][i], states["v"][i], states["act"][i], states["warm"][i])
+            env.set_ctrl([states["ctrl"][i]] * 2)
+            sens, touch = env.step(2)
+            res.append((sens.copy(), touch.copy(), [x.copy() for x in env.get_state()], env.debug("efc_force").copy(), env.debug("solver_iter").copy()))
+        assert (env.status() == 0).all()
+        out[mode] = res
+        env.close()
+    for (s0, t0, g0, f0, it0), (s1, t1, g1, f1, it1) in zip(out["0"], out["1"]):
+        np.testing.assert_array_equal(s0, s1)
+        np.testing.assert_array_equal(t0, t1)
+        for x, y in zip(g0, g1):
+            np.testing.assert_array_equal(x, y)
+        np.testing.assert_array_equal(f0, f1)
+        np.testing.assert_array_equal(it0, it1)
+
+
 @pytest.mark.parametrize("W,nw", [(4, None), (18, 4)])
 def test_emulated_divergence_is_contained_in_its_group(emu, W, nw):
     """A diverging world is reset and flagged; the other worlds of the same warp / CTA are bit-identical to a

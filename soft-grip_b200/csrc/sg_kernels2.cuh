@@ -239,6 +239,11 @@ template <> __device__ __forceinline__ float trcp<float>(float x) {
 #ifndef SG_HOIST
 #define SG_HOIST 1
 #endif
+// the chain's M^-1 block is requested from shared memory before the cost test of a contact block instead of after it:
+// 1.447e7 -> 1.474e7 world-steps/s (profiles/r02zc_sweep.log)
+#ifndef SG_MV_EARLY
+#define SG_MV_EARLY 1
+#endif
 // (the OFFSET is pinned, not the pointer: a pointer that went through an asm statement loses its address space and every
 // access through it becomes a generic load)
 __device__ __forceinline__ long long keep_off(long long o) {
@@ -333,22 +338,35 @@ __device__ __forceinline__ void tm_wait_st() {}
 // asynchronous copy of one contact record (NB bytes, 16-byte pieces) from the global scratch into shared memory: no
 // registers are held while the record is on its way from L2 (cp.async.cg: straight from L2, which is where the record's
 // force words were last written)
-template <int NB>
-__device__ __forceinline__ void cp_rec(unsigned char* dst_smem, const unsigned char* src) {
-#if defined(__CUDA_ARCH__)
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-#pragma unroll
-  for (int i = 0; i < NB; i += 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i), "l"(src + i) : "memory");
-  asm volatile("cp.async.commit_group;" ::: "memory");
-#else
-  memcpy(dst_smem, src, NB);
-#endif
-}
 __device__ __forceinline__ void cp_wait() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
 }
+// The ring is addressed through its 32-bit shared-window address, pinned in a register (see keep_off): with a generic
+// pointer ptxas rebuilds the window base (S2UR CgaCtaId, ULEA ..) and the lane's offset in every block.
+#if defined(__CUDA_ARCH__)
+typedef unsigned ring_t;
+__device__ __forceinline__ ring_t ring_of(unsigned char* p) { return (unsigned)keep_off((int)__cvta_generic_to_shared(p)); }
+template <int NB>
+__device__ __forceinline__ void cp_rec(ring_t d, const unsigned char* src) {
+#pragma unroll
+  for (int i = 0; i < NB; i += 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i), "l"(src + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void lds4(ring_t a, float* o) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(a));
+}
+__device__ __forceinline__ void lds4(ring_t a, double* o) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(a));
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[2]), "=d"(o[3]) : "r"(a + 16));
+}
+#else
+typedef unsigned char* ring_t;
+__device__ __forceinline__ ring_t ring_of(unsigned char* p) { return p; }
+template <int NB> __device__ __forceinline__ void cp_rec(ring_t d, const unsigned char* src) { memcpy(d, src, NB); }
+template <typename T> __device__ __forceinline__ void lds4(ring_t a, T* o) { memcpy(o, a, 4 * sizeof(T)); }
+#endif
 // division inside the contact blocks: MUFU.RCP + FMUL on the fp32 fast path (2 ulp), IEEE in the verification build
 template <typename T> __device__ __forceinline__ T tdiv(T a, T b);
 template <> __device__ __forceinline__ double tdiv<double>(double a, double b) { return a / b; }
@@ -513,6 +531,11 @@ template <typename T> __device__ __forceinline__ void ld2(const T* p, T& x, T& y
 template <> __device__ __forceinline__ void ld2<float>(const float* p, float& x, float& y) { const float2 v = *reinterpret_cast<const float2*>(p); x = v.x; y = v.y; }
 template <> __device__ __forceinline__ void ld2<double>(const double* p, double& x, double& y) { const double2 v = *reinterpret_cast<const double2*>(p); x = v.x; y = v.y; }
 
+// four consecutive ints of a 16-byte aligned per-world int array (contact tables: one L2 round trip per four entries)
+__device__ __forceinline__ void ldi4(const int* p, int* o) {
+  const int4* q = reinterpret_cast<const int4*>(p);
+  const int4 v = *q; o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
 template <typename T> __device__ __forceinline__ void ldg2(const T* p, T& x, T& y);
 template <> __device__ __forceinline__ void ldg2<float>(const float* p, float& x, float& y) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); x = v.x; y = v.y; }
 template <> __device__ __forceinline__ void ldg2<double>(const double* p, double& x, double& y) { const double2 v = __ldg(reinterpret_cast<const double2*>(p)); x = v.x; y = v.y; }
@@ -1427,20 +1450,27 @@ struct World2 {
       const int ce = icon[i];
       const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
       T* r = rec0 + CR_STRIDE * i;
-      const T R0 = r[CR_R0], R1 = R0 * C.inv_impratio;
+      // the words of the record in one batch of vector loads (one L2 round trip beside the one of icon[i])
+      T jg[12], w1[4], w2[4];
+      ld4(r + CR_JG, jg); ld4(r + CR_JG + 4, jg + 4); ld4(r + CR_JG + 8, jg + 8);
+      ld4(r + CR_NS, w1); ld4(r + CR_AREF, w2);
+      const T R0 = w2[3], R1 = R0 * C.inv_impratio;
       T jar[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         T sa = 0;
-        if (e >= 0) sa = r[CR_NS + k] * a()[nfd + e];
-        if (c >= 0) for (int jj = 0; jj < D.ncd[c]; jj++) sa += r[CR_JG + 4 * k + jj] * a()[D.chain_dof0[c] + jj];
-        jar[k] = sa - r[CR_AREF + k];
+        if (e >= 0) sa = w1[k] * a()[nfd + e];
+        if (c >= 0) {
+#pragma unroll
+          for (int jj = 0; jj < MAXCD; jj++) if (jj < D.ncd[c]) sa += jg[4 * k + jj] * a()[D.chain_dof0[c] + jj];
+        }
+        jar[k] = sa - w2[k];
       }
       T f[3];
       cone_force(jar, R0, R1, f);
       const T Rr[3] = {R0, R1, R1};
 #pragma unroll
-      for (int k = 0; k < 3; k++) { r[CR_F + k] = f[k]; cost += f[k] * (T(0.5) * Rr[k] * f[k] - r[CR_AREF + k]); }
+      for (int k = 0; k < 3; k++) { r[CR_F + k] = f[k]; cost += f[k] * (T(0.5) * Rr[k] * f[k] - w2[k]); }
     }
     __syncwarp();
     // J^T f of the contacts, added after the limits.  Deterministic without atomics: the contacts of slider e are
@@ -1452,22 +1482,26 @@ struct World2 {
       for (int c = 0; c < MAXCHAIN; c++)
 #pragma unroll
         for (int jj = 0; jj < MAXCD; jj++) gd[c][jj] = 0;
-      for (int i = 0; i < ncon; i++) {
-        const int ce = icon[i];
-        const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
-        if ((e >= 0 ? e : i) % LPW != sl) continue;
-        const T* r = rec0 + CR_STRIDE * i;
-        T jg[12], w1[4], f[4];
-        ld4(r + CR_NS, w1); ld4(r + CR_F, f);
-        if (e >= 0) jtf[nfd + e] += w1[0] * f[0] + w1[1] * f[1] + w1[2] * f[2];
-        if (c >= 0) {
-          ld4(r + CR_JG, jg); ld4(r + CR_JG + 4, jg + 4); ld4(r + CR_JG + 8, jg + 8);
+      for (int i0 = 0; i0 < ncon; i0 += 4) {
+        const int4 ce4 = *reinterpret_cast<const int4*>(icon + i0);     // four table entries per L2 round trip
+        for (int j = 0; j < 4 && i0 + j < ncon; j++) {
+          const int i = i0 + j;
+          const int ce = j == 0 ? ce4.x : j == 1 ? ce4.y : j == 2 ? ce4.z : ce4.w;
+          const int c = (ce & 15) - 1, e = (ce >> 4) - 1;
+          if ((e >= 0 ? e : i) % LPW != sl) continue;
+          const T* r = rec0 + CR_STRIDE * i;
+          T jg[12], w1[4], f[4];
+          ld4(r + CR_NS, w1); ld4(r + CR_F, f);
+          if (c >= 0) { ld4(r + CR_JG, jg); ld4(r + CR_JG + 4, jg + 4); ld4(r + CR_JG + 8, jg + 8); }
+          if (e >= 0) jtf[nfd + e] += w1[0] * f[0] + w1[1] * f[1] + w1[2] * f[2];
+          if (c >= 0) {
 #pragma unroll
-          for (int cc = 0; cc < MAXCHAIN; cc++)
-            if (cc == c) {
+            for (int cc = 0; cc < MAXCHAIN; cc++)
+              if (cc == c) {
 #pragma unroll
-              for (int jj = 0; jj < MAXCD; jj++) gd[cc][jj] += jg[jj] * f[0] + jg[4 + jj] * f[1] + jg[8 + jj] * f[2];
-            }
+                for (int jj = 0; jj < MAXCD; jj++) gd[cc][jj] += jg[jj] * f[0] + jg[4 + jj] * f[1] + jg[8 + jj] * f[2];
+              }
+          }
         }
       }
 #pragma unroll
@@ -1554,17 +1588,30 @@ struct World2 {
     ld4(r + CR_A, x.Aw); ld4(r + CR_A + 4, x.Aw + 4);   // A00 A01 A02 A11 | A12 A22 a11n kb
     ld4(r + CR_F, x.w3);           // f0 f1 f2, friction multiplier of the previous sweep
   }
-  // rl: where the record is read from (the record itself, or its copy in the lane's shared-memory ring); r: the record in
-  // the scratch, which takes the new force
-  __device__ __forceinline__ T contact_block(T* r, const T* rl, int e, T* ag, const T* mv, T* asl, T frc) {
-    Rec x; load_rec(x, rl);
+  __device__ __forceinline__ void load_rec_ring(Rec& x, ring_t a) const {
+    constexpr unsigned S = sizeof(T);
+    lds4(a + S * CR_JG, x.jg); lds4(a + S * (CR_JG + 4), x.jg + 4); lds4(a + S * (CR_JG + 8), x.jg + 8);
+    lds4(a + S * CR_NS, x.w1); lds4(a + S * CR_AREF, x.w2);
+    lds4(a + S * CR_A, x.Aw); lds4(a + S * (CR_A + 4), x.Aw + 4);
+    lds4(a + S * CR_F, x.w3);
+  }
+  // r: the record in the scratch, which takes the new force; RING: the record is read from its copy in the lane's
+  // shared-memory ring (rl) instead
+  template <bool RING>
+  __device__ __forceinline__ T contact_block(T* r, ring_t rl, int e, T* ag, const T* mv, T* asl, T frc, T iwu) {
+    Rec x;
+    if (RING) load_rec_ring(x, rl); else load_rec(x, r);
     // a contact without a slider (centre sphere) reads and writes the dummy slider: its ns and 1/m words are zero
     T* const pae = asl + (e >= 0 ? e : D.ns);
     const T ae = *pae;
     const T* jg = x.jg; const T* w1 = x.w1; const T* w2 = x.w2; const T* Aw = x.Aw; const T* w3 = x.w3;
     const T A00 = Aw[0], A01 = Aw[1], A02 = Aw[2], A11 = Aw[3], A12 = Aw[4], A22 = Aw[5];
     const T R0 = w2[3], R1 = R0 * C.inv_impratio;
+#if SG_SLOT8
+    const T iwe = e >= 0 ? iwu : T(0);                   // 1 / m of the contact's slider: one value for the whole shell (SG_SLOT8)
+#else
     const T iwe = e >= 0 ? stiw(e) : T(0);               // 1 / m of the contact's slider (CTA-shared table)
+#endif
     const T old0 = w3[0], old1 = w3[1], old2 = w3[2];
     T la = w3[3];
     T res[3];
@@ -1598,6 +1645,12 @@ struct World2 {
       if (f0 < T(SG_MINVAL)) { f1 = 0; f2 = 0; la = 0; }
       else friction(f1, f2, la, A11, A12, A22, Aw[6], w1[3], Aw[7], bc, frc, f0);
     }
+#if SG_MV_EARLY
+    // the chain's M^-1 block on its way (shared memory) while the cost test runs
+    T m16[16];
+#pragma unroll
+    for (int ii = 0; ii < MAXCD; ii++) ld4(mv + 4 * ii, m16 + 4 * ii);
+#endif
     // cost change, revert if positive
     T d0f = f0 - old0, d1f = f1 - old1, d2f = f2 - old2;
     T change = T(0.5) * (d0f * (A00 * d0f + A01 * d1f + A02 * d2f) + d1f * (A01 * d0f + A11 * d1f + A12 * d2f) + d2f * (A02 * d0f + A12 * d1f + A22 * d2f))
@@ -1614,7 +1667,11 @@ struct World2 {
     for (int jj = 0; jj < MAXCD; jj++) gv[jj] = jg[jj] * d0f + jg[4 + jj] * d1f + jg[8 + jj] * d2f;
 #pragma unroll
     for (int ii = 0; ii < MAXCD; ii++) {
+#if SG_MV_EARLY
+      const T* m4 = m16 + 4 * ii;
+#else
       T m4[4]; ld4(mv + 4 * ii, m4);
+#endif
       ag[ii] += m4[0] * gv[0] + m4[1] * gv[1] + m4[2] * gv[2] + m4[3] * gv[3];
     }
     return change;
@@ -1626,6 +1683,7 @@ struct World2 {
     const T* mv;            // the chain's M^-1 block (shared memory)
     T* asl;                 // the world's slider accelerations (shared memory): a() + nfd
     T frc;                  // contact friction coefficient
+    T iwu;                  // 1 / slider mass of a uniform shell (SG_SLOT8)
     int lmask, mystart, mycnt;
     bool chain_lane;
     bool primed;            // ring mode: the first record of the next sweep is already on its way
@@ -1636,21 +1694,29 @@ struct World2 {
     cs.mv = reinterpret_cast<const T*>(smem_base + keep_off((int)(reinterpret_cast<unsigned char*>(hot + L.minv + 16 * (cs.chain_lane ? sl : 0)) - smem_base)));
     cs.asl = reinterpret_cast<T*>(smem_base + keep_off((int)(reinterpret_cast<unsigned char*>(a() + D.nfd) - smem_base)));
     cs.frc = keep_val(C.con_fr);
+    cs.iwu = keep_val(stim[0]);
     cs.lmask = cs.chain_lane ? misc(M2_LMASK + sl) : 0;
     cs.mystart = 0; cs.mycnt = 0; cs.primed = false;
     const int ncon = misc(M2_NCON);
     const int* const itl = pin_g(auxi + L.i_tl);
     const int* const icon = pin_g(auxi + L.i_con);
-    for (int i = 0; i < ncon; i++) {
-      const int ln = itl[i] >> 16;
-      if (ln < sl) cs.mystart++;
-      else if (ln == sl) cs.mycnt++;
+    for (int i0 = 0; i0 < ncon; i0 += 4) {
+      int tl4[4]; ldi4(itl + i0, tl4);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int ln = tl4[j] >> 16;
+        if (i0 + j < ncon) { if (ln < sl) cs.mystart++; else if (ln == sl) cs.mycnt++; }
+      }
     }
     int k = 0;
     int* const iord = pin_g(auxi + L.i_order + cs.mystart);
-    for (int i = 0; i < ncon; i++) {
-      const int tl = itl[i];
-      if ((tl >> 16) == sl) { iord[k] = i | ((tl & 0xff) << 8) | ((icon[i] >> 4) << 16); k++; }
+    for (int i0 = 0; i0 < ncon; i0 += 4) {
+      int tl4[4]; ldi4(itl + i0, tl4);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int i = i0 + j, tl = tl4[j];
+        if (i < ncon && (tl >> 16) == sl) { iord[k] = i | ((tl & 0xff) << 8) | ((icon[i] >> 4) << 16); k++; }
+      }
     }
 #pragma unroll
     for (int jj = 0; jj < MAXCD; jj++) cs.ag[jj] = (cs.chain_lane && jj < D.ncd[sl]) ? a()[D.chain_dof0[sl] + jj] : T(0);
@@ -1673,7 +1739,7 @@ struct World2 {
   __device__ T chain_phase(ChainState& cs, int tmaxw, bool done) {
     T impr = 0;
     constexpr unsigned RB = CR_STRIDE * sizeof(T);
-    unsigned char* const ring = smem_base + keep_off((int)(reinterpret_cast<unsigned char*>(hot) - smem_base) + sl * (int)(2 * RB + 16));
+    const ring_t ring = ring_of(reinterpret_cast<unsigned char*>(hot) + sl * (int)(2 * RB + 16));
     const int* order = reinterpret_cast<const int*>(K.scratch + keep_off((long long)(reinterpret_cast<unsigned char*>(auxi + L.i_order + cs.mystart) - K.scratch)));
     const int cnt = done ? 0 : cs.mycnt;
     int entA = 0, entB = 0, entC = 0;
@@ -1713,10 +1779,10 @@ struct World2 {
         if (k < cnt && ((entA >> 8) & 0xff) == t) {
           T* r = reinterpret_cast<T*>(recb + (size_t)((unsigned)(entA & 0xff) * RB));
           const int e = (entA >> 16) - 1;
-          const T* rl = r;
+          ring_t rl = ring;
           if (RING) {
             cp_wait();                                                // this block's record has landed in its ring entry
-            rl = reinterpret_cast<const T*>(ring + (k & 1) * RB);
+            rl = ring + (k & 1) * RB;
             if (k + 1 < cnt) cp_rec<RB>(ring + ((k + 1) & 1) * RB, recb + (size_t)((unsigned)(entB & 0xff) * RB));
           }
           k++;
@@ -1728,7 +1794,7 @@ struct World2 {
 #endif
           }
           const int entD = (k + 2 < cnt) ? order[k + 2] : 0;
-          impr -= contact_block(r, rl, e, cs.ag, cs.mv, cs.asl, cs.frc);
+          impr -= contact_block<RING>(r, rl, e, cs.ag, cs.mv, cs.asl, cs.frc, cs.iwu);
           entA = entB; entB = entC; entC = entD;
         }
         __syncwarp();

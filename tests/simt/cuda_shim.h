@@ -12,6 +12,7 @@ enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cuda
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 struct cudaDeviceProp { size_t sharedMemPerBlockOptin; int multiProcessorCount; };
 struct int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };

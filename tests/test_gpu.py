@@ -476,7 +476,9 @@ def test_plain_c_caller_matches_the_python_path(torch_cuda, batched, tmp_path):
     assert status.shape == (W,) and (status == 0).all()
     env = make_env(batched, torch, W=W, dtype=torch.float32)
     traj, k, st = env.rollout(stiffness=[300.0 + 1100.0 * w / (W - 1) for w in range(W)])
-    np.testing.assert_array_equal(traj.cpu().numpy(), raw)@pytest.mark.gpu
+    np.testing.assert_array_equal(traj.cpu().numpy(), raw)
+
+
 def test_tensor_memory_rows_and_record_ring_change_no_bit(torch_cuda, batched, monkeypatch):
     """The default geometry (16 warps, one CTA per SM) keeps the equality rows in tensor memory and feeds the contact
     blocks from the shared-memory record ring (cp.async one block ahead).  Both are storage changes: the trajectories of
@@ -504,6 +506,3 @@ def test_tensor_memory_rows_and_record_ring_change_no_bit(torch_cuda, batched, m
         np.testing.assert_array_equal(out[0], out[1])
         np.testing.assert_array_equal(out[0], out[2])
         assert np.abs(out[0][:, -1, :]).max() > 0
-
-
-

@@ -556,6 +556,30 @@ template <> struct alignas(8) Slot<double> { unsigned x, y; double iw1, iw2; };
 #endif
 template <typename T> __device__ __forceinline__ Slot<T> ld_slot(const Slot<T>* p) { return *p; }
 
+// Once-per-step loops over the sliders / rows of a lane: ptxas does not move the global loads of iteration i + 1 above
+// the stores (or the divergent arithmetic) of iteration i, so a plain loop pays one L2 round trip (~400 cycles at this
+// occupancy) per iteration -- 41 of them in the row loop, 14 in every slider loop, ~140 per step, a tenth of a
+// contact-free step.  batched() runs such a loop in two phases per NB elements: every load of the batch first (into a
+// small struct per element, no stores in between), then the arithmetic and the stores.  Same operations per element, same
+// element order: bit-identical results.
+// (the lambdas are force-inlined: inside this very large kernel the inliner otherwise leaves some of them as calls, and
+// their by-reference captures then live in local memory)
+#define SG_INL __attribute__((always_inline))
+template <int NB, typename V, typename LoadF, typename UseF>
+__device__ __forceinline__ void batched(int first, int limit, int stride, LoadF load, UseF use) {
+  for (int e0 = first; e0 < limit; e0 += stride * NB) {
+    V v[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) { const int e = e0 + b * stride; V x{}; if (e < limit) load(e, x); v[b] = x; }   // (always written: stays in registers)
+#pragma unroll
+    for (int b = 0; b < NB; b++) { const int e = e0 + b * stride; if (e < limit) use(e, v[b]); }
+  }
+}
+template <typename T> struct V1 { T a; };
+template <typename T> struct V2 { T a, b; };
+template <typename T> struct V3 { T a, b, c; };
+template <typename T> struct V5 { T a, b, c, d, e; };
+
 // ---------------------------------------------------------------------------------------------
 // the world
 // ---------------------------------------------------------------------------------------------
@@ -1047,17 +1071,18 @@ struct World2 {
       const T* __restrict__ qsl = pin_g(q() + D.nfd);
       const T* __restrict__ c0 = pin_t(tab(D.o_sl_cap0));
       T* cen = scr(L.sc_cen);
-#pragma unroll 2
-      for (int e = sl; e < D.ns; e += LPW) {
-        const T qe = qsl[e];
+      struct CenV { T q, c[3]; };
+      batched<8, CenV>(sl, D.ns, LPW,
+        [&](int e, CenV& x) SG_INL { x.q = qsl[e]; x.c[0] = c0[3 * e]; x.c[1] = c0[3 * e + 1]; x.c[2] = c0[3 * e + 2]; },
+        [&](int e, const CenV& x) SG_INL {
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const T ck = off[k] + c0[3 * e + k] + sax[3 * e + k] * qe;
-          cen[3 * e + k] = ck;
-          blo[k] = ck < blo[k] ? ck : blo[k]; bhi[k] = ck > bhi[k] ? ck : bhi[k];     // a NaN centre leaves the bounds alone
-          if (!(ck == ck)) { blo[k] = -T(SG_MAXVAL); bhi[k] = T(SG_MAXVAL); }          // ... so it opens them explicitly
-        }
-      }
+          for (int k = 0; k < 3; k++) {
+            const T ck = off[k] + x.c[k] + sax[3 * e + k] * x.q;
+            cen[3 * e + k] = ck;
+            blo[k] = ck < blo[k] ? ck : blo[k]; bhi[k] = ck > bhi[k] ? ck : bhi[k];     // a NaN centre leaves the bounds alone
+            if (!(ck == ck)) { blo[k] = -T(SG_MAXVAL); bhi[k] = T(SG_MAXVAL); }          // ... so it opens them explicitly
+          }
+        });
       // bounding box of the capsule centres of this world (sub-warp min / max)
 #pragma unroll
       for (int k = 0; k < 3; k++)
@@ -1296,40 +1321,41 @@ struct World2 {
     const T* __restrict__ qp = pin_g(q() + nfd);     // qpos / qvel of the sliders are read-only in this stage
     const T* __restrict__ vp = pin_g(v() + nfd);
     T Ls = 0, Lv = 0, As = 0;
-#pragma unroll 4
-    for (int e = sl; e < ns; e += LPW) {
-      const T tc = stc[e];
-      Ls += tc * qp[e]; Lv += tc * vp[e]; As += tc * stciw[e];
-    }
+    batched<8, V2<T>>(sl, ns, LPW,
+      [&](int e, V2<T>& x) SG_INL { x.a = qp[e]; x.b = vp[e]; },
+      [&](int e, const V2<T>& x) SG_INL { const T tc = stc[e]; Ls += tc * x.a; Lv += tc * x.b; As += tc * stciw[e]; });
     Ls = gsum(Ls); Lv = gsum(Lv); As = gsum(As);
     const T Ft = -ten_stiffness() * (Ls - C.ten_lspring) - ten_damping() * Lv;
     Ft_out = Ft;
     // sliders: qacc_smooth = (passive - bias) / m  (bias = -m axis.g for a slider on a static parent)
     T* __restrict__ qsp = pin_g(qs() + nfd);
-#pragma unroll 2
-    for (int e = sl; e < ns; e += LPW) {
-      const T qe = qp[e], ve = vp[e], m = tab(D.o_sl_m)[e];
-      const T* __restrict__ ax = tab(D.o_sl_axis) + 3 * e;
-      T f = -stiffness(e) * qe - damping(e) * ve;
-      f += stc[e] * Ft;
-      f -= -(m * (ax[0] * C.g[0] + ax[1] * C.g[1] + ax[2] * C.g[2]));
-      qsp[e] = f * stiw(e);
-    }
+    batched<8, V5<T>>(sl, ns, LPW,
+      [&](int e, V5<T>& x) SG_INL { x.a = qp[e]; x.b = vp[e]; x.c = tab(D.o_sl_m)[e]; x.d = stiffness(e); x.e = damping(e); },
+      [&](int e, const V5<T>& x) SG_INL {
+        const T* ax = sax + 3 * e;                         // (the CTA-shared copy of the slider axes)
+        T f = -x.d * x.a - x.e * x.b;
+        f += stc[e] * Ft;
+        f -= -(x.c * (ax[0] * C.g[0] + ax[1] * C.g[1] + ax[2] * C.g[2]));
+        qsp[e] = f * stiw(e);
+      });
     // joint-equality rows in schedule order: row2 = (aref, R) until the warm start turns aref into u
     const int* __restrict__ rd = srd;
     const T* __restrict__ siwt = pin_t(tab(D.o_sl_iw));
     T* __restrict__ row2 = hot + L.row2;
-#pragma unroll 4
-    for (int p = sl; p < D.nrow; p += LPW) {
-      const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
-      T pos = qp[d1], vel = vp[d1], diag = siwt[d1];     // (dof_invweight0 is not bit-uniform over the sliders: table loads)
-      if (d2 != 0xffff) { pos -= qp[d2]; vel -= vp[d2]; diag += siwt[d2]; }
-      const T imp = impedance2<T>(C.eqj_si, pos);
-      const T aref = -C.eqj_B * vel - C.eqj_K * imp * pos;
-      row2[2 * p] = aref;
-      row2[2 * p + 1] = tmax(T(SG_MINVAL), (T(1) - imp) * diag / imp);
-      if (dbg) { K.debug_out[K.debug_cap - (D.nrow + 1) + p] = (double)aref; K.debug_out[K.debug_cap - 2 * (D.nrow + 1) + p] = (double)row2[2 * p + 1]; }
-    }
+    batched<8, V3<T>>(sl, D.nrow, LPW,
+      [&](int p, V3<T>& x) SG_INL {
+        const int d12 = rd[p], d1 = d12 & 0xffff, d2 = (d12 >> 16) & 0xffff;
+        T pos = qp[d1], vel = vp[d1], diag = siwt[d1];     // (dof_invweight0 is not bit-uniform over the sliders: table loads)
+        if (d2 != 0xffff) { pos -= qp[d2]; vel -= vp[d2]; diag += siwt[d2]; }
+        x.a = pos; x.b = vel; x.c = diag;
+      },
+      [&](int p, const V3<T>& x) SG_INL {
+        const T imp = impedance2<T>(C.eqj_si, x.a);
+        const T aref = -C.eqj_B * x.b - C.eqj_K * imp * x.a;
+        row2[2 * p] = aref;
+        row2[2 * p + 1] = tmax(T(SG_MINVAL), (T(1) - imp) * x.c / imp);
+        if (dbg) { K.debug_out[K.debug_cap - (D.nrow + 1) + p] = (double)aref; K.debug_out[K.debug_cap - 2 * (D.nrow + 1) + p] = (double)row2[2 * p + 1]; }
+      });
     {
       const T pos = Ls - C.ten_l0;
       const T imp = impedance2<T>(C.eqt_si, pos);
@@ -1404,32 +1430,38 @@ struct World2 {
     T cost = 0;
     // equality rows: per-dof gather of J^T f over the rows of each slider (no scatter, no atomics)
     T tja = 0;
-    for (int e = sl; e < ns; e += LPW) {
-      const int* dr = dof_rows + e * MAXDOFROWS;
-      T s = 0;
+    struct RowsV { int code[MAXDOFROWS]; };
+    batched<8, RowsV>(sl, ns, LPW,
+      [&](int e, RowsV& x) SG_INL {
+        const int* dr = dof_rows + e * MAXDOFROWS;
 #pragma unroll
-      const T ae = a()[nfd + e];
-      for (int k = 0; k < MAXDOFROWS; k++) {
-        // entry (sg_api.cu host_tables): row position | other slider << 12 (0xfff: none) | "e is the second slider" << 24
-        const int code = dr[k];
-        if (code >= 0) {
-          const int p = code & 0xfff, other = (code >> 12) & 0xfff;
-          const bool second = (code >> 24) & 1;
-          const T ao = other != 0xfff ? a()[nfd + other] : T(0);
-          const T ja = second ? ao - ae : ae - ao;
-          T ar, R; ld2(row2 + 2 * p, ar, R);
-          const T f = -(T(1) / R) * (ja - ar);
-          if (second) s -= f;
-          else { s += f; cost += f * (T(0.5) * R * f - ar); }   // the row's own cost: counted once, by its first dof
+        for (int k = 0; k < MAXDOFROWS; k++) x.code[k] = dr[k];
+      },
+      [&](int e, const RowsV& x) SG_INL {
+        T s = 0;
+        const T ae = a()[nfd + e];
+#pragma unroll
+        for (int k = 0; k < MAXDOFROWS; k++) {
+          // entry (sg_api.cu host_tables): row position | other slider << 12 (0xfff: none) | "e is the second slider" << 24
+          const int code = x.code[k];
+          if (code >= 0) {
+            const int p = code & 0xfff, other = (code >> 12) & 0xfff;
+            const bool second = (code >> 24) & 1;
+            const T ao = other != 0xfff ? a()[nfd + other] : T(0);
+            const T ja = second ? ao - ae : ae - ao;
+            T ar, R; ld2(row2 + 2 * p, ar, R);
+            const T f = -(T(1) / R) * (ja - ar);
+            if (second) s -= f;
+            else { s += f; cost += f * (T(0.5) * R * f - ar); }   // the row's own cost: counted once, by its first dof
+          }
         }
-      }
-      tja += stc[e] * a()[nfd + e];
-      jtf[nfd + e] = s;
-    }
+        tja += stc[e] * ae;
+        jtf[nfd + e] = s;
+      });
     tja = gsum(tja);
     const T tf = -(T(1) / tn.R) * (tja - tn.aref);
     if (sl == 0) cost += tf * (T(0.5) * tn.R * tf - tn.aref);
-    for (int e = sl; e < ns; e += LPW) jtf[nfd + e] += stc[e] * tf;
+    batched<8, V1<T>>(sl, ns, LPW, [&](int e, V1<T>& x) SG_INL { x.a = jtf[nfd + e]; }, [&](int e, const V1<T>& x) SG_INL { jtf[nfd + e] = x.a + stc[e] * tf; });
     // limits (the chain lanes)
     if (sl < D.nchain) {
       const int d0 = D.chain_dof0[sl];
@@ -1514,7 +1546,8 @@ struct World2 {
     }
     __syncwarp();
     // (J^T f).qacc_smooth + 0.5 (J^T f)' M^-1 (J^T f)
-    for (int e = sl; e < ns; e += LPW) { const T x = jtf[nfd + e]; cost += x * (qs()[nfd + e] + T(0.5) * x * stiw(e)); }
+    batched<8, V2<T>>(sl, ns, LPW, [&](int e, V2<T>& x) SG_INL { x.a = jtf[nfd + e]; x.b = qs()[nfd + e]; },
+                      [&](int e, const V2<T>& x) SG_INL { cost += x.a * (x.b + T(0.5) * x.a * stiw(e)); });
     for (int dof = sl; dof < nfd; dof += LPW) {
       const int c = chain_of(dof), jl = dof - D.chain_dof0[c];
       T s = 0;
@@ -1547,7 +1580,8 @@ struct World2 {
     }
     __syncwarp();
     // a = qacc_smooth + M^-1 jtf (or qacc_smooth alone)
-    for (int e = sl; e < ns; e += LPW) a()[nfd + e] = qs()[nfd + e] + (keep ? jtf[nfd + e] * stiw(e) : T(0));
+    batched<8, V2<T>>(sl, ns, LPW, [&](int e, V2<T>& x) SG_INL { x.a = qs()[nfd + e]; x.b = jtf[nfd + e]; },
+                      [&](int e, const V2<T>& x) SG_INL { a()[nfd + e] = x.a + (keep ? x.b * stiw(e) : T(0)); });
     for (int dof = sl; dof < nfd; dof += LPW) {
       const int c = chain_of(dof), jl = dof - D.chain_dof0[c];
       T s = 0;
@@ -2110,13 +2144,14 @@ struct World2 {
     {
       T* __restrict__ qp = pin_g(q() + nfd); T* __restrict__ vp = pin_g(v() + nfd);
       const T* __restrict__ ap = pin_s(a() + nfd);
-#pragma unroll 4
-      for (int e = sl; e < D.ns; e += LPW) {
-        const T m = tab(D.o_sl_m)[e];
-        const T qa = m * ap[e] / (m + h * damping(e));
-        const T vn = vp[e] + h * qa;
-        vp[e] = vn; qp[e] += h * vn;
-      }
+      struct EuV { T m, d, v, q; };
+      batched<8, EuV>(sl, D.ns, LPW,
+        [&](int e, EuV& x) SG_INL { x.m = tab(D.o_sl_m)[e]; x.d = damping(e); x.v = vp[e]; x.q = qp[e]; },
+        [&](int e, const EuV& x) SG_INL {
+          const T qa = x.m * ap[e] / (x.m + h * x.d);
+          const T vn = x.v + h * qa;
+          vp[e] = vn; qp[e] = x.q + h * vn;
+        });
     }
     for (int i = sl; i < nfd; i += LPW) { const T vn = v()[i] + h * a()[i]; v()[i] = vn; q()[i] += h * vn; }
     if (sl < D.nu) aux[L.act + sl] += h * aux[L.actdot + sl];
@@ -2128,7 +2163,8 @@ struct World2 {
   __device__ void step(bool integrate) {
     if (integrate) {
       bool badpv = false;
-      for (int i = sl; i < D.nv; i += LPW) if (!(tabs(q()[i]) <= T(SG_MAXVAL)) || !(tabs(v()[i]) <= T(SG_MAXVAL))) badpv = true;
+      batched<8, V2<T>>(sl, D.nv, LPW, [&](int i, V2<T>& x) SG_INL { x.a = q()[i]; x.b = v()[i]; },
+                        [&](int, const V2<T>& x) SG_INL { if (!(tabs(x.a) <= T(SG_MAXVAL)) || !(tabs(x.b) <= T(SG_MAXVAL))) badpv = true; });
       const bool gbad = gballot(badpv) != 0u;
       if (gbad && sl == 0) misc(M2_STATUS) |= 1;
       // reset_if contains a warp collective: every group goes through it, only the bad ones write

@@ -30,6 +30,9 @@ for cfg in cfgs:
     # r0: contact records read from the scratch instead of the shared-memory ring
     if "r" in parts: os.environ["SOFTGRIP_RING"] = str(parts["r"])
     else: os.environ.pop("SOFTGRIP_RING", None)
+    # g0: rows_and_smooth gathers the slider state from the scratch instead of its shared-memory copy
+    if "g" in parts: os.environ["SOFTGRIP_STAGE"] = str(parts["g"])
+    else: os.environ.pop("SOFTGRIP_STAGE", None)
     if "n" in parts: os.environ["SOFTGRIP_NW"] = str(parts["n"])
     else: os.environ.pop("SOFTGRIP_NW", None)
     dm = batched.DeviceModel(blob)

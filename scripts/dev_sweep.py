@@ -33,6 +33,9 @@ for cfg in cfgs:
     # g0: rows_and_smooth gathers the slider state from the scratch instead of its shared-memory copy
     if "g" in parts: os.environ["SOFTGRIP_STAGE"] = str(parts["g"])
     else: os.environ.pop("SOFTGRIP_STAGE", None)
+    # d0: fixed shares of the world batches per persistent CTA instead of the dynamic hand-out
+    if "d" in parts: os.environ["SOFTGRIP_DYNAMIC"] = str(parts["d"])
+    else: os.environ.pop("SOFTGRIP_DYNAMIC", None)
     if "n" in parts: os.environ["SOFTGRIP_NW"] = str(parts["n"])
     else: os.environ.pop("SOFTGRIP_NW", None)
     dm = batched.DeviceModel(blob)

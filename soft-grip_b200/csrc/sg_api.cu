@@ -57,6 +57,7 @@ struct sg_batch {
   long long launches = 0;
   int traj_soa = 0;           // trajectory layout of sg_batch_rollout: 0 = [W][T][C], 1 = [T][C][W]
   unsigned long long* prof = nullptr; size_t prof_n = 0;   // SOFTGRIP_PROF=1: phase clocks of kernel 2 (development aid)
+  int* batch_counter = nullptr;     // KArgs2::batch_counter (dynamic hand-out of world batches to the persistent CTAs)
   int max_ctas = 0, per_sm = 0;
 };
 
@@ -338,6 +339,7 @@ static int batch_create_body(const sg_model* m, int nworlds, int device, int pre
         CUDA_OK(cudaMemset(b->prof, 0, sizeof(unsigned long long) * b->prof_n));
       }
     }
+    CUDA_OK(cudaMalloc((void**)&b->batch_counter, sizeof(int)));
     if (!aux_in_smem) {
       CUDA_OK(cudaMalloc((void**)&b->scratch, (size_t)slots * cta_worlds * (size_t)b->L2.gs_stride));
       CUDA_OK(cudaMemset(b->scratch, 0, (size_t)slots * cta_worlds * (size_t)b->L2.gs_stride));
@@ -350,7 +352,7 @@ extern "C" void sg_batch_destroy(sg_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   void* ptrs[] = {b->tab, b->itab, b->qpos, b->qvel, b->warm, b->act, b->ctrl, b->status, b->p_stiff, b->p_damp, b->p_tdamp,
-                  b->p_objoff, b->d_ctrl_event, b->d_ctrl_value, b->debug_out, b->stage_traj, b->stage_touch, b->scratch, b->prof};
+                  b->p_objoff, b->d_ctrl_event, b->d_ctrl_value, b->debug_out, b->stage_traj, b->stage_touch, b->scratch, b->prof, b->batch_counter};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete b;
 }
@@ -490,7 +492,16 @@ static int launch_v2(sg_batch* b, const LaunchSpec& sp, cudaStream_t s) {
   K.ctrl_event = b->d_ctrl_event; K.ctrl_value = b->d_ctrl_value;
   const int cta_worlds = (32 / b->lpw) * b->nwarp;
   int grid = (b->W + cta_worlds - 1) / cta_worlds;
-  if (grid > b->max_ctas) grid = b->max_ctas;   // persistent: each CTA walks its batches of worlds
+  K.batch_counter = nullptr;
+  if (grid > b->max_ctas) {
+    grid = b->max_ctas;   // persistent: each CTA walks batches of worlds, handed out by a counter (SOFTGRIP_DYNAMIC=0: fixed shares)
+    bool dyn = true;
+    if (const char* de = std::getenv("SOFTGRIP_DYNAMIC")) dyn = std::atoi(de) != 0;
+    if (dyn && b->batch_counter) {
+      CUDA_OK(cudaMemsetAsync(b->batch_counter, 0, sizeof(int), s));
+      K.batch_counter = b->batch_counter;
+    }
+  }
   int e = k2_dispatch_launch<T>(b->lpw, K, grid, 32 * b->nwarp, b->smem2, (void*)s);
   if (e) return fail(std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)e));
   return 0;

@@ -202,6 +202,8 @@ struct KArgs2 {
   int tm_stride;               // columns per warp: warp w owns [tm_stride (w / 4), +tm_stride) of its lane quarter
   int rec_ring;                // 1: contact records reach the chain phase through a two-entry shared-memory ring per lane (needs tm_cols)
   unsigned char* scratch;      // global aux slots [gridDim.x * WPW][L.gs_stride] (null when aux_in_smem)
+  int* batch_counter;          // persistent CTAs take their batches of worlds from this counter (zeroed before the launch);
+                               // null: batch i of CTA c is i * gridDim.x + c
   // state, world-major
   T *qpos, *qvel, *warm, *act, *ctrl;
   const double *p_stiff, *p_damp, *p_tdamp, *p_objoff;
@@ -2310,7 +2312,22 @@ __global__ void __launch_bounds__(32 * SG_MAX_WARPS, SG_MIN_CTAS) sg_step_kernel
   if (K.prof && lane == 0) K.prof[PH_COUNT + (size_t)blockIdx.x * nwarp + warp] = clock64();
 #endif
   const int cta_worlds = nwarp * WPW;
-  for (int b0 = blockIdx.x * cta_worlds; b0 < K.nworlds; b0 += gridDim.x * cta_worlds) {
+  // Persistent CTAs.  Episodes differ in length of their contact phase, so the batches are handed out dynamically: a CTA
+  // that finishes early takes the next batch instead of idling behind a fixed share (65 536 worlds are 6.9 batches per
+  // CTA).  Which CTA simulates a world does not enter its arithmetic: results are identical to the static order.
+#if defined(__CUDA_ARCH__)
+  __shared__ int next_batch_s;
+#else
+  static int next_batch_s;
+#endif
+  for (int it = 0;; it++) {
+    if (K.batch_counter) {
+      if (threadIdx.x == 0) next_batch_s = atomicAdd(K.batch_counter, 1);
+      __syncthreads();
+    }
+    const int b0 = (K.batch_counter ? next_batch_s : it * (int)gridDim.x + (int)blockIdx.x) * cta_worlds;
+    if (K.batch_counter) __syncthreads();          // everybody has read the batch before thread 0 fetches the next one
+    if (b0 >= K.nworlds) break;
     const int wi = b0 + warp * WPW + grp;
     const bool valid = wi < K.nworlds;
     World2<T, LPW> W(K, smem_raw, valid ? wi : K.nworlds - 1, valid);

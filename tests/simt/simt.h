@@ -243,5 +243,6 @@ inline void simt_tm_st(unsigned ta, int n, const unsigned* in) {
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }
 inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
+inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 template <typename T> inline T __ldg(const T* p) { return *p; }

@@ -23,9 +23,14 @@
 // collide() as scratch.  Everything that is touched once per step ("aux": qpos, qvel, smooth forces, contact
 // records) lives in an L2-resident global scratch slot of the group.
 //
-// No tensor cores: nothing here is a dense contraction (largest dense objects: 4x4 finger inertia blocks,
+// No tensor-core math: nothing here is a dense contraction (largest dense objects: 4x4 finger inertia blocks,
 // 3x3 contact blocks).  The kernel is bound by issue slots / dependent-issue latency of the Gauss-Seidel
 // sweep; sub-warp worlds raise the useful lanes per issued instruction, small hot state raises resident warps.
+// The tensor cores' memory is used, though (KArgs2::tm_cols, when every resident CTA of an SM gets its window): during
+// the solve the (u, n) pairs live in tensor memory, one TMEM lane per thread (tcgen05.ld / st, see tm_ld2), and the
+// shared-memory region they leave free holds a two-entry ring of contact records per lane, filled by cp.async one
+// contact block ahead (chain_phase<RING>).  Without the window the pairs stay in shared memory and the records are read
+// from the scratch; both paths compute the same bits (tests/test_simt.py, tests/test_gpu.py).
 #pragma once
 #include <stdint.h>
 
@@ -35,8 +40,9 @@
 namespace sg {
 
 
-// how many blocks ahead a chain lane prefetches its contact records into L1.  The L1 left beside 228 KB of shared memory
-// is 28 KB; 16 warps x 8 lanes x 128 B are 16 KB of records in flight per block of look-ahead.
+// how many blocks ahead a chain lane prefetches its contact records into L1 when the shared-memory record ring is not in
+// use.  The L1 left beside 228 KB of shared memory is 28 KB; 16 warps x 8 lanes x 128 B are 16 KB of records in flight
+// per block of look-ahead -- which is why the prefetch does not hold and the ring exists (see chain_phase).
 #ifndef SG_PF_DIST
 #define SG_PF_DIST 2      // 1 and 2 measure the same (profiles/r02o_sweep.log: 1.216e7 / 1.223e7)
 #endif

@@ -192,6 +192,34 @@ def test_emulated_tensor_memory_rows_and_record_ring_are_bit_identical(emu, stat
         np.testing.assert_array_equal(it0, it1)
 
 
+def test_emulated_dynamic_batch_hand_out_equals_fixed_shares(emu, states, monkeypatch):
+    """More worlds than resident CTA slots: the persistent CTAs take their batches of worlds from a counter (default) or in
+    fixed shares (SOFTGRIP_DYNAMIC=0).  Which CTA simulates a world does not enter its arithmetic: the two orders give
+    the same bits, every world is simulated exactly once, and identical inputs give identical outputs in every batch.
+    (The emulator's device has two SMs; one-warp CTAs of four worlds leave 18 resident slots.)"""
+    W = 4 * 18 * 2 + 3
+    i = int(np.argmax(states["ncon1"]))
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SOFTGRIP_DYNAMIC", mode)
+        monkeypatch.setenv("SOFTGRIP_TMEM", "1")
+        env = emu.EmuBatch(blob_path("softbox"), W, prec=32, lpw=8, nw=1)
+        k = np.full(W, 700.0); k[5] = 450.0; k[W - 2] = 1200.0
+        env.set_params(stiffness=k)
+        env.set_state(states["q"][i], states["v"][i], states["act"][i], states["warm"][i])
+        env.set_ctrl([states["ctrl"][i]] * 2)
+        sens, touch = env.step(2)
+        out[mode] = (sens.copy(), [x.copy() for x in env.get_state()])
+        assert (env.status() == 0).all()
+        env.close()
+    np.testing.assert_array_equal(out["0"][0], out["1"][0])
+    for x, y in zip(out["0"][1], out["1"][1]):
+        np.testing.assert_array_equal(x, y)
+    s = out["1"][0]
+    same = [w for w in range(W) if w not in (5, W - 2)]
+    assert (s[same] == s[0]).all() and not (s[5] == s[0]).all() and not (s[W - 2] == s[0]).all()
+
+
 @pytest.mark.parametrize("W,nw", [(4, None), (18, 4)])
 def test_emulated_divergence_is_contained_in_its_group(emu, W, nw):
     """A diverging world is reset and flagged; the other worlds of the same warp / CTA are bit-identical to a

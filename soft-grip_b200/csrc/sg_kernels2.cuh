@@ -343,16 +343,19 @@ template <typename T> __device__ __forceinline__ void tm_wait_ld(T&, T&) {}
 __device__ __forceinline__ void tm_wait_st() {}
 #endif
 
-// asynchronous copy of one contact record (NB bytes, 16-byte pieces) from the global scratch into shared memory: no
-// registers are held while the record is on its way from L2 (cp.async.cg: straight from L2, which is where the record's
-// force words were last written)
+// ---- the record ring of the chain phase ---------------------------------------------------------------------------
+// cp_rec: asynchronous copy of one contact record (NB bytes, 16-byte pieces) from the global scratch into shared memory.
+// No registers are held while the record is on its way from L2 (cp.async.cg: straight from L2, which is where the
+// record's force words were last written); cp_wait: the lane's copies have landed.
+// The ring is addressed through its 32-bit shared-window address, pinned in a register (see keep_off): with a generic
+// pointer ptxas rebuilds the window base (S2UR CgaCtaId, ULEA ..) and the lane's offset in every block.  The explicit
+// ld.shared statements are volatile, i.e. they stay behind the cp_wait that precedes them; every other access to the
+// region is separated from them by a warp barrier.
 __device__ __forceinline__ void cp_wait() {
 #if defined(__CUDA_ARCH__)
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
 }
-// The ring is addressed through its 32-bit shared-window address, pinned in a register (see keep_off): with a generic
-// pointer ptxas rebuilds the window base (S2UR CgaCtaId, ULEA ..) and the lane's offset in every block.
 #if defined(__CUDA_ARCH__)
 typedef unsigned ring_t;
 __device__ __forceinline__ ring_t ring_of(unsigned char* p) { return (unsigned)keep_off((int)__cvta_generic_to_shared(p)); }

@@ -116,3 +116,23 @@ def test_integration_doc_maps_every_entry_point():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     missing = [s for s in declared_symbols() if s not in doc]
     assert not missing, missing
+
+
+def test_step_kernel_carries_the_tensor_memory_and_ring_instructions(libpath):
+    """The in-tree library's fp32 8-lane step kernel was compiled for sm_100a with the equality rows in tensor memory
+    (LDTM / STTM, allocation by UTCATOMSWS) and the contact-record ring (LDGSTS + LDGDEPBAR), and without tensor-core
+    math (the path has no dense contraction to offer).  Skipped without cuobjdump."""
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    listing = subprocess.run([cuobjdump, "-lelf", libpath], capture_output=True, text=True).stdout
+    assert "sm_100a" in listing, listing[:300]
+    sass = subprocess.run([cuobjdump, "-sass", libpath], capture_output=True, text=True).stdout
+    i = sass.find("Function : _ZN2sg15sg_step_kernel2IfLi8EEEvNS_6KArgs2IT_EE")
+    assert i >= 0
+    j = sass.find("Function :", i + 10)
+    body = sass[i:j if j > 0 else len(sass)]
+    for mnemonic in ("LDTM", "STTM", "UTCATOMSWS", "LDGSTS", "LDGDEPBAR"):
+        assert mnemonic in body, mnemonic
+    assert not re.search(r"\b(HMMA|UTCHMMA|UTCQMMA|UTCIMMA)\b", body)

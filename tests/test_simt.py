@@ -192,6 +192,29 @@ def test_emulated_tensor_memory_rows_and_record_ring_are_bit_identical(emu, stat
         np.testing.assert_array_equal(it0, it1)
 
 
+@pytest.mark.parametrize("name,prec,lpw", [("softball", 32, 8), ("softcylinder", 64, 8), ("softbox_refined", 32, 32)])
+def test_emulated_tensor_memory_rows_on_the_other_models(emu, batched, monkeypatch, name, prec, lpw):
+    """The other shells (other row counts and sweep schedules; the refined composite at 32 lanes per world, where the
+    window is 2 columns x (steps + 1) of a single column block and the record ring does not fit) through a short episode
+    with the rows in tensor memory and in shared memory: same bits."""
+    sched = batched.default_schedule(2, n_settle=1, n_iter=1, open_close_div=1)
+    W = 32 // lpw + 1
+    out = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SOFTGRIP_TMEM", mode)
+        env = emu.EmuBatch(blob_path(name), W, prec=prec, lpw=lpw)
+        tm = env.debug("tensor_memory")
+        assert (tm[0] > 0) == (mode == "1") and tm[0] <= 512
+        env.set_params(stiffness=np.linspace(500.0, 900.0, W))
+        traj, touch, st = env.rollout(sched)
+        assert np.isfinite(traj).all() and np.abs(traj).max() > 0
+        out.append((traj.copy(), [x.copy() for x in env.get_state()]))
+        env.close()
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    for x, y in zip(out[0][1], out[1][1]):
+        np.testing.assert_array_equal(x, y)
+
+
 def test_emulated_dynamic_batch_hand_out_equals_fixed_shares(emu, states, monkeypatch):
     """More worlds than resident CTA slots: the persistent CTAs take their batches of worlds from a counter (default) or in
     fixed shares (SOFTGRIP_DYNAMIC=0).  Which CTA simulates a world does not enter its arithmetic: the two orders give

@@ -336,7 +336,15 @@ class BatchedManEnv:
         out = (C.c_int * 8)()
         check(self.L.sg_batch_config(self.h, out))
         keys = ("lanes_per_world", "warps_per_cta", "worlds_per_cta", "ctas_per_sm", "smem_per_cta", "smem_per_world", "team_mode", "kernel")
-        return dict(zip(keys, [int(x) for x in out]))
+        cfg = dict(zip(keys, [int(x) for x in out]))
+        try:
+            # where the equality rows and the contact records live during the solve
+            tm = self.debug(0, "tensor_memory")
+            cfg["tensor_memory_columns"] = int(tm[0])
+            cfg["record_ring"] = int(tm[2])
+        except Exception:  # noqa: BLE001 -- diagnostics only
+            pass
+        return cfg
 
     PHASES = ("gripper", "collide", "rows", "warmstart", "pgs_setup", "pgs_equality", "pgs_chain", "sensors", "euler", "other")
 

@@ -30,6 +30,11 @@ struct WarpState {
   int gen = 0;
   bool finished = false, at_cta_barrier = false;
   int named_id = -1, named_warps = 0;     // waiting at bar.sync id, nthreads (a subset of the CTA's warps)
+  // tensor-memory accesses since the warp's last collective, per lane: count and rolling hash of (kind, address).  The
+  // instructions are warp-collective with a uniform address; each lane only touches its own TMEM lane, so the emulator
+  // executes them lane by lane and compares the logs at the next rendezvous instead of paying one per access.
+  unsigned tm_n[32] = {0};
+  unsigned long long tm_hash[32] = {0};
 };
 constexpr int MAX_WARPS = 32;
 struct CtaState {
@@ -76,6 +81,13 @@ inline void run_round(int wi) {
     swapcontext(&CTA.sched, &W.ctx[l]);
     if (W.done[l]) ndone++;
   }
+  for (int l = 1; l < 32; l++)
+    if (W.tm_n[l] != W.tm_n[0] || W.tm_hash[l] != W.tm_hash[0]) {
+      fprintf(stderr, "simt: tensor-memory accesses differ between lane 0 (%u) and lane %d (%u) of warp %d since the last collective (not warp-uniform)\n",
+              W.tm_n[0], l, W.tm_n[l], wi);
+      abort();
+    }
+  for (int l = 0; l < 32; l++) { W.tm_n[l] = 0; W.tm_hash[l] = 0; }
   if (ndone == 32) { W.finished = true; return; }
   if (ndone != 0) { fprintf(stderr, "simt: %d lanes of warp %d exited while others wait at a collective\n", ndone, wi); abort(); }
   const int g = W.gen & 1;
@@ -93,6 +105,7 @@ inline void run_cta() {
   for (int wi = 0; wi < CTA.nwarps; wi++) {
     WarpState& W = CTA.warp[wi];
     W.gen = 0; W.finished = false; W.at_cta_barrier = false; W.named_id = -1;
+    for (int l = 0; l < 32; l++) { W.tm_n[l] = 0; W.tm_hash[l] = 0; }
     for (int l = 0; l < 32; l++) {
       if (!W.stack[l]) W.stack[l] = (char*)malloc(STACK_BYTES);
       getcontext(&W.ctx[l]);
@@ -222,12 +235,13 @@ inline int __reduce_max_sync(unsigned, int v) {
 }
 // tensor memory in the 32x32b access shape (tcgen05.ld / tcgen05.st): [128 lanes][512 columns] of 32-bit words per CTA; a thread
 // of warp w owns lane 32 (w % 4) + its lane id.  The instructions are warp-collective with a warp-uniform address: the
-// emulator makes them a rendezvous and aborts on a non-uniform address, a lane quarter that is not the warp's, or a column
-// past the end.
+// emulator aborts on a lane quarter that is not the warp's or a column past the end at once, and on accesses that are
+// not uniform over the warp at the warp's next collective (see WarpState::tm_hash).
 inline void simt_tm_check(unsigned ta, int n, int site) {
-  const int g = simt::rendezvous(ta, site);
-  for (int l = 0; l < 32; l++)
-    if ((unsigned)simt::cur_warp().slot[g & 1][l] != ta) { fprintf(stderr, "simt: tensor-memory access with a non-uniform address\n"); abort(); }
+  simt::WarpState& W = simt::cur_warp();
+  const int lane = simt::cur_lane();
+  W.tm_n[lane]++;
+  W.tm_hash[lane] = W.tm_hash[lane] * 1000003ull + (((unsigned long long)(site * 16 + n)) << 32 | ta);     // compared at the next rendezvous
   const unsigned lane0 = ta >> 16, col = ta & 0xffffu;
   if (lane0 != 32u * (unsigned)(simt::CTA.cur_warp & 3)) { fprintf(stderr, "simt: warp %d accesses tensor-memory lanes %u..\n", simt::CTA.cur_warp, lane0); abort(); }
   if (col + (unsigned)n > 512u) { fprintf(stderr, "simt: tensor-memory column %u + %d out of range\n", col, n); abort(); }

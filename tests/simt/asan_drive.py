@@ -24,7 +24,13 @@ def rel(a, b):
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(1e-12, np.abs(b).max()))
 
 
-for prec, lpw, nw in ((32, 8, None), (64, 8, 4), (32, 16, None), (64, 32, None), (32, 4, 2)):
+# (the last column forces the equality rows into tensor memory and the contact records through the shared-memory ring, or
+# keeps both off; the driver's default decides otherwise)
+for prec, lpw, nw, tmem in ((32, 8, None, "1"), (32, 8, None, "0"), (64, 8, 4, "1"), (32, 16, None, None), (64, 32, None, "1"), (32, 4, 2, None)):
+    if tmem is None:
+        os.environ.pop("SOFTGRIP_TMEM", None)
+    else:
+        os.environ["SOFTGRIP_TMEM"] = tmem
     W = 32 // lpw + 1 if nw is None else 19
     env = emu.EmuBatch(os.path.join(golden, "softbox.sgm"), W, prec=prec, lpw=lpw, nw=nw)
     env.set_params(stiffness=np.full(W, 700.0))
@@ -37,6 +43,7 @@ for prec, lpw, nw in ((32, 8, None), (64, 8, 4), (32, 16, None), (64, 32, None),
     traj, touch, status = env.rollout(batched.default_schedule(2, n_settle=1, n_iter=3, open_close_div=2))
     assert np.isfinite(traj).all()
     env.close()
+os.environ["SOFTGRIP_TMEM"] = "1"
 for name, lpw, td in (("softbox_refined", 32, 20.0), ("softball", 8, 50.0), ("softcylinder", 16, 50.0)):
     env = emu.EmuBatch(os.path.join(golden, name + ".sgm"), 2, prec=32, lpw=lpw)
     env.set_params(stiffness=np.full(2, 700.0), tdamping=np.full(2, td))

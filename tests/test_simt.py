@@ -152,7 +152,7 @@ def test_emulated_multi_warp_cta_and_persistent_batches(emu, batched):
     assert np.abs(out[0] - out[2]).max() / np.abs(out[0]).max() < 1e-4      # other lane count: other summation order
 
 
-@pytest.mark.parametrize("prec,lpw,nw", [(32, 8, 2), (64, 8, 5), (32, 32, 1), (32, 4, 2)])
+@pytest.mark.parametrize("prec,lpw,nw", [(32, 8, 2), (64, 8, 5), (32, 32, 1), (32, 4, 2), (64, 16, 3)])
 def test_emulated_tensor_memory_rows_and_record_ring_are_bit_identical(emu, states, monkeypatch, prec, lpw, nw):
     """The equality rows in tensor memory (tcgen05.ld / st, one TMEM lane per thread) and the contact records read through
     the per-lane shared-memory ring compute the same bits as the rows in shared memory and the records read from the

@@ -1696,6 +1696,16 @@ struct World2 {
 #pragma unroll
     for (int ii = 0; ii < MAXCD; ii++) ld4(mv + 4 * ii, m16 + 4 * ii);
 #endif
+#if defined(SG_FRIC_STATS) && !defined(__CUDA_ARCH__)
+    {
+      // development statistics under the emulator: how many blocks are no-ops (an inactive contact that stays inactive)
+      static long nblk = 0, nstay = 0, nactive = 0;
+      nblk++;
+      if (!active && !(f0 > T(0))) nstay++;
+      if (active) nactive++;
+      if ((nblk & 0xfffff) == 0) fprintf(stderr, "contact_block: %ld blocks, %.3f inactive and staying inactive, %.3f active on entry\n", nblk, (double)nstay / nblk, (double)nactive / nblk);
+    }
+#endif
     // cost change, revert if positive
     T d0f = f0 - old0, d1f = f1 - old1, d2f = f2 - old2;
     T change = T(0.5) * (d0f * (A00 * d0f + A01 * d1f + A02 * d2f) + d1f * (A01 * d0f + A11 * d1f + A12 * d2f) + d2f * (A02 * d0f + A12 * d1f + A22 * d2f))

@@ -1778,8 +1778,8 @@ struct World2 {
   }
   // one sweep over this lane's limit rows and contact blocks (time slots 1..tmaxw, a warp barrier after each);
   // returns the lane's cost improvement.  The contact records live in the L2-resident scratch: the lane's schedule
-  // entries are fetched three blocks ahead (registers) and the 128-byte record of a later block is prefetched into
-  // L1 when the current block starts, so that no block waits for two dependent L2 round trips.  (Measured neutral
+  // entries are fetched three blocks ahead (registers); without the ring (!RING) the 128-byte record of a later block is
+  // prefetched into L1 when the current block starts.  (Measured neutral
   // or worse and removed again: records staged in registers one block ahead -- 1.1 KB of spills, -12 %; helper lanes
   // handing records over by shuffles, round 1; a reordered friction solve and a speculative M^-1 J' update -- the chain
   // phase sits where issue slots (4 warps x ~120 000 instructions per step) and single-warp latency (~540 000 cycles) meet.)

@@ -136,8 +136,12 @@ int sg_batch_sync(sg_batch* b, void* stream);
 /* diagnostics of the last physics step of one world (synchronous, host fp64): key is one of
  * "qacc","qacc_smooth","ncon","nefc","solver_iter","con_dist","con_pos","con_frame","efc_force",
  * "efc_aref","efc_R"; "sweep_schedule" / "pair_runs" return the host-side step tables of the equality sweep / the
- * candidate pair list and its run-length form instead (layouts in sg_api.cu).  Returns the element count (<0 on error); writes at most cap values.
- * Only valid after sg_batch_set_debug_world(b, w) and a subsequent step/forward. */
+ * candidate pair list and its run-length form instead (layouts in sg_api.cu); "tensor_memory" returns how the launch
+ * geometry of this batch stores the solver's working set: [tensor-memory columns per CTA (0: equality rows in shared
+ * memory), columns per warp, 1 if the contact records go through the shared-memory ring].
+ * Returns the element count (<0 on error); writes at most cap values.
+ * The per-step keys are only valid after sg_batch_set_debug_world(b, w) and a subsequent step/forward; the table keys
+ * ("sweep_schedule", "pair_runs", "tensor_memory") at any time. */
 int sg_batch_set_debug_world(sg_batch* b, int world);
 int sg_batch_debug_get(sg_batch* b, const char* key, double* out, int cap);
 
